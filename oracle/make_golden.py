@@ -1,0 +1,174 @@
+"""Generate tests/golden/*.pt by running the REAL reference (imported from /root/reference,
+see ref_loader.py) on CPU with fixed seeds.  Build-container only; commit the outputs.
+
+    python oracle/make_golden.py
+
+Every tensor below that is named ``out*``/``logits`` was produced by a reference function body
+executing unmodified: selective_scan_ref (selective_scan_interface.py:86-152),
+mamba_inner_ref (:636-670), bimamba_inner_ref (:673-709), rms_norm_ref (layernorm.py:35-48),
+Mamba.forward (mamba_simple.py:169-311) and AudioMamba.forward (src/models/mamba_models.py:678-685).
+"""
+from __future__ import annotations
+
+import contextlib
+import io
+import os
+import sys
+
+import torch
+
+HERE = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, HERE)
+import ref_loader  # noqa: E402
+
+OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+SEED = 3949  # the reference's experiment seed (src/run.py:28-30)
+
+
+def _perturb(module, g, scale=0.1):
+    """Move parameters off their structured init (A=-(1..N), D=1, norm weight=1, zero biases) so the
+    fixtures exercise general values; the forward that produces the outputs is still the reference's."""
+    with torch.no_grad():
+        for name, p in module.named_parameters():
+            if name.endswith(("A_log", "A_b_log")):
+                p.add_(scale * torch.randn(p.shape, generator=g))
+            elif name.endswith((".D", ".D_b")) or name in ("D", "D_b"):
+                p.add_(scale * torch.randn(p.shape, generator=g))
+            elif name.endswith("norm.weight") or name == "norm_f.weight":
+                p.add_(0.5 * scale * torch.randn(p.shape, generator=g))
+            elif name.endswith(("patch_embed.proj.bias", "head.bias")):
+                p.add_(0.2 * scale * torch.randn(p.shape, generator=g))
+
+
+def scan_cases(ns):
+    g = torch.Generator().manual_seed(SEED)
+    cases = {}
+
+    def mk(name, Bsz, D, N, L, has_z=True, has_D=True, has_bias=True, softplus=True, bc_dim=3, last=False):
+        u = torch.randn(Bsz, D, L, generator=g)
+        delta = 0.5 * torch.randn(Bsz, D, L, generator=g)
+        if not softplus:
+            delta = delta.abs() * 0.2
+        A = -torch.exp(torch.log(torch.arange(1, N + 1, dtype=torch.float32)).repeat(D, 1)
+                       + 0.1 * torch.randn(D, N, generator=g))
+        shape = (Bsz, N, L) if bc_dim == 3 else (Bsz, 1, N, L)
+        Bm = torch.randn(shape, generator=g)
+        Cm = torch.randn(shape, generator=g)
+        Dv = (1 + 0.1 * torch.randn(D, generator=g)) if has_D else None
+        z = torch.randn(Bsz, D, L, generator=g) if has_z else None
+        bias = (0.5 * torch.randn(D, generator=g) - 2.0) if has_bias else None
+        res = ns.ssi.selective_scan_ref(u, delta, A, Bm, Cm, Dv, z, bias, softplus, last)
+        c = dict(u=u, delta=delta, A=A, B=Bm, C=Cm, D=Dv, z=z, delta_bias=bias,
+                 delta_softplus=softplus, return_last_state=last)
+        if last:
+            c["out"], c["last_state"] = res
+        else:
+            c["out"] = res
+        cases[name] = c
+
+    mk("cfg1_scan", 2, 384, 16, 64)                                   # BASELINE config 1 scan shape
+    mk("full_opts_odd_L", 2, 32, 16, 37)
+    mk("plain_no_z_no_D", 1, 16, 16, 20, has_z=False, has_D=False, has_bias=False, softplus=False,
+       bc_dim=4, last=True)
+    mk("len1", 2, 8, 16, 1)
+    mk("dstate8", 1, 16, 8, 19, bc_dim=4)
+    return cases
+
+
+def inner_cases(ns):
+    g = torch.Generator().manual_seed(SEED + 1)
+    Bsz, Dm, L, N, W = 2, 192, 64, 16, 4          # BASELINE config 1: d_model=192, d_state=16, L=64
+    torch.manual_seed(SEED)
+    with contextlib.redirect_stdout(io.StringIO()):
+        m = ns.Mamba(Dm, bimamba_type="v1")
+    _perturb(m, g)
+    Di = m.d_inner
+    xz = torch.randn(Bsz, 2 * Di, L, generator=g)
+    A = -torch.exp(m.A_log.detach().float())
+    A_b = -torch.exp(m.A_b_log.detach().float())
+    out_bias = 0.1 * torch.randn(Dm, generator=g)
+    args = (xz, m.conv1d.weight.detach(), m.conv1d.bias.detach(), m.x_proj.weight.detach(),
+            m.dt_proj.weight.detach(), m.out_proj.weight.detach())
+    with torch.no_grad():
+        out_bi = ns.ssi.bimamba_inner_ref(*args, None, A, A_b, None, None, m.D.detach().float(),
+                                          delta_bias=m.dt_proj.bias.detach().float(), delta_softplus=True)
+        out_bi_bias = ns.ssi.bimamba_inner_ref(*args, out_bias, A, A_b, None, None, m.D.detach().float(),
+                                               delta_bias=m.dt_proj.bias.detach().float(), delta_softplus=True)
+        out_uni = ns.ssi.mamba_inner_ref(*args, None, A, None, None, m.D.detach().float(),
+                                         delta_bias=m.dt_proj.bias.detach().float(), delta_softplus=True)
+    return dict(xz=xz, conv1d_weight=args[1], conv1d_bias=args[2], x_proj_weight=args[3],
+                delta_proj_weight=args[4], out_proj_weight=args[5], out_proj_bias=out_bias,
+                A=A, A_b=A_b, D=m.D.detach().float(), delta_bias=m.dt_proj.bias.detach().float(),
+                out_bimamba=out_bi, out_bimamba_bias=out_bi_bias, out_mamba=out_uni)
+
+
+def module_cases(ns):
+    cases = {}
+    g = torch.Generator().manual_seed(SEED + 2)
+    for name, kw, Dm, L in (
+        ("v1", dict(bimamba_type="v1"), 64, 33),
+        ("v2_divide", dict(bimamba_type="v2", if_devide_out=True), 64, 33),
+        ("v2_nodivide", dict(bimamba_type="v2", if_devide_out=False), 48, 16),
+        ("none", dict(bimamba_type="none"), 64, 21),
+        ("v1_gamma_bias", dict(bimamba_type="v1", init_layer_scale=0.5, bias=True), 32, 9),
+    ):
+        torch.manual_seed(SEED + len(cases))
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = ns.Mamba(Dm, **kw)
+        _perturb(m, g)
+        m.eval()
+        h = torch.randn(2, L, Dm, generator=g)
+        with torch.no_grad():
+            out = m(h)
+        cases[name] = dict(kwargs=kw, d_model=Dm, hidden=h, out=out,
+                           state={k: v.clone() for k, v in m.state_dict().items()})
+    return cases
+
+
+def norm_cases(ns):
+    g = torch.Generator().manual_seed(SEED + 3)
+    x = torch.randn(3, 7, 96, generator=g)
+    r = torch.randn(3, 7, 96, generator=g)
+    w = 1 + 0.1 * torch.randn(96, generator=g)
+    out, res = ns.ln.rms_norm_ref(x, w, None, residual=r, eps=1e-5, prenorm=True, upcast=True)
+    out0 = ns.ln.rms_norm_ref(x, w, None, residual=None, eps=1e-5, prenorm=False, upcast=True)
+    return dict(x=x, residual=r, weight=w, eps=1e-5, out=out, residual_out=res, out_nores=out0)
+
+
+def model_cases(ns):
+    cases = {}
+    g = torch.Generator().manual_seed(SEED + 4)
+    for name, kw in (
+        ("fobi_tiny", dict(spectrogram_size=(128, 128), depth=2, embed_dim=96, bimamba_type="v1", num_classes=35)),
+        ("bibi_tiny", dict(spectrogram_size=(128, 96), depth=2, embed_dim=64, bimamba_type="v2", num_classes=10)),
+        ("fofo_tiny", dict(spectrogram_size=(128, 64), depth=1, embed_dim=64, bimamba_type="none", num_classes=5)),
+    ):
+        torch.manual_seed(SEED)
+        with contextlib.redirect_stdout(io.StringIO()):
+            m = ns.AudioMamba(**kw)
+        _perturb(m, g)
+        m.eval()
+        F_, T_ = kw["spectrogram_size"]
+        x = 0.5 * torch.randn(2, T_, F_, generator=g)
+        with torch.no_grad():
+            logits = m(x)
+            feats = m(x, return_features=True)
+        cases[name] = dict(kwargs=kw, x=x, logits=logits, features=feats,
+                           state={k: v.clone() for k, v in m.state_dict().items()})
+    return cases
+
+
+def main():
+    os.makedirs(OUT, exist_ok=True)
+    ns = ref_loader.load_reference_model()
+    torch.save(scan_cases(ns), os.path.join(OUT, "selective_scan_ref.pt"))
+    torch.save(inner_cases(ns), os.path.join(OUT, "inner_ref_cfg1.pt"))
+    torch.save(module_cases(ns), os.path.join(OUT, "mamba_module.pt"))
+    torch.save(norm_cases(ns), os.path.join(OUT, "rms_norm_ref.pt"))
+    torch.save(model_cases(ns), os.path.join(OUT, "audio_mamba_tiny.pt"))
+    for f in sorted(os.listdir(OUT)):
+        print(f, os.path.getsize(os.path.join(OUT, f)))
+
+
+if __name__ == "__main__":
+    main()
