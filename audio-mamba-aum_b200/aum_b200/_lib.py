@@ -1,0 +1,110 @@
+"""ctypes binding of libaum_b200.so (C ABI declared in include/aum_b200.h).
+
+The product path has NO fallback: if the shared library is missing or a call fails, this raises.
+PyTorch is used for device memory and streams only.
+"""
+from __future__ import annotations
+
+import ctypes as C
+import os
+
+import torch
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "lib", "libaum_b200.so")
+
+F32, F16, BF16 = 0, 1, 2
+ACT_NONE, ACT_SOFTPLUS = 0, 1
+GEMM_AUTO, GEMM_TCGEN05, GEMM_SIMT = 0, 1, 2
+
+_DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
+
+
+class AumError(RuntimeError):
+    pass
+
+
+class ScanDir(C.Structure):
+    """struct aum_scan_dir (include/aum_b200.h)."""
+    _fields_ = [
+        ("u", C.c_void_p), ("ld_u", C.c_int64),
+        ("delta", C.c_void_p), ("ld_delta", C.c_int64), ("delta_dtype", C.c_int),
+        ("A", C.c_void_p),
+        ("Bm", C.c_void_p), ("ld_B", C.c_int64),
+        ("Cm", C.c_void_p), ("ld_C", C.c_int64),
+        ("bc_dtype", C.c_int),
+        ("D", C.c_void_p),
+        ("delta_bias", C.c_void_p),
+        ("delta_softplus", C.c_int),
+        ("last_state", C.c_void_p),
+    ]
+
+
+# symbol -> (restype, argtypes); also the list the CPU test checks the .so against the header with
+SIGNATURES = {
+    "aum_version": (C.c_int, []),
+    "aum_last_error": (C.c_char_p, []),
+    "aum_device_info": (C.c_int, [C.POINTER(C.c_int)] * 3),
+    "aum_gemm_tn": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
+                              C.c_void_p, C.c_int64, C.c_int,
+                              C.c_void_p, C.c_int64, C.c_int, C.c_int,
+                              C.c_int, C.c_int, C.c_int,
+                              C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "aum_causal_conv1d_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "aum_selective_scan_fwd": (C.c_int, [C.POINTER(ScanDir), C.POINTER(ScanDir), C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_float, C.c_void_p]),
+    "aum_add_rmsnorm_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
+                                      C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
+                                      C.c_float, C.c_void_p]),
+    "aum_transpose": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
+                                C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load (once) and return the shared library; raises if it has not been built."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise AumError(
+                f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+                "or `make -C audio-mamba-aum_b200/csrc`. There is no CPU / PyTorch fallback.")
+        L = C.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(L, name)     # AttributeError if the symbol is not exported
+            fn.restype = res
+            fn.argtypes = args
+        _lib = L
+    return _lib
+
+
+def check(rc: int, what: str):
+    if rc != 0:
+        msg = lib().aum_last_error()
+        raise AumError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+
+
+def dt(t: torch.dtype) -> int:
+    try:
+        return _DT[t]
+    except KeyError:
+        raise AumError(f"unsupported dtype {t}") from None
+
+
+def ptr(t):
+    return None if t is None else C.c_void_p(t.data_ptr())
+
+
+def stream():
+    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+
+
+def require_cuda(*tensors):
+    for t in tensors:
+        if t is not None and not t.is_cuda:
+            raise AumError("aum_b200 ops need CUDA tensors (there is no CPU fallback)")

@@ -1,0 +1,157 @@
+"""Host-side orchestration of one Mamba mixer block on the B200 engine.
+
+Reference path being replaced: Mamba.forward fast path
+(/root/reference/vim-mamba_ssm/mamba_ssm/modules/mamba_simple.py:169-311) ->
+bimamba_inner_fn / mamba_inner_fn / mamba_inner_fn_no_out_proj
+(vim-mamba_ssm/mamba_ssm/ops/selective_scan_interface.py:437-517, 292-365, 155-224).
+
+Data layout in HBM (all token-major, rows = B*L tokens):
+    hidden (M, Dm) --in_proj--> xz (M, 2Di)  [x | z]
+    x --conv+SiLU--> u (M, Di)
+    u --x_proj--> dt (M, Rpad) act dtype  +  bc (M, 2N) fp32      (split epilogue)
+    dt --dt_proj + bias + softplus--> delta (M, Di) fp32
+    (u, delta, bc, z) --bidirectional scan--> out_z (M, Di)
+    out_z --out_proj--> out (M, Dm)
+No flip, no (b d l) transpose, no B/C rearrange copy is ever made.
+"""
+from __future__ import annotations
+
+import weakref
+from typing import Optional
+
+import torch
+
+from . import _lib as L
+from . import ops
+
+
+def _round_up(x: int, m: int) -> int:
+    return (x + m - 1) // m * m
+
+
+class _DerivedCache:
+    """Derived, read-only views of parameters (16-bit copies, zero-padded copies, A = -exp(A_log)).
+    Entries are revalidated against the parameter's version counter and storage pointer, so in-place
+    optimizer updates or load_state_dict invalidate them."""
+
+    def __init__(self):
+        self._d = {}
+
+    def get(self, param: torch.Tensor, tag: str, fn):
+        key = (id(param), tag)
+        ver = (param._version, param.data_ptr(), param.device, param.dtype)
+        hit = self._d.get(key)
+        if hit is not None and hit[0] == ver and hit[2]() is param:
+            return hit[1]
+        with torch.no_grad():
+            val = fn(param.detach())
+        if len(self._d) > 4096:      # ad-hoc (non-parameter) tensors: drop entries whose source is gone
+            self._d = {k: v for k, v in self._d.items() if v[2]() is not None}
+            if len(self._d) > 4096:
+                self._d.clear()
+        self._d[key] = (ver, val, weakref.ref(param))
+        return val
+
+    def clear(self):
+        self._d.clear()
+
+
+_cache = _DerivedCache()
+
+
+def _w(param: torch.Tensor, dtype: torch.dtype, pad_cols: Optional[int] = None) -> torch.Tensor:
+    """Weight as contiguous `dtype`, optionally zero-padded to pad_cols columns."""
+    def make(p):
+        t = p.to(dtype)
+        if pad_cols is not None and pad_cols != t.shape[1]:
+            t2 = torch.zeros((t.shape[0], pad_cols), device=t.device, dtype=dtype)
+            t2[:, : t.shape[1]] = t
+            t = t2
+        return t.contiguous()
+    return _cache.get(param, f"w:{dtype}:{pad_cols}", make)
+
+
+def _f32(param: torch.Tensor) -> torch.Tensor:
+    return _cache.get(param, "f32", lambda p: p.float().contiguous())
+
+
+def _neg_exp(a_log: torch.Tensor) -> torch.Tensor:
+    # A = -exp(A_log.float())   (mamba_simple.py:193,197)
+    return _cache.get(a_log, "negexp", lambda p: (-torch.exp(p.float())).contiguous())
+
+
+def _conv_w(weight: torch.Tensor) -> torch.Tensor:
+    # "d 1 w -> d w"  (selective_scan_interface.py:460)
+    return _cache.get(weight, "convw", lambda p: p.float().reshape(p.shape[0], p.shape[-1]).contiguous())
+
+
+def _pipeline(xz: torch.Tensor, Di: int, N: int, conv_w, conv_b, x_proj_w, dt_proj_w, dt_bias,
+              *, reverse: bool, delta_dtype: torch.dtype, backend: int):
+    """conv -> x_proj -> dt_proj for one parameter set (selective_scan_interface.py:461-496).
+    xz: (B, L, 2Di) token-major.  Returns u (B,L,Di), delta (B,L,Di), Bm, Cm (B,L,N) views."""
+    B, Lq, _ = xz.shape
+    M = B * Lq
+    act = xz.dtype
+    R = dt_proj_w.shape[1]
+    x = xz[..., :Di]
+    u = ops.causal_conv1d(x, _conv_w(conv_w), _f32(conv_b) if conv_b is not None else None, silu=True, reverse=reverse)
+    Rpad = _round_up(R, 8)
+    dt = torch.empty((M, Rpad), device=xz.device, dtype=act)
+    bc = torch.empty((M, 2 * N), device=xz.device, dtype=torch.float32)
+    ops.gemm_tn(u.view(M, Di), _w(x_proj_w, act), out=dt, out2=bc, split=R, backend=backend)
+    delta = ops.gemm_tn(dt, _w(dt_proj_w, act, pad_cols=Rpad), k=R, bias=_f32(dt_bias), act=L.ACT_SOFTPLUS,
+                        out_dtype=delta_dtype, backend=backend)
+    bc3 = bc.view(B, Lq, 2 * N)
+    return u, delta.view(B, Lq, Di), bc3[..., :N], bc3[..., N:]
+
+
+def mamba_mixer_forward(m, hidden: torch.Tensor, *, backend: int = L.GEMM_AUTO,
+                        delta_dtype: torch.dtype = torch.float32) -> torch.Tensor:
+    """Forward of one mixer.  ``m`` carries the reference module's parameters/attributes
+    (in_proj, conv1d, x_proj, dt_proj, A_log, D, out_proj [, A_b_log, conv1d_b, x_proj_b, dt_proj_b, D_b, gamma]).
+    hidden: (B, L, Dm) in the activation dtype (fp32 / fp16 / bf16).  Returns (B, L, Dm)."""
+    L.require_cuda(hidden)
+    B, Lq, Dm = hidden.shape
+    M = B * Lq
+    act = hidden.dtype
+    Di, N = m.d_inner, m.d_state
+    if delta_dtype != torch.float32:
+        delta_dtype = act
+    h2 = hidden.reshape(M, Dm)
+    if h2.stride(-1) != 1:
+        h2 = h2.contiguous()
+    in_b = _f32(m.in_proj.bias) if m.in_proj.bias is not None else None
+    xz = ops.gemm_tn(h2, _w(m.in_proj.weight, act), bias=in_b, backend=backend).view(B, Lq, 2 * Di)   # (:185-191)
+    z = xz[..., Di:]
+    A = _neg_exp(m.A_log)
+    Dv = _f32(m.D)
+    kw = dict(delta_dtype=delta_dtype, backend=backend)
+    bt = m.bimamba_type
+    scale = 1.0
+    if bt == "v1":      # Fo-Bi: shared projections, A vs A_b  (:198-213 -> BiMambaInnerFn.forward :441-517)
+        u, delta, Bm, Cm = _pipeline(xz, Di, N, m.conv1d.weight, m.conv1d.bias, m.x_proj.weight,
+                                     m.dt_proj.weight, m.dt_proj.bias, reverse=False, **kw)
+        fwd = ops.ScanDirection(u, delta, A, Bm, Cm, Dv)
+        bwd = ops.ScanDirection(u, delta, _neg_exp(m.A_b_log), Bm, Cm, Dv)
+    elif bt == "v2":    # Bi-Bi: two full parameter sets, second on the reversed sequence (:214-246)
+        u, delta, Bm, Cm = _pipeline(xz, Di, N, m.conv1d.weight, m.conv1d.bias, m.x_proj.weight,
+                                     m.dt_proj.weight, m.dt_proj.bias, reverse=False, **kw)
+        ub, deltab, Bb, Cb = _pipeline(xz, Di, N, m.conv1d_b.weight, m.conv1d_b.bias, m.x_proj_b.weight,
+                                       m.dt_proj_b.weight, m.dt_proj_b.bias, reverse=True, **kw)
+        fwd = ops.ScanDirection(u, delta, A, Bm, Cm, Dv)
+        bwd = ops.ScanDirection(ub, deltab, _neg_exp(m.A_b_log), Bb, Cb, _f32(m.D_b))
+        if m.if_devide_out:
+            scale = 0.5                                                                    # (:246)
+    elif bt == "none":  # Fo-Fo (:248-263 -> MambaInnerFn.forward :296-365)
+        u, delta, Bm, Cm = _pipeline(xz, Di, N, m.conv1d.weight, m.conv1d.bias, m.x_proj.weight,
+                                     m.dt_proj.weight, m.dt_proj.bias, reverse=False, **kw)
+        fwd, bwd = ops.ScanDirection(u, delta, A, Bm, Cm, Dv), None
+    else:
+        raise ValueError(f"unknown bimamba_type {bt!r}")
+    out_z = ops.selective_scan(fwd, bwd, z, out_scale=scale)
+    out_b = _f32(m.out_proj.bias) if m.out_proj.bias is not None else None
+    out = ops.gemm_tn(out_z.view(M, Di), _w(m.out_proj.weight, act), bias=out_b, backend=backend).view(B, Lq, Dm)  # (:517)
+    gamma = getattr(m, "gamma", None)
+    if getattr(m, "init_layer_scale", None) is not None and gamma is not None:
+        out = out * gamma.to(out.dtype)                                                    # (:309-310)
+    return out

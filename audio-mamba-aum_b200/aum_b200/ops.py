@@ -1,0 +1,188 @@
+"""Token-major op wrappers over the C ABI (include/aum_b200.h).
+
+Every tensor here is "token-major": shape (rows, C) or (B, L, C) with the channel axis contiguous and a row
+pitch (leading dimension) that may exceed C (views into wider buffers are fine and never copied).
+PyTorch allocates; the library only launches kernels on the current stream.
+"""
+from __future__ import annotations
+
+from typing import Optional, Tuple
+
+import torch
+
+from . import _lib as L
+
+
+def _as_rows(t: torch.Tensor) -> Tuple[int, int, int]:
+    """(rows, cols, ld) of a token-major tensor (2-D, or 3-D whose first two axes collapse)."""
+    if t.stride(-1) != 1 and t.shape[-1] != 1:
+        raise L.AumError("token-major tensor must have a contiguous last axis")
+    if t.dim() == 2:
+        return t.shape[0], t.shape[1], (t.stride(0) if t.shape[0] > 1 else max(t.stride(0), t.shape[1]))
+    if t.dim() == 3:
+        B, Lq, Cc = t.shape
+        ld = t.stride(1) if Lq > 1 else max(t.stride(1), Cc)
+        if B > 1 and t.stride(0) != Lq * ld:
+            raise L.AumError("3-D token-major tensor must collapse to rows (stride(0) == L*stride(1))")
+        return B * Lq, Cc, ld
+    raise L.AumError("expected a 2-D or 3-D tensor")
+
+
+def gemm_tn(a: torch.Tensor, w: torch.Tensor, *, out: Optional[torch.Tensor] = None,
+            out_dtype: Optional[torch.dtype] = None, out2: Optional[torch.Tensor] = None, split: Optional[int] = None,
+            bias: Optional[torch.Tensor] = None, row_scale: Optional[torch.Tensor] = None,
+            act: int = L.ACT_NONE, backend: int = L.GEMM_AUTO, k: Optional[int] = None) -> torch.Tensor:
+    """out[M,N] = act(row_scale * (a[M,K] @ w[N,K]^T) + bias).  a, w: same dtype, K-contiguous rows.
+    ``k`` restricts the reduction to the first k columns of both operands (zero-padded weight copies)."""
+    L.require_cuda(a, w)
+    M, Ka, lda = _as_rows(a)
+    N, Kw, ldw = _as_rows(w)
+    K = k if k is not None else Ka
+    if K > Ka or K > Kw or a.dtype != w.dtype:
+        raise L.AumError(f"gemm_tn: incompatible operands a{tuple(a.shape)} {a.dtype} w{tuple(w.shape)} {w.dtype} K={K}")
+    if out2 is None:
+        split_ = N
+        if out is None:
+            out = torch.empty((M, N), device=a.device, dtype=out_dtype or a.dtype)
+        ncols = N
+    else:
+        split_ = int(split)
+        ncols = split_
+        if out is None:
+            raise L.AumError("gemm_tn: split output needs explicit out and out2")
+    Mo, No, ldc = _as_rows(out)
+    if Mo != M or No < ncols:
+        raise L.AumError("gemm_tn: bad output shape")
+    ldc2, c2dt, p2 = 0, L.F32, None
+    if out2 is not None:
+        M2, N2, ldc2 = _as_rows(out2)
+        if M2 != M or N2 < N - split_:
+            raise L.AumError("gemm_tn: bad second output shape")
+        c2dt, p2 = L.dt(out2.dtype), L.ptr(out2)
+    if bias is not None and (bias.dtype != torch.float32 or bias.numel() != N):
+        raise L.AumError("gemm_tn: bias must be fp32 of length N")
+    if row_scale is not None and (row_scale.dtype != torch.float32 or row_scale.numel() != M):
+        raise L.AumError("gemm_tn: row_scale must be fp32 of length M")
+    rc = L.lib().aum_gemm_tn(L.ptr(a), lda, L.ptr(w), ldw, L.dt(a.dtype),
+                             L.ptr(out), ldc, L.dt(out.dtype), p2, ldc2, c2dt, split_,
+                             M, N, K, L.ptr(bias), L.ptr(row_scale), act, backend, L.stream())
+    L.check(rc, "aum_gemm_tn")
+    return out
+
+
+def causal_conv1d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, silu: bool = True,
+                  reverse: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """x: (B, L, D) token-major (may be a channel slice of a wider buffer); w: (D, W) fp32; bias (D) fp32."""
+    L.require_cuda(x, w)
+    B, Lq, D = x.shape
+    _, _, ldx = _as_rows(x)
+    if w.dtype != torch.float32 or not w.is_contiguous() or w.shape[0] != D:
+        raise L.AumError("causal_conv1d: weight must be contiguous fp32 (D, W)")
+    if bias is not None and (bias.dtype != torch.float32 or not bias.is_contiguous()):
+        raise L.AumError("causal_conv1d: bias must be contiguous fp32")
+    if out is None:
+        out = torch.empty((B, Lq, D), device=x.device, dtype=x.dtype)
+    _, _, ldo = _as_rows(out)
+    rc = L.lib().aum_causal_conv1d_fwd(L.ptr(x), ldx, L.ptr(w), L.ptr(bias), L.ptr(out), ldo,
+                                       B, Lq, D, w.shape[1], L.dt(x.dtype), int(silu), int(reverse), L.stream())
+    L.check(rc, "aum_causal_conv1d_fwd")
+    return out
+
+
+class ScanDirection:
+    """One time direction of the scan (struct aum_scan_dir).  All tensors token-major:
+    u, delta: (B, L, D); A: (D, N) fp32; Bm, Cm: (B, L, N); D, delta_bias: (D,) fp32 or None."""
+
+    def __init__(self, u, delta, A, Bm, Cm, D=None, delta_bias=None, delta_softplus=False, last_state=None):
+        self.u, self.delta, self.A, self.Bm, self.Cm = u, delta, A, Bm, Cm
+        self.D, self.delta_bias, self.delta_softplus, self.last_state = D, delta_bias, delta_softplus, last_state
+
+    def _struct(self, B, Lq, Dch, N):
+        L.require_cuda(self.u, self.delta, self.A, self.Bm, self.Cm)
+        for t, name in ((self.A, "A"), (self.D, "D"), (self.delta_bias, "delta_bias")):
+            if t is not None and (t.dtype != torch.float32 or not t.is_contiguous()):
+                raise L.AumError(f"scan: {name} must be contiguous fp32")
+        if tuple(self.u.shape) != (B, Lq, Dch) or tuple(self.delta.shape) != (B, Lq, Dch):
+            raise L.AumError("scan: u/delta shape mismatch")
+        if tuple(self.Bm.shape) != (B, Lq, N) or tuple(self.Cm.shape) != (B, Lq, N) or self.Bm.dtype != self.Cm.dtype:
+            raise L.AumError("scan: B/C shape or dtype mismatch")
+        if tuple(self.A.shape) != (Dch, N):
+            raise L.AumError("scan: A must be (D, N)")
+        s = L.ScanDir()
+        s.u, s.ld_u = self.u.data_ptr(), _as_rows(self.u)[2]
+        s.delta, s.ld_delta, s.delta_dtype = self.delta.data_ptr(), _as_rows(self.delta)[2], L.dt(self.delta.dtype)
+        s.A = self.A.data_ptr()
+        s.Bm, s.ld_B = self.Bm.data_ptr(), _as_rows(self.Bm)[2]
+        s.Cm, s.ld_C = self.Cm.data_ptr(), _as_rows(self.Cm)[2]
+        s.bc_dtype = L.dt(self.Bm.dtype)
+        s.D = self.D.data_ptr() if self.D is not None else None
+        s.delta_bias = self.delta_bias.data_ptr() if self.delta_bias is not None else None
+        s.delta_softplus = int(bool(self.delta_softplus))
+        s.last_state = self.last_state.data_ptr() if self.last_state is not None else None
+        return s
+
+
+def selective_scan(fwd: Optional[ScanDirection], bwd: Optional[ScanDirection], z: Optional[torch.Tensor], *,
+                   out: Optional[torch.Tensor] = None, out_scale: float = 1.0) -> torch.Tensor:
+    """out = out_scale * (y_fwd + y_bwd) * silu(z); either direction may be None.  Token-major (B, L, D)."""
+    ref = fwd if fwd is not None else bwd
+    if ref is None:
+        raise L.AumError("selective_scan: no direction given")
+    B, Lq, Dch = ref.u.shape
+    N = ref.A.shape[1]
+    if out is None:
+        out = torch.empty((B, Lq, Dch), device=ref.u.device, dtype=ref.u.dtype)
+    if out.dtype != ref.u.dtype or (z is not None and z.dtype != ref.u.dtype):
+        raise L.AumError("selective_scan: u, z and out must share a dtype")
+    import ctypes as C
+    sf = fwd._struct(B, Lq, Dch, N) if fwd is not None else None
+    sb = bwd._struct(B, Lq, Dch, N) if bwd is not None else None
+    ldz = _as_rows(z)[2] if z is not None else 0
+    rc = L.lib().aum_selective_scan_fwd(C.byref(sf) if sf is not None else None,
+                                        C.byref(sb) if sb is not None else None,
+                                        L.ptr(z), ldz, L.ptr(out), _as_rows(out)[2],
+                                        B, Lq, Dch, N, L.dt(out.dtype), float(out_scale), L.stream())
+    L.check(rc, "aum_selective_scan_fwd")
+    return out
+
+
+def add_rmsnorm(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor] = None,
+                residual: Optional[torch.Tensor] = None, *, eps: float = 1e-5, prenorm: bool = False,
+                residual_dtype: Optional[torch.dtype] = torch.float32, out_dtype: Optional[torch.dtype] = None,
+                rstd: Optional[torch.Tensor] = None):
+    """y = rmsnorm(x + residual) * weight (+ bias); with prenorm also returns the new residual (x + residual)."""
+    L.require_cuda(x, weight)
+    rows, dim, ldx = _as_rows(x)
+    if weight.dtype != torch.float32 or not weight.is_contiguous():
+        raise L.AumError("add_rmsnorm: weight must be contiguous fp32")
+    y = torch.empty(x.shape, device=x.device, dtype=out_dtype or x.dtype)
+    res_out = None
+    if prenorm:
+        rd = residual.dtype if residual is not None else (residual_dtype or x.dtype)
+        res_out = torch.empty(x.shape, device=x.device, dtype=rd)
+    ldr = _as_rows(residual)[2] if residual is not None else 0
+    rc = L.lib().aum_add_rmsnorm_fwd(L.ptr(x), ldx, L.dt(x.dtype),
+                                     L.ptr(residual), ldr, L.dt(residual.dtype) if residual is not None else L.F32,
+                                     L.ptr(weight), L.ptr(bias),
+                                     L.ptr(y), _as_rows(y)[2], L.dt(y.dtype),
+                                     L.ptr(res_out), _as_rows(res_out)[2] if res_out is not None else 0,
+                                     L.dt(res_out.dtype) if res_out is not None else L.F32,
+                                     L.ptr(rstd), rows, dim, float(eps), L.stream())
+    L.check(rc, "aum_add_rmsnorm_fwd")
+    return (y, res_out) if prenorm else y
+
+
+def transpose(src: torch.Tensor, dst: Optional[torch.Tensor] = None, dst_dtype: Optional[torch.dtype] = None) -> torch.Tensor:
+    """(B, R, C) -> (B, C, R) with optional dtype change; src rows must be contiguous along C."""
+    L.require_cuda(src)
+    B, R, Cc = src.shape
+    if src.stride(2) != 1 and Cc != 1:
+        raise L.AumError("transpose: source last axis must be contiguous")
+    if dst is None:
+        dst = torch.empty((B, Cc, R), device=src.device, dtype=dst_dtype or src.dtype)
+    if dst.stride(2) != 1 and R != 1:
+        raise L.AumError("transpose: destination last axis must be contiguous")
+    rc = L.lib().aum_transpose(L.ptr(src), src.stride(0), src.stride(1), L.ptr(dst), dst.stride(0), dst.stride(1),
+                               B, R, Cc, L.dt(src.dtype), L.dt(dst.dtype), L.stream())
+    L.check(rc, "aum_transpose")
+    return dst

@@ -1,0 +1,139 @@
+/*
+ * aum_b200.h — C ABI of libaum_b200.so: the B200 (sm_100a) engine behind Audio-Mamba's
+ * bidirectional selective-scan hot path.
+ *
+ * This is the drop-in boundary.  The reference reaches its native code through
+ * two pybind modules of un-vendored pip wheels (mamba_ssm==1.1.3.post1, causal_conv1d==1.1.3.post1,
+ * /root/reference/README.md:58) that take at::Tensor; each entry point below names the reference
+ * call site(s) it replaces (paths relative to /root/reference).  Here everything is plain C:
+ * raw device pointers, explicit sizes / leading dimensions, a dtype enum, and the CUDA stream as void*.
+ *
+ * Conventions
+ *   - Every function returns 0 on success, non-zero on error; aum_last_error() gives the message
+ *     (thread-local).  No C++ exception crosses this boundary.  No function synchronises the device
+ *     or allocates device memory; the caller owns all buffers (PyTorch's caching allocator in the
+ *     Python host).  All launches go to the stream passed in; everything is CUDA-graph capturable.
+ *   - Activations are TOKEN-MAJOR: a logical (batch, L, C) tensor is addressed as rows = batch*L tokens
+ *     with a leading dimension ("ld", in ELEMENTS) between consecutive tokens and channels contiguous.
+ *     (The reference's (batch, C, L) tensors are handled on the host side by aum_transpose_*.)
+ *   - dtype: AUM_F32 / AUM_F16 / AUM_BF16 for activations; parameters named "float*" are always fp32
+ *     as in the reference (A, D, delta_bias: vim-mamba_ssm/mamba_ssm/modules/mamba_simple.py:193,210-211).
+ */
+#ifndef AUM_B200_H_
+#define AUM_B200_H_
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define AUM_B200_VERSION 100 /* 0.1.0 */
+
+#if defined(__GNUC__)
+#define AUM_API __attribute__((visibility("default")))
+#else
+#define AUM_API
+#endif
+
+enum aum_dtype { AUM_F32 = 0, AUM_F16 = 1, AUM_BF16 = 2 };
+
+/* GEMM epilogue activation */
+enum aum_act { AUM_ACT_NONE = 0, AUM_ACT_SOFTPLUS = 1 /* torch softplus, threshold 20 */ };
+
+/* GEMM backend selection */
+enum aum_gemm_backend { AUM_GEMM_AUTO = 0, AUM_GEMM_TCGEN05 = 1, AUM_GEMM_SIMT = 2 };
+
+AUM_API int aum_version(void);
+AUM_API const char* aum_last_error(void);
+/* sm_count / compute capability of the current device; 0 on success. */
+AUM_API int aum_device_info(int* sm_count, int* cc_major, int* cc_minor);
+
+/* ---------------------------------------------------------------------------------------------
+ * Dense projections:  C[M,N] = act( row_scale[m] * (A[M,K] @ W[N,K]^T) + bias[n] )
+ *   replaces the cuBLAS calls at mamba_simple.py:185-189 (in_proj), selective_scan_interface.py:467
+ *   (x_proj), :468 (dt_proj), :517 (out_proj).  A and W are K-contiguous ("TN"), which is exactly
+ *   nn.Linear's weight layout and the token-major activation layout.
+ *   ab_dtype F16/BF16 -> tcgen05 tensor cores (TMA -> smem -> tcgen05.mma -> TMEM -> epilogue);
+ *   ab_dtype F32     -> fp32 CUDA-core kernel (strict-parity tier).
+ *   Optional split output: columns [0,split) go to C (c_dtype), columns [split,N) to C2 (c2_dtype) at
+ *   column index n-split; pass C2=NULL, split=N for a single output (split%8==0 keeps 16-byte stores).
+ * ------------------------------------------------------------------------------------------- */
+AUM_API int aum_gemm_tn(const void* A, int64_t lda, const void* W, int64_t ldw, int ab_dtype,
+                void* C, int64_t ldc, int c_dtype,
+                void* C2, int64_t ldc2, int c2_dtype, int split,
+                int M, int N, int K,
+                const float* bias, const float* row_scale, int act,
+                int backend, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Depthwise causal conv1d (+bias, +SiLU) along the token axis.
+ *   replaces causal_conv1d_cuda.causal_conv1d_fwd(x, w, bias, None, silu)
+ *   (selective_scan_interface.py:177,239,318,380,463,532) and causal_conv1d_fn (:646,:683).
+ *   x, out: (batch*L, D) token-major with ldx / ldo; w: (D, W) fp32; bias: (D) fp32 or NULL; 2<=W<=4.
+ *   reverse=1 computes the anti-causal conv  out[l] = b + sum_k w[k] x[l+(W-1)-k]  — what the Bi-Bi
+ *   pipeline gets by running on xz.flip(-1) and flipping back (mamba_simple.py:229-241), without flips.
+ * ------------------------------------------------------------------------------------------- */
+AUM_API int aum_causal_conv1d_fwd(const void* x, int64_t ldx, const float* w, const float* bias,
+                          void* out, int64_t ldo, int batch, int L, int D, int W,
+                          int dtype, int silu, int reverse, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Selective scan, one or both time directions in ONE launch.
+ *   replaces selective_scan_cuda.fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus)
+ *   (selective_scan_interface.py:37,213,354,499) and — for the reverse direction — the second call on
+ *   five flip(-1) copies plus the un-flip and add (:503-507).
+ *   Per direction:  delta' = softplus?(delta + delta_bias);  h_l = exp(delta'_l A) h_{l∓1} + delta'_l B_l u_l;
+ *                   y_l = <C_l, h_l> + D u_l.
+ *   out = out_scale * (y_fwd + y_bwd) * silu(z)   (z optional; a NULL direction contributes 0).
+ *   Fo-Bi (bimamba v1): both directions share u/delta/B/C/D/bias and differ in A (A vs A_b).
+ *   Bi-Bi (v2): every field differs per direction; out_scale = 0.5 when if_devide_out.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct aum_scan_dir {
+  const void* u;     int64_t ld_u;                      /* (batch*L, D)  dtype            */
+  const void* delta; int64_t ld_delta; int delta_dtype; /* (batch*L, D)  any aum_dtype    */
+  const float* A;                                       /* (D, N) fp32, real, negative    */
+  const void* Bm;    int64_t ld_B;                      /* (batch*L, N)  bc_dtype         */
+  const void* Cm;    int64_t ld_C;                      /* (batch*L, N)  bc_dtype         */
+  int bc_dtype;
+  const float* D;                                       /* (D) fp32 or NULL               */
+  const float* delta_bias;                              /* (D) fp32 or NULL               */
+  int delta_softplus;                                   /* apply softplus(delta+bias)     */
+  float* last_state;                                    /* (batch, D, N) fp32 or NULL     */
+} aum_scan_dir_t;
+
+AUM_API int aum_selective_scan_fwd(const aum_scan_dir_t* fwd, const aum_scan_dir_t* bwd,
+                           const void* z, int64_t ld_z,
+                           void* out, int64_t ld_out,
+                           int batch, int L, int D, int N, int dtype,
+                           float out_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Fused residual-add + RMSNorm (fp32 residual stream) — the op on either side of the mixer.
+ *   replaces Triton _layer_norm_fwd_1pass_kernel (vim-mamba_ssm/mamba_ssm/ops/triton/layernorm.py:65-120)
+ *   as called by rms_norm_fn (:477) from src/models/mamba_models.py:77-97,646-657.
+ *   r = x + residual_in (fp32);  y = r * rsqrt(mean(r^2)+eps) * weight (+bias);
+ *   residual_out (fp32, optional) = r;  rstd_out (rows, optional) saved for backward.
+ * ------------------------------------------------------------------------------------------- */
+AUM_API int aum_add_rmsnorm_fwd(const void* x, int64_t ldx, int x_dtype,
+                        const void* residual_in, int64_t ldr, int r_dtype,
+                        const float* weight, const float* bias,
+                        void* y, int64_t ldy, int y_dtype,
+                        void* residual_out, int64_t ldro, int ro_dtype,
+                        float* rstd_out, int rows, int dim, float eps, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Layout adapters for the reference's channel-major (batch, C, L) tensors:
+ *   dst[b, j, i] = src[b, i, j]  for a (batch, R, C) -> (batch, C, R) transpose with explicit strides
+ *   (elements): src element (b,i,j) at b*src_bs + i*src_ld + j; dst element (b,j,i) at b*dst_bs + j*dst_ld + i.
+ *   Used where the functional API receives xz as (B, 2*Di, L) with stride(-1)==1
+ *   (selective_scan_interface.py:458-461) or must return (B, Di, L) (:224).
+ * ------------------------------------------------------------------------------------------- */
+AUM_API int aum_transpose(const void* src, int64_t src_bs, int64_t src_ld,
+                  void* dst, int64_t dst_bs, int64_t dst_ld,
+                  int batch, int R, int C, int src_dtype, int dst_dtype, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* AUM_B200_H_ */

@@ -1,0 +1,113 @@
+"""Per-kernel timing at AuM-Base shapes (config 2: B=64, L=513, Dm=768, Di=1536, R=48, N=16).
+Usage: python tools/kernel_bench.py [--batch 64] [--dtype fp16] [--only scan,gemm,...]
+CUDA-event timing, L2 flushed between iterations.  Prints one JSON line per kernel."""
+import argparse
+import json
+import os
+import sys
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "audio-mamba-aum_b200"))
+import torch  # noqa: E402
+
+from aum_b200 import ops, _lib as L  # noqa: E402
+
+PEAK_GBS, PEAK_TF = 6575.8, 1693.1
+try:
+    pk = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
+    PEAK_GBS, PEAK_TF = pk["hbm_gbs"], pk["bf16_tflops"]
+except Exception:
+    pass
+
+
+def timeit(fn, iters=10, warmup=3, flush=None):
+    for _ in range(warmup):
+        fn()
+    torch.cuda.synchronize()
+    ts = []
+    for _ in range(iters):
+        if flush is not None:
+            flush.zero_()
+        s, e = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s.record()
+        fn()
+        e.record()
+        torch.cuda.synchronize()
+        ts.append(s.elapsed_time(e))
+    ts.sort()
+    return ts[len(ts) // 2]
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--batch", type=int, default=64)
+    ap.add_argument("--dtype", default="fp16")
+    ap.add_argument("--only", default="")
+    ap.add_argument("--L", type=int, default=513)
+    args = ap.parse_args()
+    dt = {"fp16": torch.float16, "bf16": torch.bfloat16, "fp32": torch.float32}[args.dtype]
+    s = 4 if dt == torch.float32 else 2
+    only = set(filter(None, args.only.split(",")))
+    dev = "cuda"
+    B, Lq, Dm, Di, R, N = args.batch, args.L, 768, 1536, 48, 16
+    M = B * Lq
+    flush = torch.empty(192 * 1024 * 1024, dtype=torch.uint8, device=dev)   # > 126 MB L2
+    g = torch.Generator(device=dev).manual_seed(0)
+    rn = lambda *sh, dtype=dt, sc=1.0: (sc * torch.randn(*sh, device=dev, generator=g)).to(dtype)
+
+    def report(name, ms, bytes_=None, flops=None, **kw):
+        r = {"kernel": name, "ms": round(ms, 4)}
+        if bytes_:
+            r["GBs"] = round(bytes_ / ms / 1e6, 1)
+            r["hbm_frac"] = round(bytes_ / ms / 1e6 / PEAK_GBS, 3)
+        if flops:
+            r["TFs"] = round(flops / ms / 1e9, 1)
+            r["tensor_frac"] = round(flops / ms / 1e9 / PEAK_TF, 3)
+        r.update(kw)
+        print(json.dumps(r), flush=True)
+
+    if not only or "conv" in only:
+        xz = rn(B, Lq, 2 * Di)
+        w, b = rn(Di, 4, dtype=torch.float32), rn(Di, dtype=torch.float32)
+        ms = timeit(lambda: ops.causal_conv1d(xz[..., :Di], w, b), flush=flush)
+        report("conv1d_silu", ms, bytes_=2 * M * Di * s)
+    if not only or "norm" in only:
+        x, r_ = rn(M, Dm), rn(M, Dm, dtype=torch.float32)
+        w = torch.ones(Dm, device=dev)
+        ms = timeit(lambda: ops.add_rmsnorm(x, w, None, r_, prenorm=True), flush=flush)
+        report("add_rmsnorm", ms, bytes_=M * Dm * (2 * s + 8))
+    if not only or "scan" in only:
+        u, z = rn(B, Lq, Di), rn(B, Lq, Di)
+        delta = torch.nn.functional.softplus(rn(B, Lq, Di, dtype=torch.float32) - 2.0)
+        bc = rn(B, Lq, 2 * N, dtype=torch.float32)
+        A = -torch.exp(torch.log(torch.arange(1, N + 1, device=dev, dtype=torch.float32)).repeat(Di, 1)
+                       + 0.1 * rn(Di, N, dtype=torch.float32))
+        A_b = -torch.exp(torch.log(torch.arange(1, N + 1, device=dev, dtype=torch.float32)).repeat(Di, 1)
+                         + 0.1 * rn(Di, N, dtype=torch.float32))
+        Dv = torch.ones(Di, device=dev)
+        mk = lambda Ax: ops.ScanDirection(u, delta, Ax, bc[..., :N], bc[..., N:], Dv)
+        out = torch.empty_like(u)
+        alg = M * Di * (3 * s + 4) + M * 2 * N * 4     # u, z, out (s) + delta fp32 + B,C fp32
+        for ch in ("64", "128"):
+            os.environ["AUM_SCAN_CH"] = ch
+            ms = timeit(lambda: ops.selective_scan(mk(A), mk(A_b), z, out=out), flush=flush)
+            report(f"biscan_ch{ch}", ms, bytes_=alg, exp_per_s_T=round(M * Di * 32 / ms / 1e9, 3))
+            ms = timeit(lambda: ops.selective_scan(mk(A), None, z, out=out), flush=flush)
+            report(f"uniscan_ch{ch}", ms, bytes_=alg, exp_per_s_T=round(M * Di * 16 / ms / 1e9, 3))
+    if dt != torch.float32 and (not only or "gemm" in only):
+        shapes = {"in_proj": (M, 2 * Di, Dm), "out_proj": (M, Dm, Di), "x_proj": (M, R + 2 * N, Di), "dt_proj": (M, Di, R)}
+        for name, (m_, n_, k_) in shapes.items():
+            kp = (k_ + 7) // 8 * 8
+            a, w = rn(m_, kp), rn(n_, kp, sc=k_ ** -0.5)
+            odt = torch.float32 if name == "dt_proj" else dt
+            out = torch.empty(m_, n_, device=dev, dtype=odt)
+            ms = timeit(lambda: ops.gemm_tn(a, w, out=out, k=k_, backend=L.GEMM_TCGEN05), flush=flush)
+            by = (m_ * k_ + n_ * k_) * 2 + m_ * n_ * out.element_size()
+            report("gemm_" + name, ms, bytes_=by, flops=2.0 * m_ * n_ * k_, shape=[m_, n_, k_])
+            if name in ("in_proj", "out_proj"):
+                ms = timeit(lambda: torch.matmul(a, w.t(), out=out), flush=flush)
+                report("cublas_" + name, ms, flops=2.0 * m_ * n_ * k_)
+
+
+if __name__ == "__main__":
+    main()
