@@ -83,10 +83,21 @@ def lib():
     return _lib
 
 
+_launches = 0
+
+
 def check(rc: int, what: str):
+    """Every wrapper calls this once per C-ABI call; each successful call enqueued exactly one kernel."""
+    global _launches
     if rc != 0:
         msg = lib().aum_last_error()
         raise AumError(f"{what} failed (rc={rc}): {msg.decode() if msg else '?'}")
+    _launches += 1
+
+
+def launch_count() -> int:
+    """Number of kernels this process has launched through the C ABI (bench.py's gpu_launches)."""
+    return _launches
 
 
 def dt(t: torch.dtype) -> int:

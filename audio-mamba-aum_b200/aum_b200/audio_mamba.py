@@ -1,0 +1,136 @@
+"""Host-side mirror of the reference's AudioMamba forward (default configuration) on the B200 engine.
+
+Mirrors /root/reference/src/models/mamba_models.py:193-685 for the configuration every released AuM checkpoint
+uses (src/run.py:224-274): rms_norm=True, fused_add_norm=True, residual_in_fp32=True, absolute pos-embed,
+one middle cls token, no RoPE, no sequence flips, drop_path 0.  Same constructor argument names and the same
+state-dict keys (patch_embed.proj.*, cls_token, pos_embed.pos_embed, layers.N.{mixer.*,norm.weight}, norm_f.weight,
+head.*), so reference checkpoints load with strict=True.
+
+This exists because the GPU box has no copy of the reference: bench.py and the whole-model parity tests need a
+caller of the hot path.  With the reference tree available, its own src/models/mamba_models.py runs unchanged on
+top of the sibling ``mamba_ssm`` package instead.
+"""
+from __future__ import annotations
+
+import torch
+import torch.nn as nn
+
+from . import _lib as L
+from . import mixer, ops
+from .modules import Mamba, RMSNorm
+
+
+class _PatchProj(nn.Module):
+    """Holds patch_embed.proj.{weight,bias} with the reference's Conv2d parameter shapes (tokenization.py:224)."""
+
+    def __init__(self, in_chans, embed_dim, patch, device=None, dtype=None):
+        super().__init__()
+        self.proj = nn.Conv2d(in_chans, embed_dim, kernel_size=patch, stride=patch, bias=True, device=device, dtype=dtype)
+        fan_in = in_chans * patch[0] * patch[1]
+        nn.init.trunc_normal_(self.proj.weight, std=(1.0 / fan_in) ** 0.5 / .87962566103423978)
+        nn.init.zeros_(self.proj.bias)
+
+
+class _PosEmbed(nn.Module):
+    def __init__(self, n_tokens, embed_dim, device=None, dtype=None):
+        super().__init__()
+        self.pos_embed = nn.Parameter(torch.zeros(1, n_tokens, embed_dim, device=device, dtype=dtype))
+        nn.init.trunc_normal_(self.pos_embed, std=.02)
+
+
+class _Block(nn.Module):
+    def __init__(self, dim, eps, layer_idx, bimamba_type, if_devide_out, device=None, dtype=None):
+        super().__init__()
+        self.mixer = Mamba(dim, layer_idx=layer_idx, bimamba_type=bimamba_type, if_devide_out=if_devide_out,
+                           device=device, dtype=dtype)
+        self.norm = RMSNorm(dim, eps=eps, device=device, dtype=dtype)
+
+
+class AudioMamba(nn.Module):
+    def __init__(self, spectrogram_size=(128, 1024), patch_size=(16, 16), strides=(16, 16), depth=24, embed_dim=768,
+                 channels=1, num_classes=527, norm_epsilon: float = 1e-5, rms_norm: bool = True,
+                 fused_add_norm: bool = True, residual_in_fp32: bool = True, device=None, dtype=None,
+                 if_abs_pos_embed=True, if_rope=False, if_cls_token=True, if_bidirectional=False,
+                 bimamba_type="v2", if_devide_out=True, use_double_cls_token=False, use_middle_cls_token=True,
+                 act_dtype: torch.dtype = torch.float32, **unsupported):
+        super().__init__()
+        bad = {k: v for k, v in unsupported.items() if v not in (None, False, 0, 0.0, -1.0, "mean")}
+        if bad:
+            raise NotImplementedError(f"AudioMamba (B200 mirror): options outside the default AuM path: {sorted(bad)}")
+        if not (rms_norm and fused_add_norm and residual_in_fp32 and if_abs_pos_embed and if_cls_token
+                and use_middle_cls_token) or if_rope or if_bidirectional or use_double_cls_token or channels != 1:
+            raise NotImplementedError("AudioMamba (B200 mirror) implements the default AuM configuration only")
+        patch = tuple(patch_size) if isinstance(patch_size, (tuple, list)) else (patch_size, patch_size)
+        if tuple(strides) != patch:
+            raise NotImplementedError("overlapping patches (strides != patch_size) are not on the default AuM path")
+        F_, T_ = spectrogram_size
+        self.patch = patch
+        self.grid = (F_ // patch[0], T_ // patch[1])
+        self.num_patches = self.grid[0] * self.grid[1]
+        self.embed_dim = self.d_model = self.num_features = embed_dim
+        self.num_classes = num_classes
+        self.eps = norm_epsilon
+        self.act_dtype = act_dtype
+        fk = {"device": device, "dtype": dtype}
+        self.cls_token = nn.Parameter(torch.zeros(1, 1, embed_dim, **fk))
+        nn.init.trunc_normal_(self.cls_token, std=.02)
+        self.head = nn.Linear(embed_dim, num_classes, **fk)
+        nn.init.trunc_normal_(self.head.weight, std=.02)
+        nn.init.zeros_(self.head.bias)
+        self.layers = nn.ModuleList([_Block(embed_dim, norm_epsilon, i, bimamba_type, if_devide_out, **fk)
+                                     for i in range(depth)])
+        with torch.no_grad():   # _init_weights rescaling of residual projections (mamba_models.py:164-172)
+            for blk in self.layers:
+                blk.mixer.out_proj.weight.div_(depth ** 0.5)
+        self.norm_f = RMSNorm(embed_dim, eps=norm_epsilon, **fk)
+        self.patch_embed = _PatchProj(channels, embed_dim, patch, **fk)
+        self.pos_embed = _PosEmbed(self.num_patches + 1, embed_dim, **fk)
+
+    # ------------------------------------------------------------------------------------------------
+    def _tokens(self, x: torch.Tensor, act: torch.dtype) -> torch.Tensor:
+        """(B, T, F) spectrogram -> (B, N+1, Dm) fp32 token sequence with the cls token in the middle and
+        the absolute position embedding added (mamba_models.py:510-541, tokenization.py:278-310,414-451)."""
+        B, T_, F_ = x.shape
+        pf, pt = self.patch
+        gf, gt = self.grid
+        # im2col of the stride-16 conv: token (f_blk, t_blk) <- pixels (kf, kt);  img[b,0,f,t] = x[b,t,f]
+        cols = x.view(B, gt, pt, gf, pf).permute(0, 3, 1, 4, 2).reshape(B * gf * gt, pf * pt)
+        cols = cols.to(act) if act != torch.float32 else cols.contiguous()
+        w = mixer._cache.get(self.patch_embed.proj.weight, f"patchw:{act}",
+                             lambda p: p.reshape(p.shape[0], -1).to(act).contiguous())
+        tok = ops.gemm_tn(cols, w, bias=mixer._f32(self.patch_embed.proj.bias), out_dtype=torch.float32)
+        tok = tok.view(B, gf * gt, self.embed_dim)
+        N = gf * gt
+        tp = N // 2
+        pe = self.pos_embed.pos_embed          # slot 0 belongs to the cls token
+        hidden = torch.empty((B, N + 1, self.embed_dim), device=x.device, dtype=torch.float32)
+        torch.add(tok[:, :tp], pe[:, 1:tp + 1], out=hidden[:, :tp])
+        hidden[:, tp] = (self.cls_token[0, 0] + pe[0, 0])
+        torch.add(tok[:, tp:], pe[:, tp + 1:], out=hidden[:, tp + 1:])
+        return hidden
+
+    def forward_features(self, x: torch.Tensor) -> torch.Tensor:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            raise NotImplementedError("aum_b200 AudioMamba: training path not built yet; use torch.no_grad()")
+        L.require_cuda(x)
+        act = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else self.act_dtype
+        hidden = self._tokens(x.float(), act)
+        B, Ntok, Dm = hidden.shape
+        tp = (Ntok - 1) // 2
+        residual = None
+        for blk in self.layers:                                                   # (mamba_models.py:602-622)
+            y, residual = ops.add_rmsnorm(hidden.view(B * Ntok, Dm), mixer._f32(blk.norm.weight), None,
+                                          residual, eps=blk.norm.eps, prenorm=True, out_dtype=act)   # (:77-97)
+            hidden = mixer.mamba_mixer_forward(blk.mixer, y.view(B, Ntok, Dm))                       # (:98)
+        # final add+norm (:646-657) is only needed on the cls rows that are returned (:660-664)
+        h_cls = hidden[:, tp, :]
+        r_cls = residual.view(B, Ntok, Dm)[:, tp, :]
+        return ops.add_rmsnorm(h_cls, mixer._f32(self.norm_f.weight), None, r_cls, eps=self.norm_f.eps,
+                               prenorm=False, out_dtype=act)
+
+    def forward(self, x: torch.Tensor, return_features: bool = False) -> torch.Tensor:
+        feat = self.forward_features(x)
+        if return_features:
+            return feat
+        return ops.gemm_tn(feat, mixer._w(self.head.weight, feat.dtype), bias=mixer._f32(self.head.bias),
+                           out_dtype=torch.float32)                                                  # (:682)

@@ -12,6 +12,9 @@ import torch
 
 from . import _lib as L
 
+# bench.py hook: when set to a list, (name, start_event, end_event) is appended around each selective-scan launch
+PROFILE = None
+
 
 def _as_rows(t: torch.Tensor) -> Tuple[int, int, int]:
     """(rows, cols, ld) of a token-major tensor (2-D, or 3-D whose first two axes collapse)."""
@@ -138,11 +141,18 @@ def selective_scan(fwd: Optional[ScanDirection], bwd: Optional[ScanDirection], z
     sf = fwd._struct(B, Lq, Dch, N) if fwd is not None else None
     sb = bwd._struct(B, Lq, Dch, N) if bwd is not None else None
     ldz = _as_rows(z)[2] if z is not None else 0
+    if PROFILE is not None:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
     rc = L.lib().aum_selective_scan_fwd(C.byref(sf) if sf is not None else None,
                                         C.byref(sb) if sb is not None else None,
                                         L.ptr(z), ldz, L.ptr(out), _as_rows(out)[2],
                                         B, Lq, Dch, N, L.dt(out.dtype), float(out_scale), L.stream())
     L.check(rc, "aum_selective_scan_fwd")
+    if PROFILE is not None:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+        PROFILE.append(("selective_scan", ev0, ev1))
     return out
 
 

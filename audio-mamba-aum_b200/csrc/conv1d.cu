@@ -2,16 +2,43 @@
 // Replaces causal_conv1d_cuda.causal_conv1d_fwd (call sites: /root/reference/vim-mamba_ssm/mamba_ssm/ops/
 // selective_scan_interface.py:177,239,318,380,463,532); semantics = mamba_simple.py:272 with padding W-1.
 //
-// HBM-bound streaming kernel: each thread owns 8 consecutive channels (one 16-byte vector for 16-bit
-// dtypes) and walks TL consecutive tokens with a rolling (W-1)-deep window in registers, so every input row
-// is read once per token tile (+ a 3-row halo) with fully coalesced 16 B accesses across the warp.
+// HBM-bound streaming kernel.  Each thread owns VEC (=2) adjacent channels and CONV_TL (=16) consecutive tokens:
+// a warp therefore reads/writes one contiguous 128-byte (16-bit) or 256-byte (fp32) segment per token row, all
+// TL+3 input rows of a thread are independent loads issued up front (one DRAM latency per thread), kept PACKED
+// in registers (19 regs) so the kernel runs at full occupancy, and the 3-row halo is served by L1/L2.
 // Algorithmic bytes per (token, channel): read s + write s (s = itemsize).
 #include "common.cuh"
 
 namespace aum {
 
-constexpr int CONV_TL = 8;    // tokens per thread
+constexpr int CONV_TL = 16;   // tokens per thread
 constexpr int CONV_MAXW = 4;
+
+template <typename T> struct Pair;        // two adjacent channels, packed as loaded
+template <> struct Pair<float> {
+  float2 v;
+  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float2*>(p); }
+  __device__ __forceinline__ void zero() { v = make_float2(0.f, 0.f); }
+  __device__ __forceinline__ void set(float a, float b) { v = make_float2(a, b); }
+  __device__ __forceinline__ float2 f() const { return v; }
+  static __device__ __forceinline__ void store(float* p, float a, float b) { *reinterpret_cast<float2*>(p) = make_float2(a, b); }
+};
+template <> struct Pair<__half> {
+  __half2 v;
+  __device__ __forceinline__ void load(const __half* p) { v = *reinterpret_cast<const __half2*>(p); }
+  __device__ __forceinline__ void zero() { v = __floats2half2_rn(0.f, 0.f); }
+  __device__ __forceinline__ void set(float a, float b) { v = __floats2half2_rn(a, b); }
+  __device__ __forceinline__ float2 f() const { return __half22float2(v); }
+  static __device__ __forceinline__ void store(__half* p, float a, float b) { *reinterpret_cast<__half2*>(p) = __floats2half2_rn(a, b); }
+};
+template <> struct Pair<__nv_bfloat16> {
+  __nv_bfloat162 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const __nv_bfloat162*>(p); }
+  __device__ __forceinline__ void zero() { v = __floats2bfloat162_rn(0.f, 0.f); }
+  __device__ __forceinline__ void set(float a, float b) { v = __floats2bfloat162_rn(a, b); }
+  __device__ __forceinline__ float2 f() const { return __bfloat1622float2(v); }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float a, float b) { *reinterpret_cast<__nv_bfloat162*>(p) = __floats2bfloat162_rn(a, b); }
+};
 
 template <typename T, int VEC>
 __global__ void __launch_bounds__(256)
@@ -27,18 +54,18 @@ conv1d_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
   const int c0 = cv * VEC;
 
   // taps, zero-padded at the front to CONV_MAXW:  y[l] = bias + sum_j wk[j] * x[l - (MAXW-1) + j]
-  float wk[CONV_MAXW][VEC];
-  float bs[VEC];
+  float wk[CONV_MAXW][2];
+  float bs[2];
 #pragma unroll
-  for (int v = 0; v < VEC; ++v) {
+  for (int v = 0; v < 2; ++v) {
     const int c = c0 + v;
-    const bool ok = c < D;
+    const bool ok = (v < VEC) && (c < D);
 #pragma unroll
     for (int j = 0; j < CONV_MAXW; ++j) {
       const int k = j - (CONV_MAXW - W);
-      wk[j][v] = (ok && k >= 0) ? w[(int64_t)c * W + k] : 0.f;
+      wk[j][v] = (ok && k >= 0) ? __ldg(w + (int64_t)c * W + k) : 0.f;
     }
-    bs[v] = (ok && bias != nullptr) ? bias[c] : 0.f;
+    bs[v] = (ok && bias != nullptr) ? __ldg(bias + c) : 0.f;
   }
 
   // Walk direction: causal -> ascending tokens with history of lower indices;
@@ -51,40 +78,34 @@ conv1d_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
   const T* xb = x + (int64_t)b * L * ldx + c0;
   T* ob = out + (int64_t)b * L * ldo + c0;
 
-  float win[CONV_MAXW][VEC];   // win[j] = x at offset (j - (MAXW-1)) steps "behind" the current token
+  constexpr int NR = CONV_TL + CONV_MAXW - 1;
+  Pair<T> rows[NR];        // rows[j] = x at walk position (j - (MAXW-1)) relative to the first token
 #pragma unroll
-  for (int j = 0; j < CONV_MAXW - 1; ++j) {
-    const int l = l_first - step * (CONV_MAXW - 1 - j);
-    const bool in = (l >= 0 && l < L);
-    if constexpr (VEC == 8) {
-      if (in) { Vec8<T> t; t.load(xb + (int64_t)l * ldx); t.unpack(win[j]); }
-      else {
-#pragma unroll
-        for (int v = 0; v < VEC; ++v) win[j][v] = 0.f;
-      }
-    } else {
-      win[j][0] = (in && c0 < D) ? to_f(xb[(int64_t)l * ldx]) : 0.f;
+  for (int j = 0; j < NR; ++j) {
+    const int pos = j - (CONV_MAXW - 1);                 // < 0: history, >= n: beyond this tile
+    const int l = l_first + step * pos;
+    const bool in = (pos < n) && (l >= 0) && (l < L);
+    rows[j].zero();
+    if (in) {
+      if constexpr (VEC == 2) rows[j].load(xb + (int64_t)l * ldx);
+      else rows[j].set(to_f(xb[(int64_t)l * ldx]), 0.f);      // scalar path: single channel in the low lane
     }
   }
-
-  for (int i = 0; i < n; ++i) {
-    const int l = l_first + step * i;
-    if constexpr (VEC == 8) { Vec8<T> t; t.load(xb + (int64_t)l * ldx); t.unpack(win[CONV_MAXW - 1]); }
-    else win[CONV_MAXW - 1][0] = (c0 < D) ? to_f(xb[(int64_t)l * ldx]) : 0.f;
-    float y[VEC];
 #pragma unroll
-    for (int v = 0; v < VEC; ++v) {
-      float acc = bs[v];
+  for (int i = 0; i < CONV_TL; ++i) {
+    if (i < n) {
+      const int l = l_first + step * i;
+      float a0 = bs[0], a1 = bs[1];
 #pragma unroll
-      for (int j = 0; j < CONV_MAXW; ++j) acc = fmaf(wk[j][v], win[j][v], acc);
-      y[v] = silu ? silu_f(acc) : acc;
+      for (int j = 0; j < CONV_MAXW; ++j) {
+        const float2 f = rows[i + j].f();
+        a0 = fmaf(wk[j][0], f.x, a0);
+        a1 = fmaf(wk[j][1], f.y, a1);
+      }
+      if (silu) { a0 = silu_f(a0); a1 = silu_f(a1); }
+      if constexpr (VEC == 2) Pair<T>::store(ob + (int64_t)l * ldo, a0, a1);
+      else ob[(int64_t)l * ldo] = from_f<T>(a0);
     }
-    if constexpr (VEC == 8) { Vec8<T> t; t.pack(y); t.store(ob + (int64_t)l * ldo); }
-    else if (c0 < D) ob[(int64_t)l * ldo] = from_f<T>(y[0]);
-#pragma unroll
-    for (int j = 0; j < CONV_MAXW - 1; ++j)
-#pragma unroll
-      for (int v = 0; v < VEC; ++v) win[j][v] = win[j + 1][v];
   }
 }
 
@@ -92,11 +113,13 @@ template <typename T>
 static int launch_conv(const void* x, int64_t ldx, const float* w, const float* bias, void* out, int64_t ldo,
                        int batch, int L, int D, int W, int silu, int reverse, cudaStream_t st) {
   const int n_ltile = ceil_div(L, CONV_TL);
-  const bool vec_ok = (D % 8 == 0) && (ldx % 8 == 0) && (ldo % 8 == 0) && aligned16(x) && aligned16(out);
+  const int esz = (int)sizeof(T);
+  const bool vec_ok = (D % 2 == 0) && (ldx % 2 == 0) && (ldo % 2 == 0) &&
+                      (reinterpret_cast<uintptr_t>(x) % (2 * esz) == 0) && (reinterpret_cast<uintptr_t>(out) % (2 * esz) == 0);
   if (vec_ok) {
-    const int n_cvec = D / 8;
+    const int n_cvec = D / 2;
     const int64_t total = (int64_t)batch * n_ltile * n_cvec;
-    conv1d_fwd_kernel<T, 8><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(
+    conv1d_fwd_kernel<T, 2><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(
         (const T*)x, ldx, w, bias, (T*)out, ldo, batch, L, D, W, silu, reverse, n_cvec, n_ltile);
   } else {
     const int n_cvec = D;

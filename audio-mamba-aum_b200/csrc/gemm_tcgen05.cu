@@ -7,11 +7,12 @@
 //               into a STAGES-deep shared-memory ring, completion on "full" mbarriers.
 //   warp 1      allocates TMEM, issues tcgen05.mma (128 x BN x 16, cta_group::1, kind::f16) from one thread;
 //               tcgen05.commit releases smem stages ("empty") and publishes accumulators ("tmem_full").
-//   warps 2..5  epilogue: tcgen05.ld 32x32b (lane == output row) -> registers -> scale/bias/activation ->
-//               16-byte global stores.  TMEM holds two accumulator buffers so the epilogue of tile i
-//               overlaps the MMAs of tile i+1.
+//   warps 2..9  epilogue (two sets of 4 warps): tcgen05.ld 32x32b (lane == output row) -> registers ->
+//               scale/bias/activation -> 128B-swizzled smem slab -> cp.async.bulk.tensor store (TMA).
+//               TMEM holds two accumulator buffers so the epilogue of tile i overlaps the MMAs of tile i+1.
 // M/N/K tails: TMA zero-fills out-of-bounds box elements (K tail adds zeros, M/N tails are masked at store).
 #include <cuda.h>   // CUtensorMap types only; the encode entry point is fetched at run time
+#include <stdlib.h>
 
 #include "gemm_common.cuh"
 
@@ -20,8 +21,10 @@ namespace aum {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;              // 64 x 2 B = 128 B = one swizzle row
 constexpr int TC_UMMA_K = 16;
-constexpr int TC_THREADS = 192;
-constexpr int TC_SMEM_BUDGET = 200 * 1024;
+constexpr int TC_THREADS = 320;             // 2 control warps + 8 epilogue warps
+constexpr int TC_SMEM_BUDGET = 192 * 1024;     // operand ring
+constexpr int TC_CSTAGE_BYTES = 128 * 128;      // one epilogue staging buffer: 128 rows x 128 B (swizzled)
+constexpr int TC_EPI_BAR = 1;                   // named barriers 1,2: the two epilogue warp-sets
 
 template <int BN> struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
@@ -31,7 +34,7 @@ template <int BN> struct TcCfg {
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // TMEM columns / buffer
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * TC_CSTAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
   static_assert(B_BYTES % 1024 == 0, "W tile must keep 1024-byte stage alignment");
 };
@@ -69,6 +72,29 @@ __device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm,
   asm volatile(
       "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
       ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void tma_store_2d(const CUtensorMap* tm, uint32_t src, int c0, int c1) {
+  asm volatile("cp.async.bulk.tensor.2d.global.shared::cta.bulk_group [%0, {%1, %2}], [%3];"
+               ::"l"(tm), "r"(c0), "r"(c1), "r"(src) : "memory");
+}
+__device__ __forceinline__ void tma_store_commit() { asm volatile("cp.async.bulk.commit_group;" ::: "memory"); }
+template <int N> __device__ __forceinline__ void tma_store_wait_read() {
+  asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void epi_barrier(int set) { asm volatile("bar.sync %0, %1;" ::"r"(TC_EPI_BAR + set), "n"(128) : "memory"); }
+// softplus for the dt_proj epilogue: ~10 instructions, relative error < 1e-5 over the whole range
+// (log1p series below t = 0.01 where 1 + t would lose the low bits; matches torch's threshold-20 semantics)
+__device__ __forceinline__ float softplus_fast(float x) {
+  if (x > 20.f) return x;
+  const float t = __expf(x);
+  return t < 0.01f ? t * (1.f - t * (0.5f - t * 0.33333334f)) : __logf(1.f + t);
+}
+__device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
+  asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
+}
+__device__ __forceinline__ uint32_t pack_h2(float lo, float hi, int dt) {
+  if (dt == AUM_F16) { __half2 h = __floats2half2_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h); }
+  __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); return *reinterpret_cast<uint32_t*>(&h);
 }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_after()  { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
@@ -110,13 +136,15 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
 template <int BN>
 __global__ void __launch_bounds__(TC_THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                    const __grid_constant__ CUtensorMap tmC, int tma_store,
                     EpiParams ep, int M, int N, int K, uint32_t idesc) {
   using Cfg = TcCfg<BN>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128-byte swizzle atoms
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t cstage_base = smem_base + STAGES * Cfg::STAGE_BYTES;     // 2 x 16 KB, 1024-aligned
+  const uint32_t bar_base = cstage_base + 2 * TC_CSTAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -130,7 +158,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -191,34 +219,97 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     __syncwarp();
   } else {
-    // ================= epilogue warps (2..5) =================
+    // ================= epilogue warps (2..9): two independent sets of 4 warps =================
+    // Each set covers all 128 accumulator rows (one warp per TMEM lane quarter) and takes every other
+    // 128-byte-wide column slab of the tile; it owns one staging buffer, one named barrier and one store thread.
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
+    const int set = (warp - 2) >> 2;                // 0 or 1
+    const bool store_thread = (lane == 0) && (((warp - 2) & 3) == 0);
+    const bool has_bias = ep.bias != nullptr, has_rs = ep.row_scale != nullptr;
+    const int act = ep.act;
+    const bool plain = !has_bias && !has_rs && act == AUM_ACT_NONE;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row = m0 + q * 32 + lane;
-      const float rs = (ep.row_scale != nullptr && row < M) ? __ldg(ep.row_scale + row) : 1.f;
+      const int row_in_tile = q * 32 + lane;
+      const int row = m0 + row_in_tile;
+      const float rs = (has_rs && row < M) ? __ldg(ep.row_scale + row) : 1.f;
       const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_STRIDE);
+      if (tma_store) {
+        // TMEM -> registers -> (scale, bias, activation) -> convert -> 128B-swizzled smem slab -> TMA store
+        const int c_sz = (ep.c_dt == AUM_F32) ? 4 : 2;
+        const int slab_cols = 128 / c_sz;            // 64 16-bit or 32 fp32 columns
+        const uint32_t buf = cstage_base + (uint32_t)set * TC_CSTAGE_BYTES;
+        const uint32_t srow = buf + (uint32_t)row_in_tile * 128u;
+        const uint32_t sw = (uint32_t)(row_in_tile & 7);
 #pragma unroll 1
-      for (int c0 = 0; c0 < BN; c0 += 32) {
-        if (n0 + c0 >= N) break;                     // warp-uniform
-        uint32_t r[32];
-        tc_ld_32x32b_x32(t_row + (uint32_t)c0, r);
-        tc_wait_ld();
+        for (int c0 = set * slab_cols; c0 < BN; c0 += 2 * slab_cols) {
+          if (n0 + c0 >= N) break;                   // warp-uniform
+          if (store_thread) tma_store_wait_read<0>();   // this set's previous store has drained its buffer
+          epi_barrier(set);
+#pragma unroll 1
+          for (int cc = 0; cc < slab_cols; cc += 32) {
+            uint32_t r[32];
+            tc_ld_32x32b_x32(t_row + (uint32_t)(c0 + cc), r);
+            tc_wait_ld();
+            if (!plain) {
+              const int colb = n0 + c0 + cc;
 #pragma unroll
-        for (int g = 0; g < 4; ++g) {
-          float v[8];
+              for (int i = 0; i < 32; ++i) {
+                float v = __uint_as_float(r[i]);
+                if (has_rs) v *= rs;
+                if (has_bias) v += (colb + i < N) ? __ldg(ep.bias + colb + i) : 0.f;
+                if (act == AUM_ACT_SOFTPLUS) v = softplus_fast(v);
+                r[i] = __float_as_uint(v);
+              }
+            }
+            if (c_sz == 4) {
 #pragma unroll
-          for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-          epi_store8(ep, row, n0 + c0 + g * 8, v, rs);
+              for (int k = 0; k < 8; ++k)            // 8 chunks of 4 floats (slab_cols == 32: cc == 0)
+                st_shared_v4(srow + ((((uint32_t)k) ^ sw) << 4), r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+            } else {
+              const bool f16 = ep.c_dt == AUM_F16;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {          // 4 chunks of 8 halves per 32 columns
+                uint32_t pk[4];
+#pragma unroll
+                for (int j = 0; j < 4; ++j) {
+                  const float lo = __uint_as_float(r[8 * k + 2 * j]), hi = __uint_as_float(r[8 * k + 2 * j + 1]);
+                  if (f16) { __half2 h = __floats2half2_rn(lo, hi); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
+                  else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
+                }
+                st_shared_v4(srow + ((((uint32_t)((cc >> 3) + k)) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+              }
+            }
+          }
+          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+          epi_barrier(set);
+          if (store_thread) { tma_store_2d(&tmC, buf, n0 + c0, m0); tma_store_commit(); }
+        }
+      } else {
+        // per-thread vector stores (split outputs, odd pitches): each set takes alternate 32-column chunks
+#pragma unroll 1
+        for (int c0 = set * 32; c0 < BN; c0 += 64) {
+          if (n0 + c0 >= N) break;                     // warp-uniform
+          uint32_t r[32];
+          tc_ld_32x32b_x32(t_row + (uint32_t)c0, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+            epi_store8(ep, row, n0 + c0 + g * 8, v, rs);
+          }
         }
       }
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
     }
+    if (tma_store && store_thread) tma_store_wait_read<0>();   // smem must outlive the last bulk store
   }
 
   tc_fence_before();
@@ -246,6 +337,23 @@ static PFN_encodeTiled get_encode() {
       fn = (PFN_encodeTiled)p;
   }
   return fn;
+}
+
+// 2-D tensor map of the output [M, N] (row pitch ldc elements) for the TMA-store epilogue: box = 128 rows x 128 B.
+static int make_tmap_out(CUtensorMap* tm, const void* base, int64_t M, int64_t N, int64_t ldc, int dt) {
+  PFN_encodeTiled enc = get_encode();
+  if (!enc) { set_error("aum_gemm_tn: cuTensorMapEncodeTiled unavailable (driver too old?)"); return 3; }
+  const int sz = dtype_size(dt);
+  cuuint64_t gdim[2] = {(cuuint64_t)N, (cuuint64_t)M};
+  cuuint64_t gstr[1] = {(cuuint64_t)ldc * sz};
+  cuuint32_t box[2] = {(cuuint32_t)(128 / sz), (cuuint32_t)TC_BM};
+  cuuint32_t estr[2] = {1, 1};
+  CUtensorMapDataType t = dt == AUM_F32 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT32
+                        : dt == AUM_F16 ? CU_TENSOR_MAP_DATA_TYPE_FLOAT16 : CU_TENSOR_MAP_DATA_TYPE_BFLOAT16;
+  CUresult r = enc(tm, t, 2, const_cast<void*>(base), gdim, gstr, box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE,
+                   CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_NONE, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (r != CUDA_SUCCESS) { set_error("aum_gemm_tn: cuTensorMapEncodeTiled(out) failed (%d) M=%lld N=%lld ldc=%lld", (int)r, (long long)M, (long long)N, (long long)ldc); return 3; }
+  return 0;
 }
 
 // 2-D tensor map over a K-contiguous [rows, K] matrix with row pitch ld (elements); box = [box_rows x 64].
@@ -277,8 +385,12 @@ template <int BN>
 static int launch_bn(const CUtensorMap& tmA, const void* W, int64_t ldw, int ab_dt, const EpiParams& ep,
                      int M, int N, int K, cudaStream_t st) {
   using Cfg = TcCfg<BN>;
-  CUtensorMap tmW;
+  CUtensorMap tmW, tmC;
   if (int rc = make_tmap(&tmW, W, N, K, ldw, BN, ab_dt)) return rc;
+  // TMA-store epilogue when there is a single, 16-byte-pitched output; otherwise per-thread vector stores
+  int tma_store = (ep.C2 == nullptr && ep.vec_ok && BN >= 64 && getenv("AUM_GEMM_DIRECT_STORE") == nullptr) ? 1 : 0;
+  if (tma_store) { if (int rc = make_tmap_out(&tmC, ep.C, M, N, ep.ldc, ep.c_dt)) return rc; }
+  else tmC = tmW;
   static bool attr_set = false;
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
@@ -294,7 +406,7 @@ static int launch_bn(const CUtensorMap& tmA, const void* W, int64_t ldw, int ab_
                        | ((uint32_t)(TC_BM >> 4) << 24);  // M >> 4
   const int tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
   const int grid = tiles < g_sm_count ? tiles : g_sm_count;
-  gemm_tcgen05_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, ep, M, N, K, idesc);
+  gemm_tcgen05_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, tmC, tma_store, ep, M, N, K, idesc);
   return check_launch("aum_gemm_tn(tcgen05)");
 }
 

@@ -11,11 +11,11 @@ namespace aum {
 
 constexpr int RN_MAXC = 8;   // 8 chunks * 32 lanes * 8 elems = dim <= 2048 on the vector path
 
-template <typename T, typename RT>
+template <typename T, typename TY, typename RT>
 __global__ void __launch_bounds__(256)
 add_rmsnorm_vec_kernel(const T* __restrict__ x, int64_t ldx, const RT* __restrict__ rin, int64_t ldr,
                        const float* __restrict__ weight, const float* __restrict__ bias,
-                       T* __restrict__ y, int64_t ldy, RT* __restrict__ rout, int64_t ldro,
+                       TY* __restrict__ y, int64_t ldy, RT* __restrict__ rout, int64_t ldro,
                        float* __restrict__ rstd_out, int rows, int dim, float eps) {
   const int warp = (int)(((int64_t)blockIdx.x * blockDim.x + threadIdx.x) >> 5);
   const int lane = threadIdx.x & 31;
@@ -59,7 +59,7 @@ add_rmsnorm_vec_kernel(const T* __restrict__ x, int64_t ldx, const RT* __restric
 #pragma unroll
         for (int i = 0; i < 8; ++i) o[i] += bf[i];
       }
-      Vec8<T> t; t.pack(o); t.store(y + (int64_t)warp * ldy + ch * 8);
+      Vec8<TY> t; t.pack(o); t.store(y + (int64_t)warp * ldy + ch * 8);
     }
   }
 }
@@ -100,13 +100,13 @@ add_rmsnorm_generic_kernel(const void* x, int64_t ldx, int x_dt, const void* rin
   }
 }
 
-template <typename T>
+template <typename T, typename TY>
 static void launch_vec(const void* x, int64_t ldx, const void* rin, int64_t ldr, const float* w, const float* b,
                        void* y, int64_t ldy, void* rout, int64_t ldro, float* rstd, int rows, int dim, float eps,
                        cudaStream_t st) {
   const int warps_per_block = 8;
-  add_rmsnorm_vec_kernel<T, float><<<ceil_div(rows, warps_per_block), warps_per_block * 32, 0, st>>>(
-      (const T*)x, ldx, (const float*)rin, ldr, w, b, (T*)y, ldy, (float*)rout, ldro, rstd, rows, dim, eps);
+  add_rmsnorm_vec_kernel<T, TY, float><<<ceil_div(rows, warps_per_block), warps_per_block * 32, 0, st>>>(
+      (const T*)x, ldx, (const float*)rin, ldr, w, b, (TY*)y, ldy, (float*)rout, ldro, rstd, rows, dim, eps);
 }
 
 }  // namespace aum
@@ -123,19 +123,21 @@ extern "C" int aum_add_rmsnorm_fwd(const void* x, int64_t ldx, int x_dtype,
   AUM_REQUIRE(ldx >= dim && ldy >= dim, "aum_add_rmsnorm_fwd: leading dimension smaller than dim");
   if (rows == 0) return 0;
   cudaStream_t st = (cudaStream_t)stream;
-  const bool vec_ok = (dim % 8 == 0) && dim <= 8 * 32 * RN_MAXC && x_dtype == y_dtype &&
+  const bool vec_ok = (dim % 8 == 0) && dim <= 8 * 32 * RN_MAXC && (x_dtype == y_dtype || x_dtype == AUM_F32) &&
                       (!residual_in || r_dtype == AUM_F32) && (!residual_out || ro_dtype == AUM_F32) &&
                       ldx % 8 == 0 && ldy % 8 == 0 && (!residual_in || ldr % 8 == 0) &&
                       (!residual_out || ldro % 8 == 0) && aligned16(x) && aligned16(y) &&
                       aligned16(weight) && (!bias || aligned16(bias)) &&
                       (!residual_in || aligned16(residual_in)) && (!residual_out || aligned16(residual_out));
   if (vec_ok) {
-    switch (x_dtype) {
-      case AUM_F32:  launch_vec<float>(x, ldx, residual_in, ldr, weight, bias, y, ldy, residual_out, ldro, rstd_out, rows, dim, eps, st); break;
-      case AUM_F16:  launch_vec<__half>(x, ldx, residual_in, ldr, weight, bias, y, ldy, residual_out, ldro, rstd_out, rows, dim, eps, st); break;
-      case AUM_BF16: launch_vec<__nv_bfloat16>(x, ldx, residual_in, ldr, weight, bias, y, ldy, residual_out, ldro, rstd_out, rows, dim, eps, st); break;
-      default: set_error("aum_add_rmsnorm_fwd: bad dtype %d", x_dtype); return 1;
-    }
+#define AUM_RN_ARGS x, ldx, residual_in, ldr, weight, bias, y, ldy, residual_out, ldro, rstd_out, rows, dim, eps, st
+    if (x_dtype == AUM_F32 && y_dtype == AUM_F32) launch_vec<float, float>(AUM_RN_ARGS);
+    else if (x_dtype == AUM_F32 && y_dtype == AUM_F16) launch_vec<float, __half>(AUM_RN_ARGS);
+    else if (x_dtype == AUM_F32 && y_dtype == AUM_BF16) launch_vec<float, __nv_bfloat16>(AUM_RN_ARGS);
+    else if (x_dtype == AUM_F16) launch_vec<__half, __half>(AUM_RN_ARGS);
+    else if (x_dtype == AUM_BF16) launch_vec<__nv_bfloat16, __nv_bfloat16>(AUM_RN_ARGS);
+    else { set_error("aum_add_rmsnorm_fwd: bad dtype %d", x_dtype); return 1; }
+#undef AUM_RN_ARGS
   } else {
     add_rmsnorm_generic_kernel<<<rows, 256, 0, st>>>(x, ldx, x_dtype, residual_in, ldr, r_dtype, weight, bias,
                                                      y, ldy, y_dtype, residual_out, ldro, ro_dtype, rstd_out,
