@@ -1,0 +1,337 @@
+// Selective scan forward, both time directions in one launch — TMA-streamed kernel (the production path).
+//
+// Same math and the same two-directions-one-pass scheme as scan_fwd.cu (see there for the reference citations:
+// selective_scan_interface.py:37,213,354,499,503-507 and selective_scan_ref :86-152); what changes is how the
+// operands reach the math:
+//   * grid = (ceil(D/128), batch); a CTA owns 128 channels of one sequence; 4 warps walk it forwards and, in
+//     the bidirectional case, 4 more warps walk it backwards (one thread per channel and direction, the 16
+//     recurrences of the channel in registers as 8 packed fp32x2 pairs, FMUL2/FFMA2 + ex2.approx).
+//   * every per-token operand is fetched by the TMA unit into a 4-stage shared-memory ring per direction:
+//     per 8-token tile one cp.async.bulk.tensor 2-D box each for u, delta (and z once the walk is in its
+//     finalising half) plus one 1-D bulk copy of the packed fp32 [B|C] rows, all completing on the stage's
+//     "full" mbarrier; warps hand stages back through an "empty" mbarrier and one elected thread refills them
+//     one tile late, so 2-3 tiles (16-24 tokens) of loads are always in flight and the math warps never touch
+//     a global-load scoreboard for them.
+//   * the partial y of the first half-walk is parked in `out` exactly as in the generic kernel; the second
+//     half reads it back through an 8-deep register ring (plain loads: CTA-scope visibility after bar.sync).
+// Eligibility (checked in launch_scan_tma): d_state == 16, packed fp32 [B|C] rows, fp32 delta without
+// bias/softplus left to apply, 16-byte aligned bases and row pitches.  Anything else runs scan_fwd.cu.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "scan_common.cuh"
+#include "tma.cuh"
+
+namespace aum {
+
+constexpr int ST_CH = 128;    // channels per CTA
+constexpr int ST_TT = 8;      // tokens per tile
+constexpr int ST_NSTG = 4;    // ring depth per direction
+
+template <typename T> struct StageLayout {
+  static constexpr int U_BYTES = ST_TT * ST_CH * (int)sizeof(T);
+  static constexpr int D_BYTES = ST_TT * ST_CH * 4;
+  static constexpr int Z_BYTES = U_BYTES;
+  static constexpr int BC_BYTES = ST_TT * SCAN_ROW * 4;
+  static constexpr int OFF_U = 0, OFF_D = OFF_U + U_BYTES, OFF_Z = OFF_D + D_BYTES, OFF_BC = OFF_Z + Z_BYTES;
+  static constexpr int STAGE_BYTES = OFF_BC + BC_BYTES;
+  static constexpr int GROUP_BYTES = ST_NSTG * STAGE_BYTES;
+  static constexpr int SMEM_BYTES = 2 * GROUP_BYTES + 128 /*align slack*/ + 2 * 2 * ST_NSTG * 8 /*mbarriers*/;
+};
+
+struct ScanTmaMaps { CUtensorMap u[2], d[2], z; };
+
+__device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap* tm, int col, int row, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tm), "r"(col), "r"(row), "r"(bar) : "memory");
+}
+__device__ __forceinline__ void sbar_arrive(uint32_t bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ float lds_f(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float4 lds_f4(uint32_t a) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+template <typename T> __device__ __forceinline__ float lds_t(uint32_t a);
+template <> __device__ __forceinline__ float lds_t<float>(uint32_t a) { return lds_f(a); }
+template <> __device__ __forceinline__ float lds_t<__half>(uint32_t a) {
+  unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return __half2float(__ushort_as_half(v));
+}
+template <> __device__ __forceinline__ float lds_t<__nv_bfloat16>(uint32_t a) {
+  unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return __uint_as_float(((uint32_t)v) << 16);
+}
+
+// One recurrence step of one channel: consumes (u, delta') and the staged B|C row at `a_bc`, returns y (+D u).
+__device__ __forceinline__ float scan_step(float u, float dl, uint32_t a_bc, float Dv,
+                                           f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2]) {
+  const float du = dl * u;
+  const f32x2 dl2 = pk2(dl, dl), du2 = pk2(du, du);
+  f32x2 ya = pk2(Dv * u, 0.f), yb = pk2(0.f, 0.f);
+#pragma unroll
+  for (int q = 0; q < SCAN_NS / 4; ++q) {
+    const float4 Bv = lds_f4(a_bc + 16u * q);
+    const float4 Cv = lds_f4(a_bc + 16u * (SCAN_NS / 4 + q));
+    const f32x2 x0 = mul2(dl2, a2[2 * q]), x1 = mul2(dl2, a2[2 * q + 1]);
+    float e0, e1, e2, e3;
+    upk2(x0, e0, e1); upk2(x1, e2, e3);
+    const f32x2 dA0 = pk2(ex2_approx(e0), ex2_approx(e1));
+    const f32x2 dA1 = pk2(ex2_approx(e2), ex2_approx(e3));
+    h[2 * q] = fma2(dA0, h[2 * q], mul2(du2, pk2(Bv.x, Bv.y)));
+    h[2 * q + 1] = fma2(dA1, h[2 * q + 1], mul2(du2, pk2(Bv.z, Bv.w)));
+    ya = fma2(h[2 * q], pk2(Cv.x, Cv.y), ya);
+    yb = fma2(h[2 * q + 1], pk2(Cv.z, Cv.w), yb);
+  }
+  float y0, y1, y2, y3;
+  upk2(ya, y0, y1); upk2(yb, y2, y3);
+  return (y0 + y1) + (y2 + y3);
+}
+
+// A full 8-step tile, unguarded and fully unrolled.  po: output row of step 0 of the tile; ostep: signed row
+// stride (elements) in walk direction.  PARTIAL: pring[t] holds the parked partial of step t and is refilled
+// with step t+8 (if it exists) right after use.
+template <typename T, bool FIN, bool PARTIAL, bool HASZ>
+__device__ __forceinline__ void scan_tile_full(uint32_t a_u, uint32_t a_d, uint32_t a_z, uint32_t a_bc,
+                                               int su, int sd, int sbc, float Dv, float oscale, bool active,
+                                               f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2],
+                                               float (&pring)[ST_TT], T* po, ptrdiff_t ostep, int steps_left_after_tile) {
+#pragma unroll
+  for (int t = 0; t < ST_TT; ++t) {
+    float y = scan_step(lds_t<T>(a_u), lds_f(a_d), a_bc, Dv, h, a2);
+    if (FIN) {
+      if (PARTIAL) {
+        y += pring[t];
+        if (t < steps_left_after_tile) pring[t] = to_f(po[ST_TT * ostep]);   // step t+8 of the walk
+      }
+      if (HASZ) y *= silu_f(lds_t<T>(a_z));
+      y *= oscale;
+    }
+    if (active) *po = from_f<T>(y);
+    po += ostep;
+    a_u += su; a_d += sd; a_bc += sbc;
+    if (FIN && HASZ) a_z += su;
+  }
+}
+
+// A short tile (first tile of the walk or its last): rolled loop, parked partials read directly.
+template <typename T>
+__device__ __forceinline__ void scan_tile_tail(int nt, bool fin, bool partial, bool has_z,
+                                               uint32_t a_u, uint32_t a_d, uint32_t a_z, uint32_t a_bc,
+                                               int su, int sd, int sbc, float Dv, float oscale, bool active,
+                                               f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2],
+                                               T* po, ptrdiff_t ostep) {
+#pragma unroll 1
+  for (int t = 0; t < nt; ++t) {
+    float y = scan_step(lds_t<T>(a_u), lds_f(a_d), a_bc, Dv, h, a2);
+    if (fin) {
+      if (partial) y += to_f(*po);
+      if (has_z) y *= silu_f(lds_t<T>(a_z));
+      y *= oscale;
+    }
+    if (active) *po = from_f<T>(y);
+    po += ostep;
+    a_u += su; a_d += sd; a_z += su; a_bc += sbc;
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(2 * ST_CH, 2)
+scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p) {
+  using SL = StageLayout<T>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (s_u32(smem_raw) + 127u) & ~127u;
+
+  const int g = threadIdx.x / ST_CH;           // direction slot
+  const int tig = threadIdx.x - g * ST_CH;
+  const int warp_in_group = tig >> 5, lane = tig & 31;
+  const ScanDirDev& d = p.dir[g];
+  const int ch_raw = blockIdx.x * ST_CH + tig;
+  const bool active = ch_raw < p.Dch;
+  const int ch = active ? ch_raw : (p.Dch - 1);
+  const int b = blockIdx.y;
+  const int L = p.L;
+  const bool bidir = p.ndirs == 2;
+  const bool rev = d.reverse != 0;
+  const int row0 = b * L;
+  const bool has_z = p.z != nullptr;
+
+  const uint32_t ring = smem0 + (uint32_t)g * SL::GROUP_BYTES;
+  const uint32_t bars = smem0 + 2u * SL::GROUP_BYTES + (uint32_t)g * (2 * ST_NSTG * 8);
+  auto full_bar = [&](int s) { return bars + 8u * s; };
+  auto empty_bar = [&](int s) { return bars + 8u * (ST_NSTG + s); };
+
+  if (tig == 0) {
+    for (int s = 0; s < ST_NSTG; ++s) { sbar_init(full_bar(s), 1); sbar_init(empty_bar(s), ST_CH / 32); }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  // ---- tiling of this direction's walk.  Steps s = 0..L-1 (token l = rev ? L-1-s : s).
+  // Phase 1 = steps [0,S1) park partials, phase 2 = steps [S1,L) finalise; the first tile is shortened so that
+  // S1 falls on a tile boundary.
+  const int mid = L / 2;
+  const int S1 = bidir ? (rev ? (L - mid) : mid) : 0;
+  const int first = (S1 % ST_TT) ? (S1 % ST_TT) : ST_TT;          // length of tile 0 when S1 > 0
+  const int n1t = S1 > 0 ? 1 + (S1 - first + ST_TT - 1) / ST_TT : 0;
+  const int n2t = (L - S1 + ST_TT - 1) / ST_TT;
+  const int ntiles = n1t + n2t;
+  auto tile_range = [&](int k, int& s0, int& nt) {
+    if (k < n1t) { s0 = k == 0 ? 0 : first + (k - 1) * ST_TT; nt = k == 0 ? min(first, S1) : min(ST_TT, S1 - s0); }
+    else { s0 = S1 + (k - n1t) * ST_TT; nt = min(ST_TT, L - s0); }
+  };
+
+  // ---- producer: one elected thread per direction
+  auto issue_tile = [&](int k) {
+    int s0, nt; tile_range(k, s0, nt);
+    const int stage = k % ST_NSTG;
+    const uint32_t st = ring + (uint32_t)stage * SL::STAGE_BYTES;
+    const uint32_t bar = full_bar(stage);
+    const bool fin = k >= n1t;
+    // box rows: forward [row0+s0, +TT); reverse [row0+L-s0-TT, +TT) so that step t sits at box row TT-1-t
+    const int brow = rev ? (row0 + L - s0 - ST_TT) : (row0 + s0);
+    const uint32_t bc_bytes = (uint32_t)nt * SCAN_ROW * 4u;
+    const uint32_t tx = SL::U_BYTES + SL::D_BYTES + ((fin && has_z) ? SL::Z_BYTES : 0) + bc_bytes;
+    sbar_expect_tx(bar, tx);
+    const int col = blockIdx.x * ST_CH;
+    tma_tile_2d(st + SL::OFF_U, &maps.u[g], col, brow, bar);
+    tma_tile_2d(st + SL::OFF_D, &maps.d[g], col, brow, bar);
+    if (fin && has_z) tma_tile_2d(st + SL::OFF_Z, &maps.z, col, brow, bar);
+    // packed [B|C] rows: only the nt valid rows, placed so that step t reads row (rev ? TT-1-t : t)
+    const int bc_row_lo = rev ? (L - s0 - nt) : s0;
+    const float* src = reinterpret_cast<const float*>(d.Bm) + (int64_t)(row0 + bc_row_lo) * SCAN_ROW;
+    const uint32_t dst = st + SL::OFF_BC + (rev ? (uint32_t)(ST_TT - nt) * SCAN_ROW * 4u : 0u);
+    bulk_g2s(dst, src, bc_bytes, bar);
+  };
+  if (tig == 0) {
+    for (int k = 0; k < ST_NSTG && k < ntiles; ++k) issue_tile(k);
+  }
+
+  // ---- per-channel constants
+  f32x2 a2[SCAN_NS / 2], h[SCAN_NS / 2];
+  {
+    const float4* ap = reinterpret_cast<const float4*>(d.A + (int64_t)ch * SCAN_NS);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = __ldg(ap + i);
+      a2[2 * i] = pk2(v.x * 1.4426950408889634f, v.y * 1.4426950408889634f);
+      a2[2 * i + 1] = pk2(v.z * 1.4426950408889634f, v.w * 1.4426950408889634f);
+    }
+#pragma unroll
+    for (int k = 0; k < SCAN_NS / 2; ++k) h[k] = pk2(0.f, 0.f);
+  }
+  const float Dv = d.D ? __ldg(d.D + ch) : 0.f;
+  const float oscale = p.out_scale;
+  const int ldo = (int)p.ld_out;
+  T* ob = reinterpret_cast<T*>(p.out) + ch;
+  const ptrdiff_t ostep = rev ? -(ptrdiff_t)ldo : (ptrdiff_t)ldo;
+  const int su = rev ? -(int)(ST_CH * sizeof(T)) : (int)(ST_CH * sizeof(T));
+  const int sd = rev ? -(ST_CH * 4) : (ST_CH * 4);
+  const int sbc = rev ? -(SCAN_ROW * 4) : (SCAN_ROW * 4);
+
+  float pring[ST_TT];                      // parked partials of the next 8 finalising steps
+#pragma unroll
+  for (int i = 0; i < ST_TT; ++i) pring[i] = 0.f;
+
+  for (int k = 0; k < ntiles; ++k) {
+    int s0, nt; tile_range(k, s0, nt);
+    const int stage = k % ST_NSTG;
+    const uint32_t st = ring + (uint32_t)stage * SL::STAGE_BYTES;
+    const bool fin = k >= n1t;
+    const bool partial = fin && bidir;
+    if (bidir && k == n1t) {
+      __syncthreads();                     // every partial of both directions is parked
+    }
+    const int r = row0 + (rev ? (L - 1 - s0) : s0);    // global row of step s0
+    T* po = ob + (int64_t)r * ldo;
+    if (partial && k == n1t) {             // prime the ring with the first 8 finalising steps
+#pragma unroll
+      for (int i = 0; i < ST_TT; ++i)
+        if (s0 + i < L) pring[i] = to_f(po[i * ostep]);
+    }
+    sbar_wait(full_bar(stage), (uint32_t)((k / ST_NSTG) & 1));
+
+    // addresses inside the stage for this thread's channel; step t lives at tile row (rev ? TT-1-t : t)
+    const int row_first = rev ? (ST_TT - 1) : 0;
+    const uint32_t a_u = st + SL::OFF_U + (uint32_t)(row_first * ST_CH + tig) * (uint32_t)sizeof(T);
+    const uint32_t a_d = st + SL::OFF_D + (uint32_t)(row_first * ST_CH + tig) * 4u;
+    const uint32_t a_z = st + SL::OFF_Z + (uint32_t)(row_first * ST_CH + tig) * (uint32_t)sizeof(T);
+    const uint32_t a_bc = st + SL::OFF_BC + (uint32_t)row_first * SCAN_ROW * 4u;
+    if (nt == ST_TT) {
+      const int left = L - (s0 + ST_TT);   // steps of the walk after this tile (ring refills stop there)
+#define AUM_TILE(F, P, Z) scan_tile_full<T, F, P, Z>(a_u, a_d, a_z, a_bc, su, sd, sbc, Dv, oscale, active, h, a2, pring, po, ostep, left)
+      if (!fin) AUM_TILE(false, false, false);
+      else if (partial) { if (has_z) AUM_TILE(true, true, true); else AUM_TILE(true, true, false); }
+      else { if (has_z) AUM_TILE(true, false, true); else AUM_TILE(true, false, false); }
+#undef AUM_TILE
+    } else {
+      scan_tile_tail<T>(nt, fin, partial, has_z, a_u, a_d, a_z, a_bc, su, sd, sbc, Dv, oscale, active, h, a2, po, ostep);
+    }
+
+    // hand the stage back; one thread refills the stage released one tile earlier
+    __syncwarp();
+    if (lane == 0) sbar_arrive(empty_bar(stage));
+    if (tig == 0 && k >= 1) {
+      const int kk = k - 1 + ST_NSTG;                 // tile that reuses the stage of tile k-1
+      if (kk < ntiles) {
+        sbar_wait(empty_bar((k - 1) % ST_NSTG), (uint32_t)(((k - 1) / ST_NSTG) & 1));
+        issue_tile(kk);
+      }
+    }
+    (void)warp_in_group;
+  }
+  if (bidir && n2t == 0) __syncthreads();   // (degenerate) keep the CTA barrier count equal across directions
+
+  if (active && d.last_state != nullptr) {
+#pragma unroll
+    for (int k = 0; k < SCAN_NS / 2; ++k) {
+      float lo, hi; upk2(h[k], lo, hi);
+      d.last_state[((int64_t)b * p.Dch + ch) * SCAN_NS + 2 * k] = lo;
+      d.last_state[((int64_t)b * p.Dch + ch) * SCAN_NS + 2 * k + 1] = hi;
+    }
+  }
+}
+
+template <typename T>
+static int launch_t(const ScanTmaMaps& maps, const ScanParams& p, cudaStream_t st) {
+  using SL = StageLayout<T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("aum_selective_scan_fwd: cudaFuncSetAttribute(smem=%d): %s", SL::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p.Dch, ST_CH), p.batch);
+  scan_fwd_tma_kernel<T><<<grid, ST_CH * p.ndirs, SL::SMEM_BYTES, st>>>(maps, p);
+  return check_launch("aum_selective_scan_fwd(tma)");
+}
+
+int launch_scan_tma(const ScanParams& p, int dtype, int delta_dt, cudaStream_t st) {
+  if (p.N != SCAN_NS || delta_dt != AUM_F32 || !tma_available()) return -1;
+  const int esz = dtype_size(dtype);
+  auto ok_mat = [](const void* base, int64_t ld, int sz) { return aligned16(base) && (ld * sz) % 16 == 0; };
+  if (!ok_mat(p.out, p.ld_out, esz) || p.ld_out * esz % 2 != 0) return -1;
+  if (p.z && !ok_mat(p.z, p.ld_z, esz)) return -1;
+  for (int g = 0; g < p.ndirs; ++g) {
+    const ScanDirDev& d = p.dir[g];
+    if (!d.bc_packed || d.delta_softplus || d.delta_bias != nullptr) return -1;
+    if (!ok_mat(d.u, d.ld_u, esz) || !ok_mat(d.delta, d.ld_delta, 4) || !aligned16(d.A)) return -1;
+  }
+  ScanTmaMaps maps;
+  const int64_t rows = (int64_t)p.batch * p.L;
+  for (int g = 0; g < 2; ++g) {
+    const ScanDirDev& d = p.dir[g < p.ndirs ? g : 0];
+    if (int rc = tma_encode_2d(&maps.u[g], d.u, dtype, rows, p.Dch, d.ld_u, ST_TT, ST_CH, false, "aum_selective_scan_fwd(u)")) return rc;
+    if (int rc = tma_encode_2d(&maps.d[g], d.delta, AUM_F32, rows, p.Dch, d.ld_delta, ST_TT, ST_CH, false, "aum_selective_scan_fwd(delta)")) return rc;
+  }
+  if (p.z) { if (int rc = tma_encode_2d(&maps.z, p.z, dtype, rows, p.Dch, p.ld_z, ST_TT, ST_CH, false, "aum_selective_scan_fwd(z)")) return rc; }
+  else maps.z = maps.u[0];
+  switch (dtype) {
+    case AUM_F32:  return launch_t<float>(maps, p, st);
+    case AUM_F16:  return launch_t<__half>(maps, p, st);
+    case AUM_BF16: return launch_t<__nv_bfloat16>(maps, p, st);
+  }
+  return -1;
+}
+
+}  // namespace aum
