@@ -92,7 +92,7 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
 
 
 def _autocast_dtype(x: torch.Tensor) -> torch.dtype:
-    return torch.get_autocast_gpu_dtype() if torch.is_autocast_enabled() else x.dtype
+    return torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
 
 
 class _P:

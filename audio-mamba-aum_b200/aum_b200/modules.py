@@ -90,7 +90,7 @@ class Mamba(nn.Module):
             return mamba_mixer_autograd(self, hidden_states)
         x = hidden_states
         if torch.is_autocast_enabled():
-            x = x.to(torch.get_autocast_gpu_dtype())
+            x = x.to(torch.get_autocast_dtype("cuda"))
         return mixer.mamba_mixer_forward(self, x)
 
     def step(self, hidden_states, conv_state, ssm_state):

@@ -134,8 +134,8 @@ __device__ __forceinline__ void scan_tile_tail(int nt, bool fin, bool partial, b
   }
 }
 
-template <typename T>
-__global__ void __launch_bounds__(2 * ST_CH, 2)
+template <typename T, int MINB>
+__global__ void __launch_bounds__(2 * ST_CH, MINB)
 scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p) {
   using SL = StageLayout<T>;
   extern __shared__ uint8_t smem_raw[];
@@ -296,13 +296,18 @@ template <typename T>
 static int launch_t(const ScanTmaMaps& maps, const ScanParams& p, cudaStream_t st) {
   using SL = StageLayout<T>;
   static bool attr_set = false;
+  static int occ = 3;       // resident CTAs per SM the kernel is compiled for (2: 128 regs, 3: 80 regs)
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
+    if (const char* e = getenv("AUM_SCAN_OCC")) { const int v = atoi(e); if (v == 2 || v == 3) occ = v; }
+    if (sizeof(T) == 4) occ = 2;        // fp32 stages are too large for three CTAs per SM
+    cudaError_t e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("aum_selective_scan_fwd: cudaFuncSetAttribute(smem=%d): %s", SL::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
     attr_set = true;
   }
   dim3 grid(ceil_div(p.Dch, ST_CH), p.batch);
-  scan_fwd_tma_kernel<T><<<grid, ST_CH * p.ndirs, SL::SMEM_BYTES, st>>>(maps, p);
+  if (occ == 3) scan_fwd_tma_kernel<T, 3><<<grid, ST_CH * p.ndirs, SL::SMEM_BYTES, st>>>(maps, p);
+  else scan_fwd_tma_kernel<T, 2><<<grid, ST_CH * p.ndirs, SL::SMEM_BYTES, st>>>(maps, p);
   return check_launch("aum_selective_scan_fwd(tma)");
 }
 

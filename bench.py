@@ -46,6 +46,15 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+def scan_traffic():
+    """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch from the committed ncu --set full capture."""
+    try:
+        t = json.load(open(os.path.join(ROOT, "profiles", "r1_scan_traffic.json")))
+        return t["dram__bytes_read.sum"] + t["dram__bytes_write.sum"]
+    except Exception:
+        return None
+
+
 # ------------------------------------------------------------------------------------------------------
 class ClockSampler:
     """nvidia-smi clocks / throttle reasons sampled DURING the timed region (B200_PROFILING.md)."""
@@ -101,7 +110,9 @@ def cpu_reference_sample(blocks: int = 2, repeats: int = 1):
     AudioMamba.forward), fp32, all host threads.  Bounded sample: ONE clip through the front end and `blocks` of
     the 24 blocks; whole-model time extrapolated linearly in the block count (every block is identical work)."""
     import aum_oracle as O
-    torch.set_num_threads(os.cpu_count() or 1)
+    # the oracle's per-token ops are small: beyond ~16 threads intra-op oversubscription makes it SLOWER
+    # (measured on the 128-core GPU box: 28.6 s/block with 128 threads vs ~5 s with 8-16), so use min(cores, 16)
+    torch.set_num_threads(min(os.cpu_count() or 1, 16))
     sd = O.make_audio_mamba_state(CFG["embed_dim"], blocks, num_classes=CFG["num_classes"],
                                   spectrogram_size=CFG["spectrogram_size"], bimamba_type=CFG["bimamba_type"],
                                   seed=SEED, perturb_A=0.1)
@@ -157,6 +168,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU (BASELINE config 2: 64)")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -181,7 +193,7 @@ def main():
 
     act = torch.float16 if args.dtype == "fp16" else torch.bfloat16
     torch.manual_seed(SEED)
-    model = AudioMamba(**CFG, act_dtype=act).to(dev).eval()
+    model = AudioMamba(**CFG, act_dtype=act, use_cuda_graph=not args.no_graph).to(dev).eval()
     g = torch.Generator(device="cpu").manual_seed(SEED)
     with torch.no_grad():   # move A off its structured S4D-real init, as trained weights are
         for blk in model.layers:
@@ -205,7 +217,7 @@ def main():
 
     def step_e2e():
         with torch.no_grad():
-            xd = x_host.to(dev, non_blocking=True)
+            xd = x_host if model.use_cuda_graph else x_host.to(dev, non_blocking=True)   # graph path copies H2D itself
             out = model(xd)
             logits_host.copy_(out, non_blocking=True)
 
@@ -216,8 +228,7 @@ def main():
 
     # ---- timed region 1: HBM-resident inputs (per-forward working set ~27 GB >> 126 MB L2)
     sampler = ClockSampler(local_rank)
-    calls0 = _lib.launch_count()
-    ops.PROFILE = []            # CUDA-event pairs around every selective-scan launch of the timed steps
+    launches_per_step = None
     sampler.start()
     barrier()
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
@@ -227,8 +238,6 @@ def main():
     e1.record()
     barrier()
     clocks = sampler.stop()
-    prof, ops.PROFILE = ops.PROFILE, None
-    launches = _lib.launch_count() - calls0
     ms_total = e0.elapsed_time(e1)
     t = torch.tensor([ms_total], device=dev)
     if dist is not None:
@@ -250,7 +259,17 @@ def main():
         dist.all_reduce(t2, op=dist.ReduceOp.MAX)
     e2e_value = world * B / (t2.item() / args.steps / 1e3)
 
-    # ---- roofline of the dominant kernel (bidirectional scan), measured live over the timed region
+    # ---- roofline of the dominant kernel (bidirectional scan): CUDA-event pairs around every scan launch of an
+    # instrumented, eagerly-launched repeat of the same K steps (kernels inside a replayed CUDA graph cannot be
+    # bracketed by events); also counts this repo's kernel launches per step.
+    calls0 = _lib.launch_count()
+    ops.PROFILE = []
+    barrier()
+    for _ in range(args.steps):
+        step_resident()
+    barrier()
+    prof, ops.PROFILE = ops.PROFILE, None
+    launches = (_lib.launch_count() - calls0)
     peak, peak_src = peaks()
     scan_ms = [s.elapsed_time(e) for (name, s, e) in prof if name == "selective_scan"] if prof else []
     Lq = (F_ // 16) * (T_ // 16) + 1
@@ -263,7 +282,7 @@ def main():
         avg = sum(scan_ms) / len(scan_ms)
         ach = alg_bytes / (avg * 1e-3) / 1e9
         roof = {"kernel": "scan_fwd_kernel (fused forward+reverse selective scan)", "bound": "hbm", "achieved": ach,
-                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": None, "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": scan_traffic(), "peak_source": peak_src,
                 "avg_launch_ms": avg, "launches_timed": len(scan_ms), "algorithmic_bytes_per_launch": alg_bytes,
                 "share_of_step": avg * CFG["depth"] / ms_step,
                 "note": "16 ex2 per (token,channel,direction): MUFU-bound before HBM-bound, see DESIGN.md"}
@@ -282,7 +301,8 @@ def main():
                           "l2": "inputs larger than L2: ~27 GB of activations per forward vs 126 MB L2"},
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                        "d2h_bytes_per_step": logits_host.numel() * 4},
-               "gpu_launches": launches, "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+               "gpu_launches": launches, "launch_mode": "eager" if args.no_graph else "cuda-graph replay of the same launches",
+               "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()
