@@ -40,6 +40,23 @@ class ScanDir(C.Structure):
     ]
 
 
+class ScanBwdDir(C.Structure):
+    """struct aum_scan_bwd_dir (include/aum_b200.h)."""
+    _fields_ = [
+        ("u", C.c_void_p), ("ld_u", C.c_int64),
+        ("delta", C.c_void_p), ("ld_delta", C.c_int64),
+        ("A", C.c_void_p),
+        ("BC", C.c_void_p), ("ld_bc", C.c_int64),
+        ("D", C.c_void_p),
+        ("du", C.c_void_p), ("ld_du", C.c_int64),
+        ("ddelta", C.c_void_p), ("ld_dd", C.c_int64),
+        ("dA", C.c_void_p),
+        ("dD", C.c_void_p),
+        ("dBC", C.c_void_p), ("ld_dbc", C.c_int64),
+        ("ckpt", C.c_void_p),
+    ]
+
+
 # symbol -> (restype, argtypes); also the list the CPU test checks the .so against the header with
 SIGNATURES = {
     "aum_version": (C.c_int, []),
@@ -54,7 +71,15 @@ SIGNATURES = {
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "aum_selective_scan_fwd": (C.c_int, [C.POINTER(ScanDir), C.POINTER(ScanDir), C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
+                                         C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
+    "aum_selective_scan_bwd_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "aum_selective_scan_bwd": (C.c_int, [C.POINTER(ScanBwdDir), C.POINTER(ScanBwdDir), C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                         C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_void_p]),
+    "aum_causal_conv1d_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "aum_add_rmsnorm_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                       C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,

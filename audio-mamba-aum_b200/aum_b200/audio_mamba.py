@@ -113,9 +113,36 @@ class AudioMamba(nn.Module):
         torch.add(tok[:, tp:], pe[:, tp + 1:], out=hidden[:, tp + 1:])
         return hidden
 
+    def _forward_train(self, x: torch.Tensor, return_features: bool) -> torch.Tensor:
+        """Autograd path (training): same data flow, differentiable glue.  The mixer and add+RMSNorm go through the
+        autograd.Functions of aum_b200.autograd (native backward kernels); the small front/back ends (patch-embed
+        conv, cls/pos assembly, head) use torch ops so autograd covers them."""
+        from .modules import rms_norm_fn
+        act = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else self.act_dtype
+        B = x.shape[0]
+        pf, pt = self.patch
+        gf, gt = self.grid
+        # stride == kernel conv as im2col + linear (plain fp32 matmul: cuDNN convolutions would silently use TF32)
+        cols = x.float().view(B, gt, pt, gf, pf).permute(0, 3, 1, 4, 2).reshape(B, gf * gt, pf * pt)
+        tok = torch.nn.functional.linear(cols, self.patch_embed.proj.weight.reshape(self.embed_dim, -1),
+                                         self.patch_embed.proj.bias)
+        N = tok.shape[1]
+        tp = N // 2
+        pe = self.pos_embed.pos_embed
+        hidden = torch.cat((tok[:, :tp] + pe[:, 1:tp + 1], (self.cls_token + pe[:, :1]).expand(B, -1, -1),
+                            tok[:, tp:] + pe[:, tp + 1:]), dim=1)
+        residual = None
+        for blk in self.layers:
+            y, residual = rms_norm_fn(hidden, blk.norm.weight, None, residual=residual, prenorm=True,
+                                      residual_in_fp32=True, eps=blk.norm.eps)
+            hidden = blk.mixer(y.to(act))
+        feat = rms_norm_fn(hidden[:, tp, :], self.norm_f.weight, None, residual=residual[:, tp, :], prenorm=False,
+                           residual_in_fp32=True, eps=self.norm_f.eps)
+        if return_features:
+            return feat
+        return torch.nn.functional.linear(feat.float(), self.head.weight, self.head.bias)
+
     def forward_features(self, x: torch.Tensor) -> torch.Tensor:
-        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
-            raise NotImplementedError("aum_b200 AudioMamba: training path not built yet; use torch.no_grad()")
         L.require_cuda(x)
         act = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else self.act_dtype
         hidden = self._tokens(x.float(), act)
@@ -143,7 +170,9 @@ class AudioMamba(nn.Module):
         self._graphs.clear()
 
     def forward(self, x: torch.Tensor, return_features: bool = False) -> torch.Tensor:
-        if not self.use_cuda_graph or torch.is_grad_enabled() or ops.PROFILE is not None:
+        if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
+            return self._forward_train(x, return_features)
+        if not self.use_cuda_graph or ops.PROFILE is not None:
             return self._forward_impl(x, return_features)
         act = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else self.act_dtype
         wver = 0

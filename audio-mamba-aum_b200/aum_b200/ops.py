@@ -126,8 +126,10 @@ class ScanDirection:
 
 
 def selective_scan(fwd: Optional[ScanDirection], bwd: Optional[ScanDirection], z: Optional[torch.Tensor], *,
-                   out: Optional[torch.Tensor] = None, out_scale: float = 1.0) -> torch.Tensor:
-    """out = out_scale * (y_fwd + y_bwd) * silu(z); either direction may be None.  Token-major (B, L, D)."""
+                   out: Optional[torch.Tensor] = None, out_scale: float = 1.0,
+                   y_pre: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = out_scale * (y_fwd + y_bwd) * silu(z); either direction may be None.  Token-major (B, L, D).
+    y_pre (optional, same shape/dtype/pitch as out) receives the pre-gate sum y_fwd + y_bwd for the backward pass."""
     ref = fwd if fwd is not None else bwd
     if ref is None:
         raise L.AumError("selective_scan: no direction given")
@@ -147,7 +149,8 @@ def selective_scan(fwd: Optional[ScanDirection], bwd: Optional[ScanDirection], z
     rc = L.lib().aum_selective_scan_fwd(C.byref(sf) if sf is not None else None,
                                         C.byref(sb) if sb is not None else None,
                                         L.ptr(z), ldz, L.ptr(out), _as_rows(out)[2],
-                                        B, Lq, Dch, N, L.dt(out.dtype), float(out_scale), L.stream())
+                                        B, Lq, Dch, N, L.dt(out.dtype), float(out_scale),
+                                        L.ptr(y_pre), _as_rows(y_pre)[2] if y_pre is not None else 0, L.stream())
     L.check(rc, "aum_selective_scan_fwd")
     if PROFILE is not None:
         ev1 = torch.cuda.Event(enable_timing=True)
@@ -196,3 +199,67 @@ def transpose(src: torch.Tensor, dst: Optional[torch.Tensor] = None, dst_dtype: 
                                B, R, Cc, L.dt(src.dtype), L.dt(dst.dtype), L.stream())
     L.check(rc, "aum_transpose")
     return dst
+
+
+def causal_conv1d_bwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], dout: torch.Tensor,
+                      dx: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], *, silu: bool = True,
+                      reverse: bool = False) -> None:
+    """Backward of causal_conv1d.  x, dx: (B, L, D) token-major (dtype); dout: (B, L, D) fp32;
+    dw (D, W) / dbias (D) fp32 are accumulated into."""
+    L.require_cuda(x, w, dout, dx, dw)
+    B, Lq, D = x.shape
+    if dout.dtype != torch.float32 or dw.dtype != torch.float32 or dx.dtype != x.dtype:
+        raise L.AumError("causal_conv1d_bwd: dout/dw must be fp32 and dx must match x")
+    rc = L.lib().aum_causal_conv1d_bwd(L.ptr(x), _as_rows(x)[2], L.ptr(w), L.ptr(bias), L.ptr(dout), _as_rows(dout)[2],
+                                       L.ptr(dx), _as_rows(dx)[2], L.ptr(dw), L.ptr(dbias), B, Lq, D, w.shape[1],
+                                       L.dt(x.dtype), int(silu), int(reverse), L.stream())
+    L.check(rc, "aum_causal_conv1d_bwd")
+
+
+class ScanBwdDirection:
+    """One time direction of the scan backward (struct aum_scan_bwd_dir).  u: (B,L,D) dtype; delta: (B,L,D) fp32
+    post-softplus; A: (D,16) fp32; bc: (B,L,32) fp32 packed [B|C]; outputs du, ddelta (B,L,D) fp32,
+    dA (D,16), dD (D), dbc (B,L,32) fp32 accumulated into; ckpt: fp32 workspace."""
+
+    def __init__(self, u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt):
+        self.t = (u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt)
+
+    def _struct(self):
+        u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt = self.t
+        for t_ in (delta, A, bc, du, ddelta, dA, dbc, ckpt):
+            if t_.dtype != torch.float32:
+                raise L.AumError("scan bwd: delta/A/bc/du/ddelta/dA/dbc/ckpt must be fp32")
+        s = L.ScanBwdDir()
+        s.u, s.ld_u = u.data_ptr(), _as_rows(u)[2]
+        s.delta, s.ld_delta = delta.data_ptr(), _as_rows(delta)[2]
+        s.A = A.data_ptr()
+        s.BC, s.ld_bc = bc.data_ptr(), _as_rows(bc)[2]
+        s.D = D.data_ptr() if D is not None else None
+        s.du, s.ld_du = du.data_ptr(), _as_rows(du)[2]
+        s.ddelta, s.ld_dd = ddelta.data_ptr(), _as_rows(ddelta)[2]
+        s.dA = dA.data_ptr()
+        s.dD = dD.data_ptr() if dD is not None else None
+        s.dBC, s.ld_dbc = dbc.data_ptr(), _as_rows(dbc)[2]
+        s.ckpt = ckpt.data_ptr()
+        return s
+
+
+def scan_bwd_workspace(batch: int, Lq: int, D: int, device) -> torch.Tensor:
+    n = L.lib().aum_selective_scan_bwd_workspace_floats(batch, Lq, D)
+    return torch.empty(n, device=device, dtype=torch.float32)
+
+
+def selective_scan_bwd(fwd: Optional[ScanBwdDirection], bwd: Optional[ScanBwdDirection], z, y_pre, dout, dz, out_z,
+                       *, out_scale: float = 1.0) -> None:
+    import ctypes as C
+    ref = fwd if fwd is not None else bwd
+    u = ref.t[0]
+    B, Lq, Dch = u.shape
+    sf = fwd._struct() if fwd is not None else None
+    sb = bwd._struct() if bwd is not None else None
+    ld = lambda t: _as_rows(t)[2] if t is not None else 0
+    rc = L.lib().aum_selective_scan_bwd(C.byref(sf) if sf is not None else None, C.byref(sb) if sb is not None else None,
+                                        L.ptr(z), ld(z), L.ptr(y_pre), ld(y_pre), L.ptr(dout), ld(dout),
+                                        L.ptr(dz), ld(dz), L.ptr(out_z), ld(out_z),
+                                        B, Lq, Dch, 16, L.dt(u.dtype), float(out_scale), L.stream())
+    L.check(rc, "aum_selective_scan_bwd")

@@ -150,3 +150,153 @@ extern "C" int aum_causal_conv1d_fwd(const void* x, int64_t ldx, const float* w,
   set_error("aum_causal_conv1d_fwd: bad dtype %d", dtype);
   return 1;
 }
+
+// ======================================================================================================
+// Backward of the depthwise causal conv (+bias, +SiLU).
+// Replaces causal_conv1d_cuda.causal_conv1d_bwd(x, w, bias, dout, None, dx, True)
+// (selective_scan_interface.py:281-283, 425-427, 594-596).  With c = bias + conv(x) (recomputed here),
+// dc = dout * silu'(c):  dx[p] = sum_k w[k] dc[p+(W-1)-k],  dw[k] = sum dc[p] x[p-(W-1)+k],  dbias = sum dc
+// (p = position in walk order: token index for the causal conv, L-1-token for the anti-causal one).
+// Block = 8 warps x 32 lanes: lane = channel pair, warp = one of 8 consecutive 16-token tiles of one sequence;
+// dw/dbias partials are reduced over the 8 warps in shared memory before one atomicAdd per value.
+// ======================================================================================================
+namespace aum {
+
+constexpr int CB_TL = 16;
+
+template <typename T>
+__global__ void __launch_bounds__(256)
+conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ bias,
+                  const float* __restrict__ dout, int64_t ldd, T* __restrict__ dx, int64_t ld_dx,
+                  float* __restrict__ dw, float* __restrict__ dbias,
+                  int batch, int L, int D, int W, int silu, int reverse, int n_cgrp, int n_tgrp) {
+  __shared__ float red[8][10][32];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int cg = blockIdx.x % n_cgrp;
+  const int tg = (blockIdx.x / n_cgrp) % n_tgrp;
+  const int b = blockIdx.x / (n_cgrp * n_tgrp);
+  const int c0 = (cg * 32 + lane) * 2;
+  const bool ok0 = c0 < D, ok1 = c0 + 1 < D;
+  const int p0 = (tg * 8 + wrp) * CB_TL;           // first walk position of this warp's tile
+
+  float wk[CONV_MAXW][2], bs[2];
+#pragma unroll
+  for (int v = 0; v < 2; ++v) {
+    const int c = c0 + v;
+    const bool ok = c < D;
+#pragma unroll
+    for (int j = 0; j < CONV_MAXW; ++j) {
+      const int k = j - (CONV_MAXW - W);
+      wk[j][v] = (ok && k >= 0) ? __ldg(w + (int64_t)c * W + k) : 0.f;
+    }
+    bs[v] = (ok && bias != nullptr) ? __ldg(bias + c) : 0.f;
+  }
+  float acc[10];
+#pragma unroll
+  for (int i = 0; i < 10; ++i) acc[i] = 0.f;
+
+  if (p0 < L && ok0) {
+    const int64_t base = (int64_t)b * L;
+    auto tok = [&](int p) { return reverse ? (L - 1 - p) : p; };
+    // x at walk positions p0-3 .. p0+TL+2, dout at p0 .. p0+TL+2
+    constexpr int NX = CB_TL + 2 * (CONV_MAXW - 1);
+    constexpr int ND = CB_TL + (CONV_MAXW - 1);
+    float xv[NX][2], dc[ND][2];
+#pragma unroll
+    for (int j = 0; j < NX; ++j) {
+      const int p = p0 - (CONV_MAXW - 1) + j;
+      xv[j][0] = 0.f; xv[j][1] = 0.f;
+      if (p >= 0 && p < L) {
+        const T* r = x + (base + tok(p)) * ldx + c0;
+        xv[j][0] = to_f(r[0]);
+        if (ok1) xv[j][1] = to_f(r[1]);
+      }
+    }
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      const int p = p0 + j;
+      dc[j][0] = 0.f; dc[j][1] = 0.f;
+      if (p < L) {
+        const float* g = dout + (base + tok(p)) * ldd + c0;
+#pragma unroll
+        for (int v = 0; v < 2; ++v) {
+          if (v == 1 && !ok1) continue;
+          float c = bs[v];
+#pragma unroll
+          for (int k = 0; k < CONV_MAXW; ++k) c = fmaf(wk[k][v], xv[j + k][v], c);   // x[p-3+k]
+          float gd = g[v];
+          if (silu) {
+            const float sg = __fdividef(1.f, 1.f + __expf(-c));
+            gd *= sg * (1.f + c * (1.f - sg));
+          }
+          dc[j][v] = gd;
+        }
+      }
+    }
+    // dx over the tile, dw/dbias over the positions this tile owns
+#pragma unroll
+    for (int i = 0; i < CB_TL; ++i) {
+      const int p = p0 + i;
+      if (p < L) {
+        float d0 = 0.f, d1 = 0.f;
+#pragma unroll
+        for (int k = 0; k < CONV_MAXW; ++k) {       // dx[p] = sum_k w[k] dc[p + 3 - k]
+          d0 = fmaf(wk[k][0], dc[i + (CONV_MAXW - 1) - k][0], d0);
+          d1 = fmaf(wk[k][1], dc[i + (CONV_MAXW - 1) - k][1], d1);
+        }
+        T* o = dx + (base + tok(p)) * ld_dx + c0;
+        o[0] = from_f<T>(d0);
+        if (ok1) o[1] = from_f<T>(d1);
+#pragma unroll
+        for (int k = 0; k < CONV_MAXW; ++k) {       // dw[k] += dc[p] x[p-3+k]
+          acc[k] = fmaf(dc[i][0], xv[i + k][0], acc[k]);
+          acc[5 + k] = fmaf(dc[i][1], xv[i + k][1], acc[5 + k]);
+        }
+        acc[4] += dc[i][0];
+        acc[9] += dc[i][1];
+      }
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 10; ++i) red[wrp][i][lane] = acc[i];
+  __syncthreads();
+  if (wrp == 0 && ok0) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += red[k][i][lane];
+      const int v = i / 5, j = i % 5;
+      const int c = c0 + v;
+      if (c < D) {
+        if (j < 4) { const int k = j - (CONV_MAXW - W); if (k >= 0) atomicAdd(dw + (int64_t)c * W + k, s); }
+        else if (dbias != nullptr) atomicAdd(dbias + c, s);
+      }
+    }
+  }
+}
+
+}  // namespace aum
+
+extern "C" int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w, const float* bias,
+                                     const float* dout, int64_t ldd, void* dx, int64_t ld_dx,
+                                     float* dw, float* dbias, int batch, int L, int D, int W,
+                                     int dtype, int silu, int reverse, void* stream) {
+  using namespace aum;
+  AUM_REQUIRE(x && w && dout && dx && dw, "aum_causal_conv1d_bwd: null pointer");
+  AUM_REQUIRE(W >= 2 && W <= CONV_MAXW, "aum_causal_conv1d_bwd: width %d unsupported (2..4)", W);
+  AUM_REQUIRE(batch >= 0 && L >= 0 && D >= 0, "aum_causal_conv1d_bwd: negative size");
+  AUM_REQUIRE(ldx >= D && ldd >= D && ld_dx >= D, "aum_causal_conv1d_bwd: leading dimension smaller than D");
+  if (batch == 0 || L == 0 || D == 0) return 0;
+  const int n_cgrp = ceil_div(D, 64), n_tgrp = ceil_div(L, 8 * CB_TL);
+  const int64_t blocks = (int64_t)batch * n_cgrp * n_tgrp;
+  AUM_REQUIRE(blocks < (1ll << 31), "aum_causal_conv1d_bwd: grid too large");
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (dtype) {
+    case AUM_F32:  conv1d_bwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, ldx, w, bias, dout, ldd, (float*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
+    case AUM_F16:  conv1d_bwd_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, ldx, w, bias, dout, ldd, (__half*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
+    case AUM_BF16: conv1d_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, w, bias, dout, ldd, (__nv_bfloat16*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
+    default: set_error("aum_causal_conv1d_bwd: bad dtype %d", dtype); return 1;
+  }
+  return check_launch("aum_causal_conv1d_bwd");
+}

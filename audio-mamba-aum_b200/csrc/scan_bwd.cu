@@ -1,0 +1,343 @@
+// Selective scan backward, one or both time directions in one launch, token-major.
+//
+// Replaces selective_scan_cuda.bwd (call sites /root/reference/vim-mamba_ssm/mamba_ssm/ops/
+// selective_scan_interface.py:62,247,389,541,548) and, for Fo-Bi, the second call on seven flip(-1) copies plus
+// the un-flips and adds of :554-561.  Gradients are those of selective_scan_ref (:86-152) under autograd; in
+// particular d/dz includes BOTH directions (the shipped BiMambaInnerFn.backward drops the reverse direction's
+// contribution, :560 after :537-538 — SURVEY.md Q2; we implement the mathematically correct gradient).
+//
+// Per direction (time order s = 0..L-1, token l = reverse ? L-1-s : s), with a_s = exp(delta_s A), b_s = delta_s B_s u_s:
+//   forward:   h_s = a_s h_{s-1} + b_s,  y_s = <C_s, h_s> + D u_s,  out = scale * (y_f + y_b) * silu(z)
+//   backward:  dy_s = scale * dout_s * silu(z_s);   dh_s = C_s dy_s + a_{s+1} dh_{s+1}
+//              dC_s += dy_s h_s;  dB_s += dh_s delta_s u_s;  du_s = delta_s <dh_s, B_s> + D dy_s;  dD += dy_s u_s
+//              ddelta_s = sum_n dh_s[n] (h_{s-1}[n] a_s[n] A[n] + B_s[n] u_s);  dA[n] += dh_s[n] h_{s-1}[n] a_s[n] delta_s
+//   gate:      dz = scale * dout * y_pre * silu'(z),   out_z = scale * y_pre * silu(z)   (y_pre = y_f + y_b saved by fwd)
+//
+// Mapping: grid = (ceil(D/64), batch); a CTA owns 64 channels of one sequence; 64 threads per direction, one thread
+// per channel with the 16 states in registers.  Sweep 1 replays the forward recurrence and checkpoints h every
+// 8 steps to a caller-provided workspace; sweep 2 walks the 8-step chunks backwards: it recomputes the chunk's
+// states from the checkpoint into shared memory, then runs the reverse-time recurrence over the chunk.
+// dB/dC are sums over channels: a 31-shuffle butterfly leaves lane i with value i of the warp's 32 channels,
+// one red.global.add.f32 per lane and token.  du / ddelta of the two directions (shared u, delta in Fo-Bi) meet
+// through the same park-in-the-output trick as the forward kernel (one CTA barrier at the midpoint).
+// This is the first, correctness-oriented version of the kernel (plain global loads, no TMA ring yet).
+#include "scan_common.cuh"
+
+namespace aum {
+
+constexpr int SB_CH = 64;     // channels per CTA
+constexpr int SB_TT = 8;      // checkpoint interval / chunk length
+
+struct ScanBwdDirDev {
+  const void* u; int64_t ld_u;
+  const float* delta; int64_t ld_delta;
+  const float* A;
+  const float* BC; int64_t ld_bc;
+  const float* D;
+  float* du; int64_t ld_du;
+  float* ddelta; int64_t ld_dd;
+  float* dA; float* dD;
+  float* dBC; int64_t ld_dbc;
+  float* ckpt;
+  int reverse;
+};
+
+struct ScanBwdParams {
+  ScanBwdDirDev dir[2];
+  int ndirs, shared_du;
+  const void* z; int64_t ld_z;
+  const void* ypre; int64_t ld_y;
+  const void* dout; int64_t ld_dout;
+  void* dz; int64_t ld_dz;
+  void* outz; int64_t ld_oz;
+  int batch, L, Dch, nchunks;
+  float scale;
+};
+
+__device__ __forceinline__ void red_add(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// 32 values per lane -> lane i ends up with sum over the warp's lanes of value i (31 shuffles).
+__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
+#pragma unroll
+  for (int half = 16; half >= 1; half >>= 1) {
+    const bool upper = (lane & half) != 0;
+#pragma unroll
+    for (int i = 0; i < half; ++i) {
+      const float keep = upper ? v[i + half] : v[i];
+      const float send = upper ? v[i] : v[i + half];
+      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
+    }
+  }
+  return v[0];
+}
+
+template <typename T>
+__global__ void __launch_bounds__(2 * SB_CH, 3)
+scan_bwd_kernel(const ScanBwdParams p) {
+  // state history of the current chunk: hist[j] = state BEFORE step j of the chunk, hist[j+1] = state after it
+  extern __shared__ float hist_raw[];
+  float (*hist)[SB_TT + 1][SCAN_NS][SB_CH] = reinterpret_cast<float (*)[SB_TT + 1][SCAN_NS][SB_CH]>(hist_raw);
+
+  const int g = threadIdx.x / SB_CH;
+  const int tig = threadIdx.x - g * SB_CH;
+  const int lane = tig & 31;
+  const ScanBwdDirDev& d = p.dir[g];
+  const int ch_raw = blockIdx.x * SB_CH + tig;
+  const bool active = ch_raw < p.Dch;
+  const int ch = active ? ch_raw : (p.Dch - 1);
+  const int b = blockIdx.y;
+  const int L = p.L;
+  const bool rev = d.reverse != 0;
+  const int64_t row0 = (int64_t)b * L;
+  const bool bidir = p.ndirs == 2;
+  const bool shared = bidir && p.shared_du;
+  const float scale = p.scale;
+
+  float a2[SCAN_NS], Av[SCAN_NS];
+  {
+    const float4* ap = reinterpret_cast<const float4*>(d.A + (int64_t)ch * SCAN_NS);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = __ldg(ap + i);
+      Av[4 * i] = v.x; Av[4 * i + 1] = v.y; Av[4 * i + 2] = v.z; Av[4 * i + 3] = v.w;
+    }
+#pragma unroll
+    for (int n = 0; n < SCAN_NS; ++n) a2[n] = Av[n] * 1.4426950408889634f;
+  }
+  const float Dv = d.D ? __ldg(d.D + ch) : 0.f;
+  const T* ub = reinterpret_cast<const T*>(d.u) + ch;
+  const float* db = d.delta + ch;
+  float* ck = d.ckpt + ((int64_t)b * p.nchunks) * SCAN_NS * p.Dch + ch;    // [b][chunk][n][D]
+  auto token = [&](int s) { return rev ? (L - 1 - s) : s; };
+
+  // ---------------- sweep 1: forward recurrence, checkpoint every SB_TT steps ----------------
+  {
+    float h[SCAN_NS];
+#pragma unroll
+    for (int n = 0; n < SCAN_NS; ++n) h[n] = 0.f;
+    for (int s = 0; s < L; ++s) {
+      if ((s % SB_TT) == 0) {
+        float* c = ck + (int64_t)(s / SB_TT) * SCAN_NS * p.Dch;
+        if (active) {
+#pragma unroll
+          for (int n = 0; n < SCAN_NS; ++n) c[(int64_t)n * p.Dch] = h[n];
+        }
+      }
+      const int64_t r = row0 + token(s);
+      const float u = to_f(ub[r * d.ld_u]);
+      const float dl = db[r * d.ld_delta];
+      const float du_ = dl * u;
+      const float4* bq = reinterpret_cast<const float4*>(d.BC + r * d.ld_bc);
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 Bv = __ldg(bq + q);
+        const float bb[4] = {Bv.x, Bv.y, Bv.z, Bv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int n = 4 * q + k;
+          h[n] = fmaf(ex2_approx(dl * a2[n]), h[n], du_ * bb[k]);
+        }
+      }
+    }
+  }
+  // the checkpoints are re-read by the same thread that wrote them: no barrier needed
+
+  // ---------------- sweep 2: chunks in reverse time order ----------------
+  const T* zb = p.z ? reinterpret_cast<const T*>(p.z) + ch : nullptr;
+  const T* yb = p.ypre ? reinterpret_cast<const T*>(p.ypre) + ch : nullptr;
+  const T* gb = reinterpret_cast<const T*>(p.dout) + ch;
+  T* dzb = p.dz ? reinterpret_cast<T*>(p.dz) + ch : nullptr;
+  T* ozb = p.outz ? reinterpret_cast<T*>(p.outz) + ch : nullptr;
+  float* dub = d.du + ch;
+  float* ddb = d.ddelta + ch;
+
+  // visiting order q = 0..L-1 of sweep 2 is s = L-1-q.  With shared du/ddelta the first Q1 visits park partials.
+  const int mid = L / 2;
+  const int Q1 = shared ? (rev ? (L - mid) : mid) : 0;
+  // the gate outputs (dz, out_z) are written exactly once per token: by the finalising visit when the directions
+  // share outputs, otherwise by direction slot 0.
+  const bool writes_gate_all = !shared && g == 0;
+
+  float gcar[SCAN_NS], dA_acc[SCAN_NS];
+#pragma unroll
+  for (int n = 0; n < SCAN_NS; ++n) { gcar[n] = 0.f; dA_acc[n] = 0.f; }
+  float dD_acc = 0.f;
+  bool synced = false;
+
+  for (int c = p.nchunks - 1; c >= 0; --c) {
+    const int s0 = c * SB_TT;
+    const int ns = min(SB_TT, L - s0);
+    // ---- recompute the chunk's states into shared memory
+    {
+      float h[SCAN_NS];
+      const float* cp = ck + (int64_t)c * SCAN_NS * p.Dch;
+#pragma unroll
+      for (int n = 0; n < SCAN_NS; ++n) { h[n] = cp[(int64_t)n * p.Dch]; hist[g][0][n][tig] = h[n]; }
+      for (int j = 0; j < ns; ++j) {
+        const int64_t r = row0 + token(s0 + j);
+        const float u = to_f(ub[r * d.ld_u]);
+        const float dl = db[r * d.ld_delta];
+        const float du_ = dl * u;
+        const float4* bq = reinterpret_cast<const float4*>(d.BC + r * d.ld_bc);
+#pragma unroll
+        for (int q = 0; q < 4; ++q) {
+          const float4 Bv = __ldg(bq + q);
+          const float bb[4] = {Bv.x, Bv.y, Bv.z, Bv.w};
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {
+            const int n = 4 * q + k;
+            h[n] = fmaf(ex2_approx(dl * a2[n]), h[n], du_ * bb[k]);
+            hist[g][j + 1][n][tig] = h[n];
+          }
+        }
+      }
+    }
+    // (each thread only reads back its own column of hist: no barrier needed)
+
+    // ---- reverse-time recurrence over the chunk
+    for (int j = ns - 1; j >= 0; --j) {
+      const int s = s0 + j;
+      const int qv = L - 1 - s;                       // visit index of sweep 2
+      if (shared && !synced && qv == Q1) { __syncthreads(); synced = true; }   // all partials are parked
+      const bool finalize = !shared || qv >= Q1;
+      const int64_t r = row0 + token(s);
+      const float u = to_f(ub[r * d.ld_u]);
+      const float dl = db[r * d.ld_delta];
+      const float go = to_f(gb[r * p.ld_dout]) * scale;
+      float sz = 1.f, zv = 0.f;
+      if (zb) { zv = to_f(zb[r * p.ld_z]); sz = silu_f(zv); }
+      const float dy = go * sz;
+      dD_acc = fmaf(dy, u, dD_acc);
+      const float4* bq = reinterpret_cast<const float4*>(d.BC + r * d.ld_bc);
+      float red[32];
+      float sB = 0.f, dd = 0.f;
+      const float dlu = dl * u;
+#pragma unroll
+      for (int q = 0; q < 4; ++q) {
+        const float4 Bv = __ldg(bq + q);
+        const float4 Cv = __ldg(bq + 4 + q);
+        const float bb[4] = {Bv.x, Bv.y, Bv.z, Bv.w};
+        const float cc[4] = {Cv.x, Cv.y, Cv.z, Cv.w};
+#pragma unroll
+        for (int k = 0; k < 4; ++k) {
+          const int n = 4 * q + k;
+          const float a = ex2_approx(dl * a2[n]);
+          const float dh = fmaf(cc[k], dy, gcar[n]);
+          gcar[n] = a * dh;
+          const float t1 = gcar[n] * hist[g][j][n][tig];            // dh * a * h_{s-1}
+          dA_acc[n] = fmaf(t1, dl, dA_acc[n]);
+          dd = fmaf(t1, Av[n], dd);
+          sB = fmaf(dh, bb[k], sB);
+          red[n] = dh * dlu;                                        // dB contribution
+          red[SCAN_NS + n] = dy * hist[g][j + 1][n][tig];           // dC contribution
+        }
+      }
+      dd = fmaf(sB, u, dd);
+      float duv = fmaf(dl, sB, Dv * dy);
+      if (!active) {
+#pragma unroll
+        for (int i = 0; i < 32; ++i) red[i] = 0.f;
+      }
+      // cross-channel sums of this token: lane i of each warp adds value i
+      const float rsum = warp_transpose_reduce(red, lane);
+      red_add(d.dBC + r * d.ld_dbc + lane, rsum);
+
+      if (shared) {
+        if (!finalize) {
+          if (active) { dub[r * d.ld_du] = duv; ddb[r * d.ld_dd] = dd; }
+        } else {
+          if (active) {
+            duv += dub[r * d.ld_du]; dd += ddb[r * d.ld_dd];
+            dub[r * d.ld_du] = duv; ddb[r * d.ld_dd] = dd;
+          }
+        }
+      } else if (active) {
+        dub[r * d.ld_du] = duv; ddb[r * d.ld_dd] = dd;
+      }
+      if (active && ((shared && finalize) || writes_gate_all || !bidir)) {
+        if (zb && (dzb || ozb)) {
+          const float yp = yb ? to_f(yb[r * p.ld_y]) : 0.f;
+          if (dzb) {
+            const float sg = __fdividef(1.f, 1.f + __expf(-zv));             // sigmoid(z)
+            dzb[r * p.ld_dz] = from_f<T>(go * yp * (sg * (1.f + zv * (1.f - sg))));
+          }
+          if (ozb) ozb[r * p.ld_oz] = from_f<T>(scale * yp * sz);
+        }
+      }
+    }
+  }
+  if (shared && !synced) __syncthreads();   // (degenerate L) keep the CTA barrier count equal across directions
+
+  if (active) {
+#pragma unroll
+    for (int n = 0; n < SCAN_NS; ++n) atomicAdd(d.dA + (int64_t)ch * SCAN_NS + n, dA_acc[n]);
+    if (d.dD) atomicAdd(d.dD + ch, dD_acc);
+  }
+}
+
+}  // namespace aum
+
+extern "C" int64_t aum_selective_scan_bwd_workspace_floats(int batch, int L, int D) {
+  const int64_t nchunks = (L + aum::SB_TT - 1) / aum::SB_TT;
+  return (int64_t)batch * nchunks * aum::SCAN_NS * D;
+}
+
+extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_scan_bwd_dir_t* bwd,
+                                      const void* z, int64_t ld_z, const void* y_pre, int64_t ld_y,
+                                      const void* dout, int64_t ld_dout,
+                                      void* dz, int64_t ld_dz, void* out_z, int64_t ld_oz,
+                                      int batch, int L, int D, int N, int dtype, float out_scale, void* stream) {
+  using namespace aum;
+  AUM_REQUIRE(fwd || bwd, "aum_selective_scan_bwd: at least one direction is required");
+  AUM_REQUIRE(dout, "aum_selective_scan_bwd: null dout");
+  AUM_REQUIRE(N == SCAN_NS, "aum_selective_scan_bwd: d_state must be %d", SCAN_NS);
+  AUM_REQUIRE(batch >= 0 && L >= 0 && D >= 0 && batch <= 65535, "aum_selective_scan_bwd: bad sizes");
+  AUM_REQUIRE(dtype >= AUM_F32 && dtype <= AUM_BF16, "aum_selective_scan_bwd: bad dtype %d", dtype);
+  AUM_REQUIRE(!z || y_pre || (!dz && !out_z), "aum_selective_scan_bwd: dz/out_z need the saved pre-gate output y_pre");
+  if (batch == 0 || L == 0 || D == 0) return 0;
+  ScanBwdParams p;
+  memset(&p, 0, sizeof(p));
+  const aum_scan_bwd_dir_t* src[2] = {fwd, bwd};
+  for (int i = 0; i < 2; ++i) {
+    const aum_scan_bwd_dir_t* s = src[i];
+    if (!s) continue;
+    AUM_REQUIRE(s->u && s->delta && s->A && s->BC && s->du && s->ddelta && s->dA && s->dBC && s->ckpt,
+                "aum_selective_scan_bwd: null pointer in direction %d", i);
+    AUM_REQUIRE(s->ld_u >= D && s->ld_delta >= D && s->ld_du >= D && s->ld_dd >= D && s->ld_bc >= 2 * N && s->ld_dbc >= 2 * N,
+                "aum_selective_scan_bwd: leading dimension too small");
+    AUM_REQUIRE(aligned16(s->A) && aligned16(s->BC) && (s->ld_bc % 4) == 0, "aum_selective_scan_bwd: A / BC must be 16-byte aligned");
+    ScanBwdDirDev& d = p.dir[p.ndirs++];
+    d.u = s->u; d.ld_u = s->ld_u; d.delta = s->delta; d.ld_delta = s->ld_delta; d.A = s->A;
+    d.BC = s->BC; d.ld_bc = s->ld_bc; d.D = s->D; d.du = s->du; d.ld_du = s->ld_du;
+    d.ddelta = s->ddelta; d.ld_dd = s->ld_dd; d.dA = s->dA; d.dD = s->dD; d.dBC = s->dBC; d.ld_dbc = s->ld_dbc;
+    d.ckpt = s->ckpt; d.reverse = i;
+  }
+  if (p.ndirs == 2) {
+    const bool same_du = p.dir[0].du == p.dir[1].du, same_dd = p.dir[0].ddelta == p.dir[1].ddelta;
+    AUM_REQUIRE(same_du == same_dd, "aum_selective_scan_bwd: du and ddelta must be shared together or not at all");
+    AUM_REQUIRE(p.dir[0].ckpt != p.dir[1].ckpt, "aum_selective_scan_bwd: each direction needs its own checkpoint workspace");
+    p.shared_du = same_du ? 1 : 0;
+  }
+  p.z = z; p.ld_z = ld_z; p.ypre = y_pre; p.ld_y = ld_y; p.dout = dout; p.ld_dout = ld_dout;
+  p.dz = dz; p.ld_dz = ld_dz; p.outz = out_z; p.ld_oz = ld_oz;
+  p.batch = batch; p.L = L; p.Dch = D; p.nchunks = (L + SB_TT - 1) / SB_TT; p.scale = out_scale;
+  dim3 grid(ceil_div(D, SB_CH), batch);
+  cudaStream_t st = (cudaStream_t)stream;
+  const int smem = 2 * (SB_TT + 1) * SCAN_NS * SB_CH * (int)sizeof(float);     // 73 728 B
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(scan_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_bwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_bwd_kernel<__nv_bfloat16>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
+    if (e != cudaSuccess) { set_error("aum_selective_scan_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 2; }
+    attr_set = true;
+  }
+  switch (dtype) {
+    case AUM_F32:  scan_bwd_kernel<float><<<grid, SB_CH * p.ndirs, smem, st>>>(p); break;
+    case AUM_F16:  scan_bwd_kernel<__half><<<grid, SB_CH * p.ndirs, smem, st>>>(p); break;
+    case AUM_BF16: scan_bwd_kernel<__nv_bfloat16><<<grid, SB_CH * p.ndirs, smem, st>>>(p); break;
+  }
+  return check_launch("aum_selective_scan_bwd");
+}

@@ -29,6 +29,7 @@ struct ScanParams {
   int ndirs;
   const void* z; int64_t ld_z;
   void* out; int64_t ld_out;
+  void* ypre; int64_t ld_ypre;   // optional: pre-gate y_fwd + y_bwd (saved for the backward pass), activation dtype
   int batch, L, Dch, N;
   float out_scale;
 };

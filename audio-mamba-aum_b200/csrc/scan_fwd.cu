@@ -41,7 +41,7 @@ __device__ __forceinline__ void scan_chunk(int ns, const float* bc_row, int row_
                                            f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2],
                                            float Dv, float dbias, float oscale,
                                            const T* ub, int ldu, const TD* db, int ldd,
-                                           const T* zb, int ldz, T* ob, int ldo, int r, int dr) {
+                                           const T* zb, int ldz, T* ob, int ldo, T* ypb, int ldy, int r, int dr) {
   Slots w;
   // r: row of the step being computed; rl: row of the step being loaded (4 steps ahead)
   int rl = r;
@@ -90,6 +90,7 @@ __device__ __forceinline__ void scan_chunk(int ns, const float* bc_row, int row_
       float y = (y0 + y1) + (y2 + y3);
       if (FINAL) {
         if (PARTIAL) y += w.p[i];
+        if (ypb != nullptr && t < ns) ypb[(int64_t)r * ldy] = from_f<T>(y);
         if (HASZ) y *= silu_f(w.z[i]);
         y *= oscale;
       }
@@ -198,6 +199,8 @@ scan_fwd_kernel(const ScanParams p) {
   const TD* db = reinterpret_cast<const TD*>(d.delta) + ch;
   const T* zb = reinterpret_cast<const T*>(p.z) + ch;
   T* ob = reinterpret_cast<T*>(p.out) + ch;
+  T* ypb = p.ypre ? reinterpret_cast<T*>(p.ypre) + ch : nullptr;
+  const int ldy = (int)p.ld_ypre;
 
   for (int k = 0; k < nchunks; ++k) {
     int s0, ns; chunk_range(k, s0, ns);
@@ -236,7 +239,7 @@ scan_fwd_kernel(const ScanParams p) {
     const float* bc_row0 = &bc[rev ? (ns - 1) : 0][0];
     const int row_step = rev ? -SCAN_ROW : SCAN_ROW;
     const bool finalize = k >= n1;
-#define AUM_SCAN_CHUNK(F, P, Z) scan_chunk<T, TD, F, P, Z, SP>(ns, bc_row0, row_step, h, a2, Dv, dbias, oscale, ub, ldu, db, ldd, zb, ldz, ob, ldo, r, dr)
+#define AUM_SCAN_CHUNK(F, P, Z) scan_chunk<T, TD, F, P, Z, SP>(ns, bc_row0, row_step, h, a2, Dv, dbias, oscale, ub, ldu, db, ldd, zb, ldz, ob, ldo, ypb, ldy, r, dr)
     if (!finalize) AUM_SCAN_CHUNK(false, false, false);
     else if (bidir) { if (has_z) AUM_SCAN_CHUNK(true, true, true); else AUM_SCAN_CHUNK(true, true, false); }
     else            { if (has_z) AUM_SCAN_CHUNK(true, false, true); else AUM_SCAN_CHUNK(true, false, false); }
@@ -284,7 +287,7 @@ static int launch_scan_t(const ScanParams& p, int delta_dt, int dtype, int ch, b
 extern "C" int aum_selective_scan_fwd(const aum_scan_dir_t* fwd, const aum_scan_dir_t* bwd,
                                       const void* z, int64_t ld_z, void* out, int64_t ld_out,
                                       int batch, int L, int D, int N, int dtype,
-                                      float out_scale, void* stream) {
+                                      float out_scale, void* y_pre, int64_t ld_ypre, void* stream) {
   using namespace aum;
   AUM_REQUIRE(fwd || bwd, "aum_selective_scan_fwd: at least one direction is required");
   AUM_REQUIRE(out, "aum_selective_scan_fwd: null output");
@@ -318,6 +321,8 @@ extern "C" int aum_selective_scan_fwd(const aum_scan_dir_t* fwd, const aum_scan_
     d.last_state = s->last_state; d.reverse = i;
   }
   p.z = z; p.ld_z = ld_z; p.out = out; p.ld_out = ld_out;
+  p.ypre = y_pre; p.ld_ypre = ld_ypre;
+  AUM_REQUIRE(!y_pre || ld_ypre >= D, "aum_selective_scan_fwd: ld_ypre too small");
   p.batch = batch; p.L = L; p.Dch = D; p.N = N; p.out_scale = out_scale;
   AUM_REQUIRE(ld_out >= D && (!z || ld_z >= D), "aum_selective_scan_fwd: leading dimension too small");
 

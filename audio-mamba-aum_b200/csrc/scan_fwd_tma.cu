@@ -94,7 +94,8 @@ template <typename T, bool FIN, bool PARTIAL, bool HASZ>
 __device__ __forceinline__ void scan_tile_full(uint32_t a_u, uint32_t a_d, uint32_t a_z, uint32_t a_bc,
                                                int su, int sd, int sbc, float Dv, float oscale, bool active,
                                                f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2],
-                                               float (&pring)[ST_TT], T* po, ptrdiff_t ostep, int steps_left_after_tile) {
+                                               float (&pring)[ST_TT], T* po, ptrdiff_t ostep, int steps_left_after_tile,
+                                               ptrdiff_t ypre_off) {
 #pragma unroll
   for (int t = 0; t < ST_TT; ++t) {
     float y = scan_step(lds_t<T>(a_u), lds_f(a_d), a_bc, Dv, h, a2);
@@ -103,6 +104,7 @@ __device__ __forceinline__ void scan_tile_full(uint32_t a_u, uint32_t a_d, uint3
         y += pring[t];
         if (t < steps_left_after_tile) pring[t] = to_f(po[ST_TT * ostep]);   // step t+8 of the walk
       }
+      if (ypre_off != 0 && active) po[ypre_off] = from_f<T>(y);   // pre-gate y saved for the backward pass
       if (HASZ) y *= silu_f(lds_t<T>(a_z));
       y *= oscale;
     }
@@ -119,12 +121,13 @@ __device__ __forceinline__ void scan_tile_tail(int nt, bool fin, bool partial, b
                                                uint32_t a_u, uint32_t a_d, uint32_t a_z, uint32_t a_bc,
                                                int su, int sd, int sbc, float Dv, float oscale, bool active,
                                                f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2],
-                                               T* po, ptrdiff_t ostep) {
+                                               T* po, ptrdiff_t ostep, ptrdiff_t ypre_off) {
 #pragma unroll 1
   for (int t = 0; t < nt; ++t) {
     float y = scan_step(lds_t<T>(a_u), lds_f(a_d), a_bc, Dv, h, a2);
     if (fin) {
       if (partial) y += to_f(*po);
+      if (ypre_off != 0 && active) po[ypre_off] = from_f<T>(y);
       if (has_z) y *= silu_f(lds_t<T>(a_z));
       y *= oscale;
     }
@@ -225,6 +228,8 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   const int ldo = (int)p.ld_out;
   T* ob = reinterpret_cast<T*>(p.out) + ch;
   const ptrdiff_t ostep = rev ? -(ptrdiff_t)ldo : (ptrdiff_t)ldo;
+  // the pre-gate output (if requested) shares out's row pitch: address it as an element offset from the out row
+  const ptrdiff_t ypre_off = p.ypre ? (reinterpret_cast<T*>(p.ypre) - reinterpret_cast<T*>(p.out)) : 0;
   const int su = rev ? -(int)(ST_CH * sizeof(T)) : (int)(ST_CH * sizeof(T));
   const int sd = rev ? -(ST_CH * 4) : (ST_CH * 4);
   const int sbc = rev ? -(SCAN_ROW * 4) : (SCAN_ROW * 4);
@@ -259,13 +264,13 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     const uint32_t a_bc = st + SL::OFF_BC + (uint32_t)row_first * SCAN_ROW * 4u;
     if (nt == ST_TT) {
       const int left = L - (s0 + ST_TT);   // steps of the walk after this tile (ring refills stop there)
-#define AUM_TILE(F, P, Z) scan_tile_full<T, F, P, Z>(a_u, a_d, a_z, a_bc, su, sd, sbc, Dv, oscale, active, h, a2, pring, po, ostep, left)
+#define AUM_TILE(F, P, Z) scan_tile_full<T, F, P, Z>(a_u, a_d, a_z, a_bc, su, sd, sbc, Dv, oscale, active, h, a2, pring, po, ostep, left, ypre_off)
       if (!fin) AUM_TILE(false, false, false);
       else if (partial) { if (has_z) AUM_TILE(true, true, true); else AUM_TILE(true, true, false); }
       else { if (has_z) AUM_TILE(true, false, true); else AUM_TILE(true, false, false); }
 #undef AUM_TILE
     } else {
-      scan_tile_tail<T>(nt, fin, partial, has_z, a_u, a_d, a_z, a_bc, su, sd, sbc, Dv, oscale, active, h, a2, po, ostep);
+      scan_tile_tail<T>(nt, fin, partial, has_z, a_u, a_d, a_z, a_bc, su, sd, sbc, Dv, oscale, active, h, a2, po, ostep, ypre_off);
     }
 
     // hand the stage back; one thread refills the stage released one tile earlier
@@ -316,6 +321,7 @@ int launch_scan_tma(const ScanParams& p, int dtype, int delta_dt, cudaStream_t s
   const int esz = dtype_size(dtype);
   auto ok_mat = [](const void* base, int64_t ld, int sz) { return aligned16(base) && (ld * sz) % 16 == 0; };
   if (!ok_mat(p.out, p.ld_out, esz) || p.ld_out * esz % 2 != 0) return -1;
+  if (p.ypre && (p.ld_ypre != p.ld_out || p.ypre == p.out)) return -1;   // pre-gate rows must mirror the out rows
   if (p.z && !ok_mat(p.z, p.ld_z, esz)) return -1;
   for (int g = 0; g < p.ndirs; ++g) {
     const ScanDirDev& d = p.dir[g];

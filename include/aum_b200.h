@@ -78,6 +78,14 @@ AUM_API int aum_causal_conv1d_fwd(const void* x, int64_t ldx, const float* w, co
                           void* out, int64_t ldo, int batch, int L, int D, int W,
                           int dtype, int silu, int reverse, void* stream);
 
+/* Backward of the above.  replaces causal_conv1d_cuda.causal_conv1d_bwd(x, w, bias, dout, None, dx, silu)
+ *   (selective_scan_interface.py:281-283, 425-427, 594-596).  dout: fp32 gradient w.r.t. the conv output
+ *   (after the activation); dx: written (dtype); dw (D, W) and dbias (D) are ACCUMULATED (+=): zero them first. */
+AUM_API int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w, const float* bias,
+                          const float* dout, int64_t ldd, void* dx, int64_t ld_dx,
+                          float* dw, float* dbias, int batch, int L, int D, int W,
+                          int dtype, int silu, int reverse, void* stream);
+
 /* ---------------------------------------------------------------------------------------------
  * Selective scan, one or both time directions in ONE launch.
  *   replaces selective_scan_cuda.fwd(u, delta, A, B, C, D, z, delta_bias, delta_softplus)
@@ -106,7 +114,42 @@ AUM_API int aum_selective_scan_fwd(const aum_scan_dir_t* fwd, const aum_scan_dir
                            const void* z, int64_t ld_z,
                            void* out, int64_t ld_out,
                            int batch, int L, int D, int N, int dtype,
-                           float out_scale, void* stream);
+                           float out_scale,
+                           void* y_pre, int64_t ld_ypre,   /* optional (training): pre-gate y_fwd+y_bwd, dtype */
+                           void* stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Selective scan backward, one or both time directions in ONE launch.
+ *   replaces selective_scan_cuda.bwd(u, delta, A, B, C, D, z, delta_bias, dout, x, out, dz, softplus, recompute_out_z)
+ *   (selective_scan_interface.py:62,247,389,541,548) and the flip/un-flip/add combination of :554-561.
+ *   delta is the POST-softplus value (the softplus/bias chain rule is applied by the caller's dt_proj backward:
+ *   d(pre) = ddelta * (1 - exp(-delta))).  [B|C] are packed fp32 rows (batch*L, 2N), N = 16.
+ *   Outputs per direction: du, ddelta (fp32, (batch*L, D)) — pass the SAME pointers in both directions when u and
+ *   delta are shared (Fo-Bi) and the kernel sums the two directions; dA (D,N), dD (D), dBC (batch*L, 2N) are
+ *   ACCUMULATED (+=): zero them first.  ckpt: workspace of aum_selective_scan_bwd_workspace_floats() floats per
+ *   direction.  Gate: dz and the recomputed out_z = out_scale*y_pre*silu(z) are written when z and y_pre are given.
+ *   d/dz is the mathematically correct gradient (both directions), see SURVEY.md Q2.
+ * ------------------------------------------------------------------------------------------- */
+typedef struct aum_scan_bwd_dir {
+  const void* u;      int64_t ld_u;      /* (batch*L, D) dtype */
+  const float* delta; int64_t ld_delta;  /* (batch*L, D) fp32, post-softplus */
+  const float* A;                        /* (D, N) */
+  const float* BC;    int64_t ld_bc;     /* (batch*L, 2N) fp32 [B|C] */
+  const float* D;                        /* (D) or NULL */
+  float* du;     int64_t ld_du;          /* out (batch*L, D) fp32 */
+  float* ddelta; int64_t ld_dd;          /* out (batch*L, D) fp32 */
+  float* dA;                             /* += (D, N) */
+  float* dD;                             /* += (D) or NULL */
+  float* dBC;    int64_t ld_dbc;         /* += (batch*L, 2N) */
+  float* ckpt;                           /* workspace */
+} aum_scan_bwd_dir_t;
+
+AUM_API int64_t aum_selective_scan_bwd_workspace_floats(int batch, int L, int D);
+AUM_API int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_scan_bwd_dir_t* bwd,
+                                   const void* z, int64_t ld_z, const void* y_pre, int64_t ld_y,
+                                   const void* dout, int64_t ld_dout,
+                                   void* dz, int64_t ld_dz, void* out_z, int64_t ld_oz,
+                                   int batch, int L, int D, int N, int dtype, float out_scale, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused residual-add + RMSNorm (fp32 residual stream) — the op on either side of the mixer.

@@ -1,0 +1,178 @@
+"""Gradients of the training path (row a12 of SURVEY.md section 8a: BiMambaInnerFn.backward and friends) against
+torch autograd through the CPU oracle.  B200 only (-m gpu)."""
+import pytest
+import torch
+
+import aum_oracle as O
+from conftest import load_golden
+
+pytestmark = pytest.mark.gpu
+DEV = "cuda"
+
+
+def gen(seed):
+    return torch.Generator().manual_seed(seed)
+
+
+def rnd(shape, g, scale=1.0):
+    return scale * torch.randn(shape, generator=g)
+
+
+def _close(a, b, rtol, atol, msg=""):
+    scale = max(b.abs().max().item(), 1e-12)
+    torch.testing.assert_close(a.float().cpu(), b.float(), rtol=rtol, atol=atol * max(scale, 1.0), msg=lambda m: f"{msg}: {m}")
+
+
+@pytest.mark.parametrize("reverse", [False, True])
+@pytest.mark.parametrize("B,Lq,D,W", [(2, 37, 40, 4), (1, 130, 6, 3), (2, 16, 64, 4)])
+def test_causal_conv1d_bwd(reverse, B, Lq, D, W):
+    from aum_b200 import ops
+    g = gen(1)
+    x = rnd((B, Lq, D), g).requires_grad_()
+    w = rnd((D, W), g, 0.5).requires_grad_()
+    b = rnd((D,), g, 0.5).requires_grad_()
+    G = rnd((B, Lq, D), g)
+    xc = x.permute(0, 2, 1)
+    y = O.causal_conv1d_oracle(xc.flip(-1) if reverse else xc, w, b, True)
+    y = (y.flip(-1) if reverse else y).permute(0, 2, 1)
+    (y * G).sum().backward()
+    dx = torch.empty((B, Lq, D), device=DEV)
+    dw = torch.zeros((D, W), device=DEV)
+    db = torch.zeros((D,), device=DEV)
+    ops.causal_conv1d_bwd(x.detach().to(DEV), w.detach().to(DEV), b.detach().to(DEV), G.to(DEV), dx, dw, db,
+                          silu=True, reverse=reverse)
+    _close(dx, x.grad, 1e-4, 1e-5, "dx")
+    _close(dw, w.grad, 1e-4, 1e-5, "dw")
+    _close(db, b.grad, 1e-4, 1e-5, "dbias")
+
+
+def _scan_ref(u, delta, A, A_b, Bm, Cm, Dv, z, scale, dirs):
+    """token-major oracle: out = scale * (y_f + y_b) * silu(z) with differentiable torch ops."""
+    uc, dc = u.permute(0, 2, 1), delta.permute(0, 2, 1)
+    Bc, Cc = Bm.permute(0, 2, 1), Cm.permute(0, 2, 1)
+    y = 0
+    if "f" in dirs:
+        y = y + O.selective_scan_oracle(uc, dc, A, Bc, Cc, Dv, None, None, False)
+    if "b" in dirs:
+        y = y + O.selective_scan_oracle(uc.flip(-1), dc.flip(-1), A_b, Bc.flip(-1), Cc.flip(-1), Dv, None, None, False).flip(-1)
+    y = y.permute(0, 2, 1)
+    return scale * y * O.silu_oracle(z), y
+
+
+@pytest.mark.parametrize("dirs", ["fb", "f", "b"])
+@pytest.mark.parametrize("B,Lq,D", [(2, 37, 40), (1, 8, 64), (2, 70, 96), (1, 1, 16)])
+def test_selective_scan_bwd_vs_oracle_autograd(dirs, B, Lq, D):
+    from aum_b200 import ops
+    N = 16
+    g = gen(2)
+    u = rnd((B, Lq, D), g).requires_grad_()
+    delta = (0.05 + 0.3 * torch.rand((B, Lq, D), generator=g)).requires_grad_()
+    A = (-torch.exp(torch.log(torch.arange(1, N + 1.0)).repeat(D, 1) + 0.1 * rnd((D, N), g))).requires_grad_()
+    A_b = (-torch.exp(torch.log(torch.arange(1, N + 1.0)).repeat(D, 1) + 0.1 * rnd((D, N), g))).requires_grad_()
+    Bm, Cm = rnd((B, Lq, N), g).requires_grad_(), rnd((B, Lq, N), g).requires_grad_()
+    Dv = (1 + 0.1 * rnd((D,), g)).requires_grad_()
+    z = rnd((B, Lq, D), g).requires_grad_()
+    G = rnd((B, Lq, D), g)
+    scale = 0.5
+    out, ypre = _scan_ref(u, delta, A, A_b, Bm, Cm, Dv, z, scale, dirs)
+    (out * G).sum().backward()
+
+    cu = lambda t: t.detach().to(DEV).contiguous()
+    bc = torch.cat([cu(Bm), cu(Cm)], dim=-1).contiguous()
+    du = torch.empty((B, Lq, D), device=DEV); dd = torch.empty_like(du)
+    dbc = torch.zeros((B, Lq, 2 * N), device=DEV)
+    dA = torch.zeros((D, N), device=DEV); dAb = torch.zeros((D, N), device=DEV); dD = torch.zeros((D,), device=DEV)
+    dz = torch.empty((B, Lq, D), device=DEV); oz = torch.empty_like(dz)
+    mk = lambda Ax, dAx: ops.ScanBwdDirection(cu(u), cu(delta), cu(Ax), bc, cu(Dv), du, dd, dAx, dD, dbc,
+                                              ops.scan_bwd_workspace(B, Lq, D, DEV))
+    ops.selective_scan_bwd(mk(A, dA) if "f" in dirs else None, mk(A_b, dAb) if "b" in dirs else None,
+                           cu(z), cu(ypre), G.to(DEV), dz, oz, out_scale=scale)
+    tol = dict(rtol=2e-4, atol=2e-5)
+    _close(oz, out.detach(), msg="out_z", **tol)
+    _close(dz, z.grad, msg="dz", **tol)
+    _close(du, u.grad, msg="du", **tol)
+    _close(dd, delta.grad, msg="ddelta", **tol)
+    _close(dbc[..., :N], Bm.grad, msg="dB", **tol)
+    _close(dbc[..., N:], Cm.grad, msg="dC", **tol)
+    _close(dD, Dv.grad, msg="dD", **tol)
+    if "f" in dirs:
+        _close(dA, A.grad, msg="dA", **tol)
+    if "b" in dirs:
+        _close(dAb, A_b.grad, msg="dA_b", **tol)
+
+
+@pytest.mark.parametrize("bt,kw", [("v1", {}), ("none", {}), ("v2", {"if_devide_out": True}), ("v1", {"bias": True, "init_layer_scale": 0.5})])
+def test_mamba_module_backward_vs_oracle_autograd(bt, kw):
+    """All parameter gradients and d(hidden) of one mixer, fp32 tier, against autograd through the oracle."""
+    from mamba_ssm.modules.mamba_simple import Mamba
+    Dm, Lq, B = 64, 33, 2
+    torch.manual_seed(5)
+    m = Mamba(Dm, bimamba_type=bt, **kw)
+    g = gen(6)
+    with torch.no_grad():
+        for n, p in m.named_parameters():
+            if n.endswith(("A_log", "A_b_log", "D", "D_b")):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+            if n.endswith("in_proj.bias") or n.endswith("out_proj.bias"):
+                p.add_(0.1 * torch.randn(p.shape, generator=g))
+    hidden = rnd((B, Lq, Dm), g)
+    G = rnd((B, Lq, Dm), g)
+    # oracle autograd on CPU
+    ref_p = {k: v.detach().clone().requires_grad_() for k, v in m.state_dict().items()}
+    h_ref = hidden.clone().requires_grad_()
+    out_ref = O.mamba_forward_oracle(ref_p, h_ref, bt, kw.get("if_devide_out", False))
+    (out_ref * G).sum().backward()
+    # engine
+    m = m.to(DEV)
+    h = hidden.to(DEV).requires_grad_()
+    out = m(h)
+    torch.testing.assert_close(out.detach().cpu(), out_ref.detach(), rtol=1e-4, atol=1e-5)
+    (out * G.to(DEV)).sum().backward()
+    _close(h.grad, h_ref.grad, 5e-4, 5e-5, "d hidden")
+    for n, p in m.named_parameters():
+        assert p.grad is not None, n
+        _close(p.grad, ref_p[n].grad, 1e-3, 1e-4, n)
+
+
+@pytest.mark.parametrize("dt,budget", [(torch.float16, 2e-2), (torch.bfloat16, 8e-2)])
+def test_mamba_module_backward_16bit_budget(dt, budget):
+    from mamba_ssm.modules.mamba_simple import Mamba
+    Dm, Lq, B = 128, 65, 2
+    p = O.make_mamba_params(Dm, bimamba_type="v1", seed=31, perturb_A=0.1)
+    g = gen(7)
+    hidden = rnd((B, Lq, Dm), g)
+    G = rnd((B, Lq, Dm), g)
+    ref_p = {k: v.clone().requires_grad_() for k, v in p.items()}
+    h_ref = hidden.clone().requires_grad_()
+    (O.mamba_forward_oracle(ref_p, h_ref, "v1") * G).sum().backward()
+    m = Mamba(Dm, bimamba_type="v1").to(DEV)
+    m.load_state_dict(p)
+    h = hidden.to(DEV).to(dt).requires_grad_()
+    (m(h).float() * G.to(DEV)).sum().backward()
+    rel = lambda a, b: (a.float().cpu() - b).abs().max().item() / max(b.abs().max().item(), 1e-9)
+    assert rel(h.grad, h_ref.grad) < budget
+    for n, q in m.named_parameters():
+        assert rel(q.grad, ref_p[n].grad) < budget, n
+
+
+def test_audio_mamba_training_step_matches_oracle_autograd():
+    """A tiny Fo-Bi AudioMamba: loss.backward() through the engine vs autograd through the oracle (fp32 tier)."""
+    from aum_b200.audio_mamba import AudioMamba
+    c = load_golden("audio_mamba_tiny.pt")["fobi_tiny"]
+    kw = c["kwargs"]
+    sd = c["state"]
+    x = c["x"]
+    tgt = (torch.rand(x.shape[0], kw["num_classes"], generator=gen(8)) > 0.7).float()
+    ref_p = {k: v.clone().requires_grad_() for k, v in sd.items()}
+    logits_ref = O.audio_mamba_forward_oracle(ref_p, x, depth=kw["depth"], bimamba_type="v1")
+    torch.nn.functional.binary_cross_entropy_with_logits(logits_ref, tgt).backward()
+    m = AudioMamba(**kw).to(DEV)
+    m.load_state_dict(sd, strict=True)
+    logits = m(x.to(DEV))
+    torch.testing.assert_close(logits.detach().cpu(), logits_ref.detach(), rtol=1e-3, atol=1e-5)
+    torch.nn.functional.binary_cross_entropy_with_logits(logits, tgt.to(DEV)).backward()
+    for n, p in m.named_parameters():
+        assert p.grad is not None and torch.isfinite(p.grad).all(), n
+        ref = ref_p[n].grad
+        err = (p.grad.cpu() - ref).abs().max().item()
+        assert err <= 2e-3 * max(ref.abs().max().item(), 1e-6) + 1e-7, (n, err, ref.abs().max().item())

@@ -108,8 +108,10 @@ def test_rmsnorm_module_matches_reference_golden():
         torch.testing.assert_close(n(c["x"].to(DEV)).cpu(), c["out_nores"], rtol=2e-5, atol=2e-6)
 
 
-def test_training_path_fails_loudly_until_backward_exists():
-    from mamba_ssm.modules.mamba_simple import Mamba
-    m = Mamba(64, bimamba_type="v1").to(DEV)
+def test_functional_ops_are_forward_only_and_say_so():
+    """The module path trains (tests/test_backward_gpu.py); the bare functional ops refuse autograd loudly."""
+    from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
+    u = torch.randn(1, 8, 16, device=DEV, requires_grad=True)
     with pytest.raises(NotImplementedError):
-        m(torch.randn(1, 8, 64, device=DEV))
+        selective_scan_fn(u, u, -torch.ones(8, 16, device=DEV), torch.randn(1, 16, 16, device=DEV),
+                          torch.randn(1, 16, 16, device=DEV))
