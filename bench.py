@@ -46,6 +46,20 @@ def peaks():
         return 6650.0, "fallback (B200_PROFILING.md 6.65 TB/s)"
 
 
+class _StdoutToStderr:
+    """NCCL prints its version banner on fd 1 during initialisation; keep stdout clean for the ONE JSON line."""
+
+    def __enter__(self):
+        sys.stdout.flush()
+        self._saved = os.dup(1)
+        os.dup2(2, 1)
+
+    def __exit__(self, *a):
+        sys.stdout.flush()
+        os.dup2(self._saved, 1)
+        os.close(self._saved)
+
+
 def scan_traffic():
     """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch from the committed ncu --set full capture."""
     try:
@@ -168,6 +182,7 @@ def main():
     ap.add_argument("--batch", type=int, default=BATCH_PER_GPU, help="clips per GPU (BASELINE config 2: 64)")
     ap.add_argument("--dtype", default="fp16", choices=["fp16", "bf16"])
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--micro-batches", type=int, default=2, help="independent sequence groups on separate CUDA streams")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
@@ -186,14 +201,18 @@ def main():
     if world > 1:
         import torch.distributed as dist_
         dist = dist_
-        dist.init_process_group("nccl", device_id=dev)
+        with _StdoutToStderr():
+            dist.init_process_group("nccl", device_id=dev)
+            dist.barrier()          # forces communicator creation (and NCCL's banner) now
+            torch.cuda.synchronize()
 
     from aum_b200 import _lib, ops
     from aum_b200.audio_mamba import AudioMamba
 
     act = torch.float16 if args.dtype == "fp16" else torch.bfloat16
     torch.manual_seed(SEED)
-    model = AudioMamba(**CFG, act_dtype=act, use_cuda_graph=not args.no_graph).to(dev).eval()
+    model = AudioMamba(**CFG, act_dtype=act, use_cuda_graph=not args.no_graph,
+                       micro_batches=args.micro_batches).to(dev).eval()
     g = torch.Generator(device="cpu").manual_seed(SEED)
     with torch.no_grad():   # move A off its structured S4D-real init, as trained weights are
         for blk in model.layers:
