@@ -37,6 +37,7 @@ class ScanDir(C.Structure):
         ("delta_bias", C.c_void_p),
         ("delta_softplus", C.c_int),
         ("last_state", C.c_void_p),
+        ("ckpt", C.c_void_p),
     ]
 
 
@@ -54,6 +55,7 @@ class ScanBwdDir(C.Structure):
         ("dD", C.c_void_p),
         ("dBC", C.c_void_p), ("ld_dbc", C.c_int64),
         ("ckpt", C.c_void_p),
+        ("ckpt_valid", C.c_int),
     ]
 
 

@@ -60,13 +60,17 @@ class MambaMixerFn(torch.autograd.Function):
         z = xz[..., Di:]
         bt = m.bimamba_type
         u, delta, dt, bc = _branch_fwd(xz, Di, N, m.conv1d, m.x_proj, m.dt_proj, False, act)
-        fwd = ops.ScanDirection(u, delta, mixer._neg_exp(m.A_log), bc[..., :N], bc[..., N:], mixer._f32(m.D))
+        # the forward scan leaves its state checkpoints (every 8 steps) for the backward kernel
+        ck_f = ops.scan_bwd_workspace(B, Lq, Di, hidden.device)
+        ck_b = ops.scan_bwd_workspace(B, Lq, Di, hidden.device) if bt != "none" else ck_f
+        fwd = ops.ScanDirection(u, delta, mixer._neg_exp(m.A_log), bc[..., :N], bc[..., N:], mixer._f32(m.D), ckpt=ck_f)
         bwd, dt_b, bc_b, scale = None, None, None, 1.0
         if bt == "v1":
-            bwd = ops.ScanDirection(u, delta, mixer._neg_exp(m.A_b_log), bc[..., :N], bc[..., N:], mixer._f32(m.D))
+            bwd = ops.ScanDirection(u, delta, mixer._neg_exp(m.A_b_log), bc[..., :N], bc[..., N:], mixer._f32(m.D), ckpt=ck_b)
         elif bt == "v2":
             ub, deltab, dt_b, bc_b = _branch_fwd(xz, Di, N, m.conv1d_b, m.x_proj_b, m.dt_proj_b, True, act)
-            bwd = ops.ScanDirection(ub, deltab, mixer._neg_exp(m.A_b_log), bc_b[..., :N], bc_b[..., N:], mixer._f32(m.D_b))
+            bwd = ops.ScanDirection(ub, deltab, mixer._neg_exp(m.A_b_log), bc_b[..., :N], bc_b[..., N:], mixer._f32(m.D_b),
+                                    ckpt=ck_b)
             scale = 0.5 if m.if_devide_out else 1.0
         out_z = torch.empty((B, Lq, Di), device=hidden.device, dtype=act)
         y_pre = torch.empty_like(out_z)
@@ -74,13 +78,14 @@ class MambaMixerFn(torch.autograd.Function):
         out_b = mixer._f32(m.out_proj.bias) if m.out_proj.bias is not None else None
         out = ops.gemm_tn(out_z.view(M, Di), mixer._w(m.out_proj.weight, act), bias=out_b).view(B, Lq, Dm)
         ctx.m, ctx.scale = m, scale
-        ctx.save_for_backward(h2, xz, dt, bc, y_pre, dt_b if dt_b is not None else dt, bc_b if bc_b is not None else bc)
+        ctx.save_for_backward(h2, xz, dt, bc, y_pre, dt_b if dt_b is not None else dt, bc_b if bc_b is not None else bc,
+                              ck_f, ck_b)
         return out
 
     @staticmethod
     def backward(ctx, dout):
         m, scale = ctx.m, ctx.scale
-        h2, xz, dt, bc, y_pre, dt_b, bc_b = ctx.saved_tensors
+        h2, xz, dt, bc, y_pre, dt_b, bc_b, ck_f, ck_b = ctx.saved_tensors
         act = xz.dtype
         B, Lq, two_di = xz.shape
         Di, N, M = two_di // 2, m.d_state, B * Lq
@@ -115,14 +120,13 @@ class MambaMixerFn(torch.autograd.Function):
         du = torch.empty((B, Lq, Di), **f32)
         ddelta = torch.empty((B, Lq, Di), **f32)
         dbc = torch.zeros((B, Lq, 2 * N), **f32)
-        ck_f = ops.scan_bwd_workspace(B, Lq, Di, dev)
-        d_f = ops.ScanBwdDirection(u, delta, A, bc, mixer._f32(m.D), du, ddelta, dA, dD, dbc, ck_f)
+        d_f = ops.ScanBwdDirection(u, delta, A, bc, mixer._f32(m.D), du, ddelta, dA, dD, dbc, ck_f, ckpt_valid=True)
         d_b = None
         grads_b = {}
         if bt == "v1":
             dA_b = torch.zeros((Di, N), **f32)
-            ck_b = ops.scan_bwd_workspace(B, Lq, Di, dev)
-            d_b = ops.ScanBwdDirection(u, delta, mixer._neg_exp(m.A_b_log), bc, mixer._f32(m.D), du, ddelta, dA_b, dD, dbc, ck_b)
+            d_b = ops.ScanBwdDirection(u, delta, mixer._neg_exp(m.A_b_log), bc, mixer._f32(m.D), du, ddelta, dA_b, dD, dbc,
+                                       ck_b, ckpt_valid=True)
         elif bt == "v2":
             ub, deltab = recompute(m.conv1d_b, m.dt_proj_b, dt_b, True)
             dA_b = torch.zeros((Di, N), **f32)
@@ -130,9 +134,8 @@ class MambaMixerFn(torch.autograd.Function):
             du_b = torch.empty((B, Lq, Di), **f32)
             ddelta_b = torch.empty((B, Lq, Di), **f32)
             dbc_b = torch.zeros((B, Lq, 2 * N), **f32)
-            ck_b = ops.scan_bwd_workspace(B, Lq, Di, dev)
             d_b = ops.ScanBwdDirection(ub, deltab, mixer._neg_exp(m.A_b_log), bc_b, mixer._f32(m.D_b), du_b, ddelta_b,
-                                       dA_b, dD_b, dbc_b, ck_b)
+                                       dA_b, dD_b, dbc_b, ck_b, ckpt_valid=True)
         ops.selective_scan_bwd(d_f, d_b, z, y_pre, dout_z, dz, out_z, out_scale=scale)
 
         g = {}

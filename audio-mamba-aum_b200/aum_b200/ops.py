@@ -96,9 +96,10 @@ class ScanDirection:
     """One time direction of the scan (struct aum_scan_dir).  All tensors token-major:
     u, delta: (B, L, D); A: (D, N) fp32; Bm, Cm: (B, L, N); D, delta_bias: (D,) fp32 or None."""
 
-    def __init__(self, u, delta, A, Bm, Cm, D=None, delta_bias=None, delta_softplus=False, last_state=None):
+    def __init__(self, u, delta, A, Bm, Cm, D=None, delta_bias=None, delta_softplus=False, last_state=None, ckpt=None):
         self.u, self.delta, self.A, self.Bm, self.Cm = u, delta, A, Bm, Cm
         self.D, self.delta_bias, self.delta_softplus, self.last_state = D, delta_bias, delta_softplus, last_state
+        self.ckpt = ckpt       # optional fp32 workspace (scan_bwd_workspace) receiving the state checkpoints
 
     def _struct(self, B, Lq, Dch, N):
         L.require_cuda(self.u, self.delta, self.A, self.Bm, self.Cm)
@@ -122,6 +123,7 @@ class ScanDirection:
         s.delta_bias = self.delta_bias.data_ptr() if self.delta_bias is not None else None
         s.delta_softplus = int(bool(self.delta_softplus))
         s.last_state = self.last_state.data_ptr() if self.last_state is not None else None
+        s.ckpt = self.ckpt.data_ptr() if self.ckpt is not None else None
         return s
 
 
@@ -221,8 +223,9 @@ class ScanBwdDirection:
     post-softplus; A: (D,16) fp32; bc: (B,L,32) fp32 packed [B|C]; outputs du, ddelta (B,L,D) fp32,
     dA (D,16), dD (D), dbc (B,L,32) fp32 accumulated into; ckpt: fp32 workspace."""
 
-    def __init__(self, u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt):
+    def __init__(self, u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt, ckpt_valid=False):
         self.t = (u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt)
+        self.ckpt_valid = ckpt_valid   # ckpt was filled by selective_scan(... ScanDirection(ckpt=...)) of the same call shape
 
     def _struct(self):
         u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt = self.t
@@ -241,6 +244,7 @@ class ScanBwdDirection:
         s.dD = dD.data_ptr() if dD is not None else None
         s.dBC, s.ld_dbc = dbc.data_ptr(), _as_rows(dbc)[2]
         s.ckpt = ckpt.data_ptr()
+        s.ckpt_valid = int(bool(self.ckpt_valid))
         return s
 
 

@@ -39,6 +39,7 @@ struct ScanBwdDirDev {
   float* dA; float* dD;
   float* dBC; int64_t ld_dbc;
   float* ckpt;
+  int ckpt_valid;
   int reverse;
 };
 
@@ -73,6 +74,27 @@ __device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane)
   return v[0];
 }
 
+// ---- per-step pieces (packed fp32x2: two states per instruction) --------------------------------------
+__device__ __forceinline__ void bwd_recompute_step(float u, float dl, const float4* __restrict__ bq,
+                                                   f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2],
+                                                   float* hist_next /* [n][SB_CH] column of this thread */) {
+  const float du_ = dl * u;
+  const f32x2 dl2 = pk2(dl, dl), du2 = pk2(du_, du_);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 Bv = __ldg(bq + q);
+    const f32x2 x0 = mul2(dl2, a2[2 * q]), x1 = mul2(dl2, a2[2 * q + 1]);
+    float e0, e1, e2, e3;
+    upk2(x0, e0, e1); upk2(x1, e2, e3);
+    h[2 * q] = fma2(pk2(ex2_approx(e0), ex2_approx(e1)), h[2 * q], mul2(du2, pk2(Bv.x, Bv.y)));
+    h[2 * q + 1] = fma2(pk2(ex2_approx(e2), ex2_approx(e3)), h[2 * q + 1], mul2(du2, pk2(Bv.z, Bv.w)));
+    float h0, h1, h2, h3;
+    upk2(h[2 * q], h0, h1); upk2(h[2 * q + 1], h2, h3);
+    hist_next[(4 * q + 0) * SB_CH] = h0; hist_next[(4 * q + 1) * SB_CH] = h1;
+    hist_next[(4 * q + 2) * SB_CH] = h2; hist_next[(4 * q + 3) * SB_CH] = h3;
+  }
+}
+
 template <typename T>
 __global__ void __launch_bounds__(2 * SB_CH, 3)
 scan_bwd_kernel(const ScanBwdParams p) {
@@ -95,54 +117,54 @@ scan_bwd_kernel(const ScanBwdParams p) {
   const bool shared = bidir && p.shared_du;
   const float scale = p.scale;
 
-  float a2[SCAN_NS], Av[SCAN_NS];
+  f32x2 a2[SCAN_NS / 2], Av2[SCAN_NS / 2];
   {
     const float4* ap = reinterpret_cast<const float4*>(d.A + (int64_t)ch * SCAN_NS);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 v = __ldg(ap + i);
-      Av[4 * i] = v.x; Av[4 * i + 1] = v.y; Av[4 * i + 2] = v.z; Av[4 * i + 3] = v.w;
+      Av2[2 * i] = pk2(v.x, v.y); Av2[2 * i + 1] = pk2(v.z, v.w);
+      a2[2 * i] = pk2(v.x * 1.4426950408889634f, v.y * 1.4426950408889634f);
+      a2[2 * i + 1] = pk2(v.z * 1.4426950408889634f, v.w * 1.4426950408889634f);
     }
-#pragma unroll
-    for (int n = 0; n < SCAN_NS; ++n) a2[n] = Av[n] * 1.4426950408889634f;
   }
   const float Dv = d.D ? __ldg(d.D + ch) : 0.f;
   const T* ub = reinterpret_cast<const T*>(d.u) + ch;
   const float* db = d.delta + ch;
-  float* ck = d.ckpt + ((int64_t)b * p.nchunks) * SCAN_NS * p.Dch + ch;    // [b][chunk][n][D]
+  float* ck = d.ckpt + ((int64_t)b * scan_ck_count_max(L)) * SCAN_NS * p.Dch + ch;    // [b][chunk][n][D]
   auto token = [&](int s) { return rev ? (L - 1 - s) : s; };
 
-  // ---------------- sweep 1: forward recurrence, checkpoint every SB_TT steps ----------------
-  {
-    float h[SCAN_NS];
+  // checkpoint chunking (identical to the forward kernels'): chunk 0 = [0, first), chunk c = [first + 8(c-1), +8)
+  const int first = min(scan_ck_first(L, bidir, rev), L);
+  const int nchunks = 1 + (L - first + SB_TT - 1) / SB_TT;
+  auto chunk_range = [&](int c, int& s0, int& ns) {
+    if (c == 0) { s0 = 0; ns = first; } else { s0 = first + (c - 1) * SB_TT; ns = min(SB_TT, L - s0); }
+  };
+  float* hcol = &hist[g][0][0][tig];                 // this thread's column; [j][n] at hcol[(j*16 + n) * SB_CH]
+
+  // ---------------- sweep 1 (only when the forward did not leave checkpoints) ----------------
+  if (!d.ckpt_valid) {
+    f32x2 h[SCAN_NS / 2];
 #pragma unroll
-    for (int n = 0; n < SCAN_NS; ++n) h[n] = 0.f;
-    for (int s = 0; s < L; ++s) {
-      if ((s % SB_TT) == 0) {
-        float* c = ck + (int64_t)(s / SB_TT) * SCAN_NS * p.Dch;
-        if (active) {
+    for (int k = 0; k < SCAN_NS / 2; ++k) h[k] = pk2(0.f, 0.f);
+    for (int c = 0; c < nchunks; ++c) {
+      int s0, ns; chunk_range(c, s0, ns);
+      if (active) {
+        float* cp = ck + (int64_t)c * SCAN_NS * p.Dch;
 #pragma unroll
-          for (int n = 0; n < SCAN_NS; ++n) c[(int64_t)n * p.Dch] = h[n];
+        for (int k = 0; k < SCAN_NS / 2; ++k) {
+          float lo, hi; upk2(h[k], lo, hi);
+          cp[(int64_t)(2 * k) * p.Dch] = lo; cp[(int64_t)(2 * k + 1) * p.Dch] = hi;
         }
       }
-      const int64_t r = row0 + token(s);
-      const float u = to_f(ub[r * d.ld_u]);
-      const float dl = db[r * d.ld_delta];
-      const float du_ = dl * u;
-      const float4* bq = reinterpret_cast<const float4*>(d.BC + r * d.ld_bc);
-#pragma unroll
-      for (int q = 0; q < 4; ++q) {
-        const float4 Bv = __ldg(bq + q);
-        const float bb[4] = {Bv.x, Bv.y, Bv.z, Bv.w};
-#pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int n = 4 * q + k;
-          h[n] = fmaf(ex2_approx(dl * a2[n]), h[n], du_ * bb[k]);
-        }
+      for (int j = 0; j < ns; ++j) {
+        const int64_t r = row0 + token(s0 + j);
+        bwd_recompute_step(to_f(ub[r * d.ld_u]), db[r * d.ld_delta], reinterpret_cast<const float4*>(d.BC + r * d.ld_bc),
+                           h, a2, hcol + SCAN_NS * SB_CH);      // (history slot 1 used as scratch here)
       }
     }
   }
-  // the checkpoints are re-read by the same thread that wrote them: no barrier needed
+  // the checkpoints are re-read by the same thread that wrote them (or were written by an earlier kernel)
 
   // ---------------- sweep 2: chunks in reverse time order ----------------
   const T* zb = p.z ? reinterpret_cast<const T*>(p.z) + ch : nullptr;
@@ -156,47 +178,52 @@ scan_bwd_kernel(const ScanBwdParams p) {
   // visiting order q = 0..L-1 of sweep 2 is s = L-1-q.  With shared du/ddelta the first Q1 visits park partials.
   const int mid = L / 2;
   const int Q1 = shared ? (rev ? (L - mid) : mid) : 0;
-  // the gate outputs (dz, out_z) are written exactly once per token: by the finalising visit when the directions
-  // share outputs, otherwise by direction slot 0.
   const bool writes_gate_all = !shared && g == 0;
+  const bool gate_here_always = writes_gate_all || !bidir;
 
-  float gcar[SCAN_NS], dA_acc[SCAN_NS];
+  f32x2 gcar[SCAN_NS / 2], dA_acc[SCAN_NS / 2];
 #pragma unroll
-  for (int n = 0; n < SCAN_NS; ++n) { gcar[n] = 0.f; dA_acc[n] = 0.f; }
+  for (int k = 0; k < SCAN_NS / 2; ++k) { gcar[k] = pk2(0.f, 0.f); dA_acc[k] = pk2(0.f, 0.f); }
   float dD_acc = 0.f;
   bool synced = false;
 
-  for (int c = p.nchunks - 1; c >= 0; --c) {
-    const int s0 = c * SB_TT;
-    const int ns = min(SB_TT, L - s0);
+  for (int c = nchunks - 1; c >= 0; --c) {
+    int s0, ns; chunk_range(c, s0, ns);
     // ---- recompute the chunk's states into shared memory
     {
-      float h[SCAN_NS];
+      f32x2 h[SCAN_NS / 2];
       const float* cp = ck + (int64_t)c * SCAN_NS * p.Dch;
 #pragma unroll
-      for (int n = 0; n < SCAN_NS; ++n) { h[n] = cp[(int64_t)n * p.Dch]; hist[g][0][n][tig] = h[n]; }
-      for (int j = 0; j < ns; ++j) {
-        const int64_t r = row0 + token(s0 + j);
-        const float u = to_f(ub[r * d.ld_u]);
-        const float dl = db[r * d.ld_delta];
-        const float du_ = dl * u;
-        const float4* bq = reinterpret_cast<const float4*>(d.BC + r * d.ld_bc);
+      for (int k = 0; k < SCAN_NS / 2; ++k) {
+        const float lo = cp[(int64_t)(2 * k) * p.Dch], hi = cp[(int64_t)(2 * k + 1) * p.Dch];
+        h[k] = pk2(lo, hi);
+        hcol[(2 * k) * SB_CH] = lo; hcol[(2 * k + 1) * SB_CH] = hi;
+      }
+      if (ns == SB_TT) {
+        float uu[SB_TT], dd_[SB_TT];
 #pragma unroll
-        for (int q = 0; q < 4; ++q) {
-          const float4 Bv = __ldg(bq + q);
-          const float bb[4] = {Bv.x, Bv.y, Bv.z, Bv.w};
+        for (int j = 0; j < SB_TT; ++j) {
+          const int64_t r = row0 + token(s0 + j);
+          uu[j] = to_f(ub[r * d.ld_u]); dd_[j] = db[r * d.ld_delta];
+        }
 #pragma unroll
-          for (int k = 0; k < 4; ++k) {
-            const int n = 4 * q + k;
-            h[n] = fmaf(ex2_approx(dl * a2[n]), h[n], du_ * bb[k]);
-            hist[g][j + 1][n][tig] = h[n];
-          }
+        for (int j = 0; j < SB_TT; ++j) {
+          const int64_t r = row0 + token(s0 + j);
+          bwd_recompute_step(uu[j], dd_[j], reinterpret_cast<const float4*>(d.BC + r * d.ld_bc), h, a2,
+                             hcol + (j + 1) * SCAN_NS * SB_CH);
+        }
+      } else {
+        for (int j = 0; j < ns; ++j) {
+          const int64_t r = row0 + token(s0 + j);
+          bwd_recompute_step(to_f(ub[r * d.ld_u]), db[r * d.ld_delta], reinterpret_cast<const float4*>(d.BC + r * d.ld_bc),
+                             h, a2, hcol + (j + 1) * SCAN_NS * SB_CH);
         }
       }
     }
     // (each thread only reads back its own column of hist: no barrier needed)
 
     // ---- reverse-time recurrence over the chunk
+#pragma unroll 2
     for (int j = ns - 1; j >= 0; --j) {
       const int s = s0 + j;
       const int qv = L - 1 - s;                       // visit index of sweep 2
@@ -212,29 +239,39 @@ scan_bwd_kernel(const ScanBwdParams p) {
       dD_acc = fmaf(dy, u, dD_acc);
       const float4* bq = reinterpret_cast<const float4*>(d.BC + r * d.ld_bc);
       float red[32];
-      float sB = 0.f, dd = 0.f;
       const float dlu = dl * u;
+      const f32x2 dl2 = pk2(dl, dl), dy2 = pk2(dy, dy), dlu2 = pk2(dlu, dlu);
+      f32x2 sB2 = pk2(0.f, 0.f), dd2 = pk2(0.f, 0.f);
+      const float* hb = hcol + j * SCAN_NS * SB_CH;              // h_{s-1}
+      const float* ha = hb + SCAN_NS * SB_CH;                    // h_s
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 Bv = __ldg(bq + q);
         const float4 Cv = __ldg(bq + 4 + q);
-        const float bb[4] = {Bv.x, Bv.y, Bv.z, Bv.w};
-        const float cc[4] = {Cv.x, Cv.y, Cv.z, Cv.w};
 #pragma unroll
-        for (int k = 0; k < 4; ++k) {
-          const int n = 4 * q + k;
-          const float a = ex2_approx(dl * a2[n]);
-          const float dh = fmaf(cc[k], dy, gcar[n]);
-          gcar[n] = a * dh;
-          const float t1 = gcar[n] * hist[g][j][n][tig];            // dh * a * h_{s-1}
-          dA_acc[n] = fmaf(t1, dl, dA_acc[n]);
-          dd = fmaf(t1, Av[n], dd);
-          sB = fmaf(dh, bb[k], sB);
-          red[n] = dh * dlu;                                        // dB contribution
-          red[SCAN_NS + n] = dy * hist[g][j + 1][n][tig];           // dC contribution
+        for (int hq = 0; hq < 2; ++hq) {
+          const int k = 2 * q + hq;                               // state pair (2k, 2k+1)
+          const f32x2 Bp = hq ? pk2(Bv.z, Bv.w) : pk2(Bv.x, Bv.y);
+          const f32x2 Cp = hq ? pk2(Cv.z, Cv.w) : pk2(Cv.x, Cv.y);
+          float e0, e1; upk2(mul2(dl2, a2[k]), e0, e1);
+          const f32x2 a = pk2(ex2_approx(e0), ex2_approx(e1));
+          const f32x2 dh = fma2(Cp, dy2, gcar[k]);
+          gcar[k] = mul2(a, dh);
+          const f32x2 hprev = pk2(hb[(2 * k) * SB_CH], hb[(2 * k + 1) * SB_CH]);
+          const f32x2 t1 = mul2(gcar[k], hprev);                  // dh * a * h_{s-1}
+          dA_acc[k] = fma2(t1, dl2, dA_acc[k]);
+          dd2 = fma2(t1, Av2[k], dd2);
+          sB2 = fma2(dh, Bp, sB2);
+          float r0, r1; upk2(mul2(dh, dlu2), r0, r1);             // dB contributions
+          red[2 * k] = r0; red[2 * k + 1] = r1;
+          red[SCAN_NS + 2 * k] = dy * ha[(2 * k) * SB_CH];        // dC contributions
+          red[SCAN_NS + 2 * k + 1] = dy * ha[(2 * k + 1) * SB_CH];
         }
       }
-      dd = fmaf(sB, u, dd);
+      float s0_, s1_, d0_, d1_;
+      upk2(sB2, s0_, s1_); upk2(dd2, d0_, d1_);
+      const float sB = s0_ + s1_;
+      float dd = fmaf(sB, u, d0_ + d1_);
       float duv = fmaf(dl, sB, Dv * dy);
       if (!active) {
 #pragma unroll
@@ -245,18 +282,14 @@ scan_bwd_kernel(const ScanBwdParams p) {
       red_add(d.dBC + r * d.ld_dbc + lane, rsum);
 
       if (shared) {
-        if (!finalize) {
-          if (active) { dub[r * d.ld_du] = duv; ddb[r * d.ld_dd] = dd; }
-        } else {
-          if (active) {
-            duv += dub[r * d.ld_du]; dd += ddb[r * d.ld_dd];
-            dub[r * d.ld_du] = duv; ddb[r * d.ld_dd] = dd;
-          }
+        if (active) {
+          if (finalize) { duv += dub[r * d.ld_du]; dd += ddb[r * d.ld_dd]; }
+          dub[r * d.ld_du] = duv; ddb[r * d.ld_dd] = dd;
         }
       } else if (active) {
         dub[r * d.ld_du] = duv; ddb[r * d.ld_dd] = dd;
       }
-      if (active && ((shared && finalize) || writes_gate_all || !bidir)) {
+      if (active && ((shared && finalize) || gate_here_always)) {
         if (zb && (dzb || ozb)) {
           const float yp = yb ? to_f(yb[r * p.ld_y]) : 0.f;
           if (dzb) {
@@ -272,7 +305,11 @@ scan_bwd_kernel(const ScanBwdParams p) {
 
   if (active) {
 #pragma unroll
-    for (int n = 0; n < SCAN_NS; ++n) atomicAdd(d.dA + (int64_t)ch * SCAN_NS + n, dA_acc[n]);
+    for (int k = 0; k < SCAN_NS / 2; ++k) {
+      float lo, hi; upk2(dA_acc[k], lo, hi);
+      atomicAdd(d.dA + (int64_t)ch * SCAN_NS + 2 * k, lo);
+      atomicAdd(d.dA + (int64_t)ch * SCAN_NS + 2 * k + 1, hi);
+    }
     if (d.dD) atomicAdd(d.dD + ch, dD_acc);
   }
 }
@@ -280,8 +317,7 @@ scan_bwd_kernel(const ScanBwdParams p) {
 }  // namespace aum
 
 extern "C" int64_t aum_selective_scan_bwd_workspace_floats(int batch, int L, int D) {
-  const int64_t nchunks = (L + aum::SB_TT - 1) / aum::SB_TT;
-  return (int64_t)batch * nchunks * aum::SCAN_NS * D;
+  return (int64_t)batch * aum::scan_ck_count_max(L) * aum::SCAN_NS * D;
 }
 
 extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_scan_bwd_dir_t* bwd,
@@ -312,7 +348,7 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
     d.u = s->u; d.ld_u = s->ld_u; d.delta = s->delta; d.ld_delta = s->ld_delta; d.A = s->A;
     d.BC = s->BC; d.ld_bc = s->ld_bc; d.D = s->D; d.du = s->du; d.ld_du = s->ld_du;
     d.ddelta = s->ddelta; d.ld_dd = s->ld_dd; d.dA = s->dA; d.dD = s->dD; d.dBC = s->dBC; d.ld_dbc = s->ld_dbc;
-    d.ckpt = s->ckpt; d.reverse = i;
+    d.ckpt = s->ckpt; d.ckpt_valid = s->ckpt_valid; d.reverse = i;
   }
   if (p.ndirs == 2) {
     const bool same_du = p.dir[0].du == p.dir[1].du, same_dd = p.dir[0].ddelta == p.dir[1].ddelta;
@@ -322,7 +358,7 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
   }
   p.z = z; p.ld_z = ld_z; p.ypre = y_pre; p.ld_y = ld_y; p.dout = dout; p.ld_dout = ld_dout;
   p.dz = dz; p.ld_dz = ld_dz; p.outz = out_z; p.ld_oz = ld_oz;
-  p.batch = batch; p.L = L; p.Dch = D; p.nchunks = (L + SB_TT - 1) / SB_TT; p.scale = out_scale;
+  p.batch = batch; p.L = L; p.Dch = D; p.nchunks = scan_ck_count_max(L); p.scale = out_scale;
   dim3 grid(ceil_div(D, SB_CH), batch);
   cudaStream_t st = (cudaStream_t)stream;
   const int smem = 2 * (SB_TT + 1) * SCAN_NS * SB_CH * (int)sizeof(float);     // 73 728 B

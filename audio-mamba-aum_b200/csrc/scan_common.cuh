@@ -21,8 +21,20 @@ struct ScanDirDev {
   const float* delta_bias;
   int delta_softplus;
   float* last_state;
+  float* ckpt;     // optional: state before each checkpoint chunk, [batch][chunk][16][D]
   int reverse;     // 0: walks l = 0..L-1, 1: walks l = L-1..0
 };
+
+// Checkpoint chunking shared by the forward kernels (writers) and the backward kernel (reader): chunk 0 covers steps
+// [0, first), chunk c >= 1 covers [first + 8(c-1), first + 8c); `first` makes the forward's phase switch S1 a chunk
+// boundary (S1 = 0 for a unidirectional walk).
+constexpr int SCAN_CK = 8;
+__host__ __device__ inline int scan_S1(int L, bool bidir, bool reverse) { return bidir ? (reverse ? (L - L / 2) : (L / 2)) : 0; }
+__host__ __device__ inline int scan_ck_first(int L, bool bidir, bool reverse) {
+  const int S1 = scan_S1(L, bidir, reverse);
+  return (S1 % SCAN_CK) ? (S1 % SCAN_CK) : SCAN_CK;
+}
+__host__ __device__ inline int scan_ck_count_max(int L) { return (L + SCAN_CK - 1) / SCAN_CK + 1; }
 
 struct ScanParams {
   ScanDirDev dir[2];

@@ -41,7 +41,8 @@ __device__ __forceinline__ void scan_chunk(int ns, const float* bc_row, int row_
                                            f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2],
                                            float Dv, float dbias, float oscale,
                                            const T* ub, int ldu, const TD* db, int ldd,
-                                           const T* zb, int ldz, T* ob, int ldo, T* ypb, int ldy, int r, int dr) {
+                                           const T* zb, int ldz, T* ob, int ldo, T* ypb, int ldy, int r, int dr,
+                                           float* ck, int ck_stride, int s_glob, int ck_first) {
   Slots w;
   // r: row of the step being computed; rl: row of the step being loaded (4 steps ahead)
   int rl = r;
@@ -64,6 +65,17 @@ __device__ __forceinline__ void scan_chunk(int ns, const float* bc_row, int row_
 #pragma unroll
     for (int i = 0; i < SCAN_U; ++i) {
       const int t = t0 + i;
+      if (ck != nullptr && t < ns) {        // training: state BEFORE this step at checkpoint-chunk starts
+        const int s = s_glob + t;
+        if (s == 0 || (s >= ck_first && ((s - ck_first) % SCAN_CK) == 0)) {
+          float* c = ck + (int64_t)(s == 0 ? 0 : 1 + (s - ck_first) / SCAN_CK) * SCAN_NS * ck_stride;
+#pragma unroll
+          for (int k = 0; k < SCAN_NS / 2; ++k) {
+            float lo, hi; upk2(h[k], lo, hi);
+            c[(int64_t)(2 * k) * ck_stride] = lo; c[(int64_t)(2 * k + 1) * ck_stride] = hi;
+          }
+        }
+      }
       float dl = w.d[i] + dbias;
       if (SP) dl = (t < ns) ? softplus_f(dl) : 0.f;
       const float u = w.u[i];
@@ -201,6 +213,9 @@ scan_fwd_kernel(const ScanParams p) {
   T* ob = reinterpret_cast<T*>(p.out) + ch;
   T* ypb = p.ypre ? reinterpret_cast<T*>(p.ypre) + ch : nullptr;
   const int ldy = (int)p.ld_ypre;
+  const int ck_first = scan_ck_first(L, bidir, rev);
+  // (lanes shadowing channel Dch-1 write the same values to the same checkpoint slots: benign)
+  float* ckp = d.ckpt ? d.ckpt + (int64_t)b * scan_ck_count_max(L) * SCAN_NS * p.Dch + ch : nullptr;
 
   for (int k = 0; k < nchunks; ++k) {
     int s0, ns; chunk_range(k, s0, ns);
@@ -239,7 +254,7 @@ scan_fwd_kernel(const ScanParams p) {
     const float* bc_row0 = &bc[rev ? (ns - 1) : 0][0];
     const int row_step = rev ? -SCAN_ROW : SCAN_ROW;
     const bool finalize = k >= n1;
-#define AUM_SCAN_CHUNK(F, P, Z) scan_chunk<T, TD, F, P, Z, SP>(ns, bc_row0, row_step, h, a2, Dv, dbias, oscale, ub, ldu, db, ldd, zb, ldz, ob, ldo, ypb, ldy, r, dr)
+#define AUM_SCAN_CHUNK(F, P, Z) scan_chunk<T, TD, F, P, Z, SP>(ns, bc_row0, row_step, h, a2, Dv, dbias, oscale, ub, ldu, db, ldd, zb, ldz, ob, ldo, ypb, ldy, r, dr, ckp, p.Dch, s0, ck_first)
     if (!finalize) AUM_SCAN_CHUNK(false, false, false);
     else if (bidir) { if (has_z) AUM_SCAN_CHUNK(true, true, true); else AUM_SCAN_CHUNK(true, true, false); }
     else            { if (has_z) AUM_SCAN_CHUNK(true, false, true); else AUM_SCAN_CHUNK(true, false, false); }
@@ -319,6 +334,8 @@ extern "C" int aum_selective_scan_fwd(const aum_scan_dir_t* fwd, const aum_scan_
                    aligned16(s->Bm)) ? 1 : 0;
     d.D = s->D; d.delta_bias = s->delta_bias; d.delta_softplus = s->delta_softplus;
     d.last_state = s->last_state; d.reverse = i;
+    d.ckpt = s->ckpt;
+    AUM_REQUIRE(!s->ckpt || N == SCAN_NS, "aum_selective_scan_fwd: checkpoints need d_state == 16");
   }
   p.z = z; p.ld_z = ld_z; p.out = out; p.ld_out = ld_out;
   p.ypre = y_pre; p.ld_ypre = ld_ypre;

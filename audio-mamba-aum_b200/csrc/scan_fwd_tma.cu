@@ -234,6 +234,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   const int sd = rev ? -(ST_CH * 4) : (ST_CH * 4);
   const int sbc = rev ? -(SCAN_ROW * 4) : (SCAN_ROW * 4);
 
+  float* ckp = d.ckpt ? d.ckpt + (int64_t)b * scan_ck_count_max(L) * SCAN_NS * p.Dch + ch : nullptr;
   float pring[ST_TT];                      // parked partials of the next 8 finalising steps
 #pragma unroll
   for (int i = 0; i < ST_TT; ++i) pring[i] = 0.f;
@@ -253,6 +254,14 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
 #pragma unroll
       for (int i = 0; i < ST_TT; ++i)
         if (s0 + i < L) pring[i] = to_f(po[i * ostep]);
+    }
+    if (ckp != nullptr && active) {        // training: state before this tile (tiles == checkpoint chunks)
+      float* c = ckp + (int64_t)k * SCAN_NS * p.Dch;
+#pragma unroll
+      for (int i = 0; i < SCAN_NS / 2; ++i) {
+        float lo, hi; upk2(h[i], lo, hi);
+        c[(int64_t)(2 * i) * p.Dch] = lo; c[(int64_t)(2 * i + 1) * p.Dch] = hi;
+      }
     }
     sbar_wait(full_bar(stage), (uint32_t)((k / ST_NSTG) & 1));
 

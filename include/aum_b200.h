@@ -108,6 +108,9 @@ typedef struct aum_scan_dir {
   const float* delta_bias;                              /* (D) fp32 or NULL               */
   int delta_softplus;                                   /* apply softplus(delta+bias)     */
   float* last_state;                                    /* (batch, D, N) fp32 or NULL     */
+  float* ckpt;                                          /* optional (training, N == 16): state checkpoints for
+                                                           aum_selective_scan_bwd, aum_selective_scan_bwd_workspace_floats()
+                                                           floats, layout [batch][chunk][N][D]                */
 } aum_scan_dir_t;
 
 AUM_API int aum_selective_scan_fwd(const aum_scan_dir_t* fwd, const aum_scan_dir_t* bwd,
@@ -141,7 +144,9 @@ typedef struct aum_scan_bwd_dir {
   float* dA;                             /* += (D, N) */
   float* dD;                             /* += (D) or NULL */
   float* dBC;    int64_t ld_dbc;         /* += (batch*L, 2N) */
-  float* ckpt;                           /* workspace */
+  float* ckpt;                           /* workspace (same size as the forward's ckpt) */
+  int ckpt_valid;                        /* 1: ckpt was filled by aum_selective_scan_fwd for the SAME direction slot and
+                                            directionality (uni/bi) — the backward then skips its own forward sweep */
 } aum_scan_bwd_dir_t;
 
 AUM_API int64_t aum_selective_scan_bwd_workspace_floats(int batch, int L, int D);

@@ -134,6 +134,13 @@ def test_mamba_module_backward_vs_oracle_autograd(bt, kw):
         _close(p.grad, ref_p[n].grad, 1e-3, 1e-4, n)
 
 
+def test_mamba_module_backward_with_generic_scan_kernel(monkeypatch):
+    """Same gradients when the forward runs the generic (non-TMA) scan kernel: its checkpoints must line up too."""
+    monkeypatch.setenv("AUM_SCAN_GENERIC", "1")
+    test_mamba_module_backward_vs_oracle_autograd("v1", {})
+    test_mamba_module_backward_vs_oracle_autograd("v2", {"if_devide_out": True})
+
+
 @pytest.mark.parametrize("dt,budget", [(torch.float16, 2e-2), (torch.bfloat16, 8e-2)])
 def test_mamba_module_backward_16bit_budget(dt, budget):
     from mamba_ssm.modules.mamba_simple import Mamba

@@ -94,6 +94,39 @@ def main():
             report(f"biscan_ch{ch}", ms, bytes_=alg, exp_per_s_T=round(M * Di * 32 / ms / 1e9, 3))
             ms = timeit(lambda: ops.selective_scan(mk(A), None, z, out=out), flush=flush)
             report(f"uniscan_ch{ch}", ms, bytes_=alg, exp_per_s_T=round(M * Di * 16 / ms / 1e9, 3))
+    if "bwd" in only:
+        u, z = rn(B, Lq, Di), rn(B, Lq, Di)
+        ypre, dout = rn(B, Lq, Di), rn(B, Lq, Di)
+        delta = torch.nn.functional.softplus(rn(B, Lq, Di, dtype=torch.float32) - 2.0)
+        bc = rn(B, Lq, 2 * N, dtype=torch.float32)
+        mkA = lambda: -torch.exp(torch.log(torch.arange(1, N + 1, device=dev, dtype=torch.float32)).repeat(Di, 1)
+                                 + 0.1 * rn(Di, N, dtype=torch.float32))
+        A, A_b = mkA(), mkA()
+        Dv = torch.ones(Di, device=dev)
+        f32 = dict(device=dev, dtype=torch.float32)
+        du, dd = torch.empty((B, Lq, Di), **f32), torch.empty((B, Lq, Di), **f32)
+        dbc = torch.zeros((B, Lq, 2 * N), **f32)
+        dA, dAb, dD = torch.zeros((Di, N), **f32), torch.zeros((Di, N), **f32), torch.zeros(Di, **f32)
+        dz, oz = torch.empty_like(u), torch.empty_like(u)
+        ckf, ckb = ops.scan_bwd_workspace(B, Lq, Di, dev), ops.scan_bwd_workspace(B, Lq, Di, dev)
+        out = torch.empty_like(u)
+        # forward with checkpoints (what training does), then the backward with and without them
+        fw = lambda: ops.selective_scan(ops.ScanDirection(u, delta, A, bc[..., :N], bc[..., N:], Dv, ckpt=ckf),
+                                        ops.ScanDirection(u, delta, A_b, bc[..., :N], bc[..., N:], Dv, ckpt=ckb), z, out=out, y_pre=ypre)
+        report("biscan_fwd_train(ckpt+ypre)", timeit(fw, flush=flush), exp_per_s_T=None)
+        for valid in (True, False):
+            bw = lambda: ops.selective_scan_bwd(
+                ops.ScanBwdDirection(u, delta, A, bc, Dv, du, dd, dA, dD, dbc, ckf, ckpt_valid=valid),
+                ops.ScanBwdDirection(u, delta, A_b, bc, Dv, du, dd, dAb, dD, dbc, ckb, ckpt_valid=valid),
+                z, ypre, dout, dz, oz)
+            report(f"biscan_bwd(ckpt_valid={valid})", timeit(bw, iters=5, flush=flush))
+        x = rn(B, Lq, 2 * Di)
+        w, b_ = rn(Di, 4, dtype=torch.float32), rn(Di, dtype=torch.float32)
+        g32 = rn(B, Lq, Di, dtype=torch.float32)
+        dx = torch.empty((B, Lq, Di), device=dev, dtype=dt)
+        dw, db_ = torch.zeros((Di, 4), **f32), torch.zeros(Di, **f32)
+        report("conv1d_bwd", timeit(lambda: ops.causal_conv1d_bwd(x[..., :Di], w, b_, g32, dx, dw, db_), flush=flush),
+               bytes_=M * Di * (2 * s + 4))
     if dt != torch.float32 and (not only or "gemm" in only):
         shapes = {"in_proj": (M, 2 * Di, Dm), "out_proj": (M, Dm, Di), "x_proj": (M, R + 2 * N, Di), "dt_proj": (M, Di, R)}
         for name, (m_, n_, k_) in shapes.items():
