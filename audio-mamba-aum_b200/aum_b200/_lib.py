@@ -54,6 +54,7 @@ class ScanBwdDir(C.Structure):
         ("dA", C.c_void_p),
         ("dD", C.c_void_p),
         ("dBC", C.c_void_p), ("ld_dbc", C.c_int64),
+        ("dbc_ws", C.c_void_p),
         ("ckpt", C.c_void_p),
         ("ckpt_valid", C.c_int),
     ]
@@ -75,17 +76,21 @@ SIGNATURES = {
                                          C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
     "aum_selective_scan_bwd_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
+    "aum_selective_scan_bwd_dbc_ws_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "aum_selective_scan_bwd": (C.c_int, [C.POINTER(ScanBwdDir), C.POINTER(ScanBwdDir), C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                         C.c_float, C.c_void_p]),
-    "aum_causal_conv1d_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
+                                         C.c_float, C.c_int, C.c_void_p]),
+    "aum_causal_conv1d_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                         C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "aum_add_rmsnorm_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,
                                       C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int, C.c_int,
                                       C.c_float, C.c_void_p]),
+    "aum_add_rmsnorm_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                      C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
     "aum_transpose": (C.c_int, [C.c_void_p, C.c_int64, C.c_int64, C.c_void_p, C.c_int64, C.c_int64,
                                 C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
 }

@@ -136,7 +136,8 @@ class MambaMixerFn(torch.autograd.Function):
             dbc_b = torch.zeros((B, Lq, 2 * N), **f32)
             d_b = ops.ScanBwdDirection(ub, deltab, mixer._neg_exp(m.A_b_log), bc_b, mixer._f32(m.D_b), du_b, ddelta_b,
                                        dA_b, dD_b, dbc_b, ck_b, ckpt_valid=True)
-        ops.selective_scan_bwd(d_f, d_b, z, y_pre, dout_z, dz, out_z, out_scale=scale)
+        # ddelta comes back already multiplied by softplus'(pre) = 1 - exp(-delta): it IS d(pre-activation)
+        ops.selective_scan_bwd(d_f, d_b, z, y_pre, dout_z, dz, out_z, out_scale=scale, softplus_grad=True)
 
         g = {}
         # ---- out_proj weight grads (library GEMM: reduction over tokens)       (reference :563-564)
@@ -151,8 +152,7 @@ class MambaMixerFn(torch.autograd.Function):
         def branch_bwd(sfx, conv, xproj, dtproj, u_, delta_, dt_, du_, ddelta_, dbc_, reverse, dx_out):
             R = dtproj.weight.shape[1]
             Rpad = dt_.shape[1]
-            # softplus'(pre) = 1 - exp(-softplus(pre)) = 1 - exp(-delta)
-            dpre = (ddelta_.view(M, Di) * (-torch.expm1(-delta_.view(M, Di))))
+            dpre = ddelta_.view(M, Di)                      # gradient w.r.t. dt_proj's pre-activation (see above)
             g[f"dt_proj{sfx}.bias"] = dpre.sum(0)
             dpre_h = dpre.to(act)
             g[f"dt_proj{sfx}.weight"] = torch.matmul(dpre_h.t(), dt_[:, :R]).float()          # (Di, R)
@@ -166,13 +166,13 @@ class MambaMixerFn(torch.autograd.Function):
             # d(conv_out) = du_scan + dx_dbl @ W_x
             wxT = mixer._cache.get(xproj.weight, f"wT_pad:{act}:{dxdbl.shape[1]}",
                                    lambda p: torch.nn.functional.pad(p.t().to(act), (0, dxdbl.shape[1] - p.shape[0])).contiguous())
-            du_tot = ops.gemm_tn(dxdbl, wxT, out_dtype=torch.float32)                            # (M, Di) fp32
-            du_tot.add_(du_.view(M, Di))
+            du_x = ops.gemm_tn(dxdbl, wxT, out_dtype=torch.float32)                              # (M, Di) fp32
             dw = torch.zeros((Di, conv.weight.shape[-1]), **f32)
             db = torch.zeros((Di,), **f32) if conv.bias is not None else None
             ops.causal_conv1d_bwd(xz[..., :Di], mixer._conv_w(conv.weight),
                                   mixer._f32(conv.bias) if conv.bias is not None else None,
-                                  du_tot.view(B, Lq, Di), dx_out, dw, db, silu=True, reverse=reverse)
+                                  du_.view(B, Lq, Di), dx_out, dw, db, silu=True, reverse=reverse,
+                                  dout2=du_x.view(B, Lq, Di))                       # sums both terms on the fly
             g[f"conv1d{sfx}.weight"] = dw.view(conv.weight.shape)
             if db is not None:
                 g[f"conv1d{sfx}.bias"] = db
@@ -217,8 +217,8 @@ def mamba_mixer_autograd(module, hidden_states):
 
 
 class AddRMSNormFn(torch.autograd.Function):
-    """Fused add + RMSNorm forward on the engine; backward with torch ops for now (the native
-    backward kernel is the next item).  Semantics of LayerNormFn (layernorm.py:380-461) with is_rms_norm=True."""
+    """Fused add + RMSNorm, forward and backward on the engine.
+    Semantics of LayerNormFn (layernorm.py:380-461) with is_rms_norm=True."""
 
     @staticmethod
     def forward(ctx, x, weight, bias, residual, prenorm, residual_in_fp32, eps):
@@ -239,14 +239,28 @@ class AddRMSNormFn(torch.autograd.Function):
     def backward(ctx, dy, *args):
         res, weight, rstd = ctx.saved_tensors
         dim = res.shape[-1]
+        dro = args[0] if (ctx.prenorm and args and args[0] is not None) else None
+        native = (not ctx.has_bias and res.dtype == torch.float32 and dim % 8 == 0 and dim <= 2048
+                  and (dro is None or dro.dtype == torch.float32) and ctx.r_dtype in (None, torch.float32))
+        if native:      # CUDA kernel (aum_add_rmsnorm_bwd)
+            dy2 = dy.reshape(-1, dim)
+            if dy2.dtype != ctx.x_dtype:
+                dy2 = dy2.to(ctx.x_dtype)
+            dy2 = dy2.contiguous()
+            dro2 = dro.reshape(-1, dim).contiguous() if dro is not None else None
+            dw = torch.zeros(dim, device=dy.device, dtype=torch.float32)
+            dx, dri = ops.add_rmsnorm_bwd(dy2, dro2, res, rstd, mixer._f32(weight), dw, want_dres_in=ctx.has_res)
+            return (dx.view(dy.shape), dw.to(weight.dtype), None, dri.view(dy.shape) if dri is not None else None,
+                    None, None, None)
+        # generic shapes / dtypes: same formula with torch ops on the GPU
         dyf = dy.reshape(-1, dim).float()
         r = res.float()
         xhat = r * rstd[:, None]
         wdy = dyf * weight.float()
         c1 = (xhat * wdy).mean(dim=-1, keepdim=True)
         dr = (wdy - xhat * c1) * rstd[:, None]
-        if ctx.prenorm and args and args[0] is not None:
-            dr = dr + args[0].reshape(-1, dim).float()
+        if dro is not None:
+            dr = dr + dro.reshape(-1, dim).float()
         dw = (dyf * xhat).sum(0).to(weight.dtype)
         db = dyf.sum(0) if ctx.has_bias else None
         dx = dr.to(ctx.x_dtype).view(dy.shape)

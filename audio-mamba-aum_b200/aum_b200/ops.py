@@ -205,14 +205,16 @@ def transpose(src: torch.Tensor, dst: Optional[torch.Tensor] = None, dst_dtype: 
 
 def causal_conv1d_bwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], dout: torch.Tensor,
                       dx: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], *, silu: bool = True,
-                      reverse: bool = False) -> None:
+                      reverse: bool = False, dout2: Optional[torch.Tensor] = None) -> None:
     """Backward of causal_conv1d.  x, dx: (B, L, D) token-major (dtype); dout: (B, L, D) fp32;
     dw (D, W) / dbias (D) fp32 are accumulated into."""
     L.require_cuda(x, w, dout, dx, dw)
     B, Lq, D = x.shape
     if dout.dtype != torch.float32 or dw.dtype != torch.float32 or dx.dtype != x.dtype:
         raise L.AumError("causal_conv1d_bwd: dout/dw must be fp32 and dx must match x")
-    rc = L.lib().aum_causal_conv1d_bwd(L.ptr(x), _as_rows(x)[2], L.ptr(w), L.ptr(bias), L.ptr(dout), _as_rows(dout)[2],
+    if dout2 is not None and (dout2.dtype != torch.float32 or _as_rows(dout2)[2] != _as_rows(dout)[2]):
+        raise L.AumError("causal_conv1d_bwd: dout2 must be fp32 with dout's pitch")
+    rc = L.lib().aum_causal_conv1d_bwd(L.ptr(x), _as_rows(x)[2], L.ptr(w), L.ptr(bias), L.ptr(dout), L.ptr(dout2), _as_rows(dout)[2],
                                        L.ptr(dx), _as_rows(dx)[2], L.ptr(dw), L.ptr(dbias), B, Lq, D, w.shape[1],
                                        L.dt(x.dtype), int(silu), int(reverse), L.stream())
     L.check(rc, "aum_causal_conv1d_bwd")
@@ -245,6 +247,10 @@ class ScanBwdDirection:
         s.dBC, s.ld_dbc = dbc.data_ptr(), _as_rows(dbc)[2]
         s.ckpt = ckpt.data_ptr()
         s.ckpt_valid = int(bool(self.ckpt_valid))
+        B, Lq, Dch = u.shape
+        n = L.lib().aum_selective_scan_bwd_dbc_ws_floats(B, Lq, Dch)
+        self._ws = torch.empty(n, device=u.device, dtype=torch.float32)   # per-warp dB|dC partials (kept alive here)
+        s.dbc_ws = self._ws.data_ptr()
         return s
 
 
@@ -254,7 +260,9 @@ def scan_bwd_workspace(batch: int, Lq: int, D: int, device) -> torch.Tensor:
 
 
 def selective_scan_bwd(fwd: Optional[ScanBwdDirection], bwd: Optional[ScanBwdDirection], z, y_pre, dout, dz, out_z,
-                       *, out_scale: float = 1.0) -> None:
+                       *, out_scale: float = 1.0, softplus_grad: bool = False) -> None:
+    """softplus_grad: the ddelta outputs are multiplied by (1 - exp(-delta)), i.e. they become the gradient w.r.t. the
+    pre-softplus dt_proj output."""
     import ctypes as C
     ref = fwd if fwd is not None else bwd
     u = ref.t[0]
@@ -265,5 +273,21 @@ def selective_scan_bwd(fwd: Optional[ScanBwdDirection], bwd: Optional[ScanBwdDir
     rc = L.lib().aum_selective_scan_bwd(C.byref(sf) if sf is not None else None, C.byref(sb) if sb is not None else None,
                                         L.ptr(z), ld(z), L.ptr(y_pre), ld(y_pre), L.ptr(dout), ld(dout),
                                         L.ptr(dz), ld(dz), L.ptr(out_z), ld(out_z),
-                                        B, Lq, Dch, 16, L.dt(u.dtype), float(out_scale), L.stream())
+                                        B, Lq, Dch, 16, L.dt(u.dtype), float(out_scale), int(softplus_grad), L.stream())
     L.check(rc, "aum_selective_scan_bwd")
+
+
+def add_rmsnorm_bwd(dy: torch.Tensor, dres_out: Optional[torch.Tensor], r: torch.Tensor, rstd: torch.Tensor,
+                    weight: torch.Tensor, dweight: torch.Tensor, *, want_dres_in: bool):
+    """Backward of add_rmsnorm (RMSNorm, no bias).  dy: (rows, dim) dtype; dres_out: (rows, dim) fp32 or None;
+    r: saved residual_out fp32; returns (dx [dy.dtype], dres_in [fp32] or None); dweight (dim) fp32 accumulated into."""
+    L.require_cuda(dy, r, rstd, weight, dweight)
+    rows, dim, ld_dy = _as_rows(dy)
+    dx = torch.empty((rows, dim), device=dy.device, dtype=dy.dtype)
+    dri = torch.empty((rows, dim), device=dy.device, dtype=torch.float32) if want_dres_in else None
+    rc = L.lib().aum_add_rmsnorm_bwd(L.ptr(dy), ld_dy, L.dt(dy.dtype), L.ptr(dres_out),
+                                     _as_rows(dres_out)[2] if dres_out is not None else 0,
+                                     L.ptr(r), _as_rows(r)[2], L.ptr(rstd), L.ptr(weight),
+                                     L.ptr(dx), dim, L.ptr(dri), dim, L.ptr(dweight), rows, dim, L.stream())
+    L.check(rc, "aum_add_rmsnorm_bwd")
+    return dx, dri

@@ -162,13 +162,13 @@ extern "C" int aum_causal_conv1d_fwd(const void* x, int64_t ldx, const float* w,
 // ======================================================================================================
 namespace aum {
 
-constexpr int CB_TL = 16;
+constexpr int CB_TL = 8;
 
 template <typename T>
-__global__ void __launch_bounds__(256)
+__global__ void __launch_bounds__(256, 3)
 conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ bias,
-                  const float* __restrict__ dout, int64_t ldd, T* __restrict__ dx, int64_t ld_dx,
-                  float* __restrict__ dw, float* __restrict__ dbias,
+                  const float* __restrict__ dout, const float* __restrict__ dout2, int64_t ldd,
+                  T* __restrict__ dx, int64_t ld_dx, float* __restrict__ dw, float* __restrict__ dbias,
                   int batch, int L, int D, int W, int silu, int reverse, int n_cgrp, int n_tgrp) {
   __shared__ float red[8][10][32];
   const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
@@ -177,6 +177,10 @@ conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
   const int b = blockIdx.x / (n_cgrp * n_tgrp);
   const int c0 = (cg * 32 + lane) * 2;
   const bool ok0 = c0 < D, ok1 = c0 + 1 < D;
+  const bool pair_ok = ok1 && (ldx % 2 == 0) && (ldd % 2 == 0) && (ld_dx % 2 == 0) &&
+                       (reinterpret_cast<uintptr_t>(x) % (2 * sizeof(T)) == 0) &&
+                       (reinterpret_cast<uintptr_t>(dx) % (2 * sizeof(T)) == 0) &&
+                       (reinterpret_cast<uintptr_t>(dout) % 8 == 0) && (reinterpret_cast<uintptr_t>(dout2) % 8 == 0);
   const int p0 = (tg * 8 + wrp) * CB_TL;           // first walk position of this warp's tile
 
   float wk[CONV_MAXW][2], bs[2];
@@ -198,42 +202,52 @@ conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
   if (p0 < L && ok0) {
     const int64_t base = (int64_t)b * L;
     auto tok = [&](int p) { return reverse ? (L - 1 - p) : p; };
-    // x at walk positions p0-3 .. p0+TL+2, dout at p0 .. p0+TL+2
+    // everything this tile touches is fetched up front (independent loads), kept packed:
+    //   x at walk positions p0-3 .. p0+TL+2, dout at p0 .. p0+TL+2
     constexpr int NX = CB_TL + 2 * (CONV_MAXW - 1);
     constexpr int ND = CB_TL + (CONV_MAXW - 1);
-    float xv[NX][2], dc[ND][2];
+    Pair<T> xr[NX];
+    float2 gr[ND];
 #pragma unroll
     for (int j = 0; j < NX; ++j) {
       const int p = p0 - (CONV_MAXW - 1) + j;
-      xv[j][0] = 0.f; xv[j][1] = 0.f;
+      xr[j].zero();
       if (p >= 0 && p < L) {
         const T* r = x + (base + tok(p)) * ldx + c0;
-        xv[j][0] = to_f(r[0]);
-        if (ok1) xv[j][1] = to_f(r[1]);
+        if (pair_ok) xr[j].load(r); else xr[j].set(to_f(r[0]), ok1 ? to_f(r[1]) : 0.f);
       }
     }
 #pragma unroll
     for (int j = 0; j < ND; ++j) {
       const int p = p0 + j;
-      dc[j][0] = 0.f; dc[j][1] = 0.f;
+      gr[j] = make_float2(0.f, 0.f);
       if (p < L) {
         const float* g = dout + (base + tok(p)) * ldd + c0;
-#pragma unroll
-        for (int v = 0; v < 2; ++v) {
-          if (v == 1 && !ok1) continue;
-          float c = bs[v];
-#pragma unroll
-          for (int k = 0; k < CONV_MAXW; ++k) c = fmaf(wk[k][v], xv[j + k][v], c);   // x[p-3+k]
-          float gd = g[v];
-          if (silu) {
-            const float sg = __fdividef(1.f, 1.f + __expf(-c));
-            gd *= sg * (1.f + c * (1.f - sg));
-          }
-          dc[j][v] = gd;
+        if (pair_ok) gr[j] = *reinterpret_cast<const float2*>(g); else gr[j] = make_float2(g[0], ok1 ? g[1] : 0.f);
+        if (dout2 != nullptr) {          // second gradient term (same layout), summed on the fly
+          const float* g2 = dout2 + (base + tok(p)) * ldd + c0;
+          if (pair_ok) { const float2 t = *reinterpret_cast<const float2*>(g2); gr[j].x += t.x; gr[j].y += t.y; }
+          else { gr[j].x += g2[0]; if (ok1) gr[j].y += g2[1]; }
         }
       }
     }
-    // dx over the tile, dw/dbias over the positions this tile owns
+    // dc[j] = dout * act'(c) at position p0 + j
+    float2 dc[ND];
+#pragma unroll
+    for (int j = 0; j < ND; ++j) {
+      float ca = bs[0], cb = bs[1];
+#pragma unroll
+      for (int k = 0; k < CONV_MAXW; ++k) {
+        const float2 f = xr[j + k].f();                     // x[p-3+k]
+        ca = fmaf(wk[k][0], f.x, ca); cb = fmaf(wk[k][1], f.y, cb);
+      }
+      float ga = gr[j].x, gb = gr[j].y;
+      if (silu) {
+        const float sa = __fdividef(1.f, 1.f + __expf(-ca)), sb = __fdividef(1.f, 1.f + __expf(-cb));
+        ga *= sa * (1.f + ca * (1.f - sa)); gb *= sb * (1.f + cb * (1.f - sb));
+      }
+      dc[j] = (p0 + j < L) ? make_float2(ga, gb) : make_float2(0.f, 0.f);
+    }
 #pragma unroll
     for (int i = 0; i < CB_TL; ++i) {
       const int p = p0 + i;
@@ -241,19 +255,20 @@ conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
         float d0 = 0.f, d1 = 0.f;
 #pragma unroll
         for (int k = 0; k < CONV_MAXW; ++k) {       // dx[p] = sum_k w[k] dc[p + 3 - k]
-          d0 = fmaf(wk[k][0], dc[i + (CONV_MAXW - 1) - k][0], d0);
-          d1 = fmaf(wk[k][1], dc[i + (CONV_MAXW - 1) - k][1], d1);
+          d0 = fmaf(wk[k][0], dc[i + (CONV_MAXW - 1) - k].x, d0);
+          d1 = fmaf(wk[k][1], dc[i + (CONV_MAXW - 1) - k].y, d1);
         }
         T* o = dx + (base + tok(p)) * ld_dx + c0;
-        o[0] = from_f<T>(d0);
-        if (ok1) o[1] = from_f<T>(d1);
+        if (pair_ok) Pair<T>::store(o, d0, d1);
+        else { o[0] = from_f<T>(d0); if (ok1) o[1] = from_f<T>(d1); }
 #pragma unroll
         for (int k = 0; k < CONV_MAXW; ++k) {       // dw[k] += dc[p] x[p-3+k]
-          acc[k] = fmaf(dc[i][0], xv[i + k][0], acc[k]);
-          acc[5 + k] = fmaf(dc[i][1], xv[i + k][1], acc[5 + k]);
+          const float2 f = xr[i + k].f();
+          acc[k] = fmaf(dc[i].x, f.x, acc[k]);
+          acc[5 + k] = fmaf(dc[i].y, f.y, acc[5 + k]);
         }
-        acc[4] += dc[i][0];
-        acc[9] += dc[i][1];
+        acc[4] += dc[i].x;
+        acc[9] += dc[i].y;
       }
     }
   }
@@ -279,7 +294,7 @@ conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
 }  // namespace aum
 
 extern "C" int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w, const float* bias,
-                                     const float* dout, int64_t ldd, void* dx, int64_t ld_dx,
+                                     const float* dout, const float* dout2, int64_t ldd, void* dx, int64_t ld_dx,
                                      float* dw, float* dbias, int batch, int L, int D, int W,
                                      int dtype, int silu, int reverse, void* stream) {
   using namespace aum;
@@ -293,9 +308,9 @@ extern "C" int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w,
   AUM_REQUIRE(blocks < (1ll << 31), "aum_causal_conv1d_bwd: grid too large");
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case AUM_F32:  conv1d_bwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, ldx, w, bias, dout, ldd, (float*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
-    case AUM_F16:  conv1d_bwd_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, ldx, w, bias, dout, ldd, (__half*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
-    case AUM_BF16: conv1d_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, w, bias, dout, ldd, (__nv_bfloat16*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
+    case AUM_F32:  conv1d_bwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, ldx, w, bias, dout, dout2, ldd, (float*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
+    case AUM_F16:  conv1d_bwd_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, ldx, w, bias, dout, dout2, ldd, (__half*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
+    case AUM_BF16: conv1d_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, w, bias, dout, dout2, ldd, (__nv_bfloat16*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
     default: set_error("aum_causal_conv1d_bwd: bad dtype %d", dtype); return 1;
   }
   return check_launch("aum_causal_conv1d_bwd");

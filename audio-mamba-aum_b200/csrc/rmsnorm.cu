@@ -145,3 +145,130 @@ extern "C" int aum_add_rmsnorm_fwd(const void* x, int64_t ldx, int x_dtype,
   }
   return check_launch("aum_add_rmsnorm_fwd");
 }
+
+// ======================================================================================================
+// Backward of fused add + RMSNorm (prenorm, fp32 residual stream).
+// Replaces the Triton _layer_norm_bwd_kernel (/root/reference/vim-mamba_ssm/mamba_ssm/ops/triton/layernorm.py:196-290)
+// for is_rms_norm=True, no bias.  With r = x + residual_in (saved), xhat = r*rstd, wdy = dy*w:
+//   dr = (wdy - xhat * mean(xhat*wdy)) * rstd + dresidual_out ;  dx = dr (x dtype) ;  dresidual_in = dr (fp32)
+//   dw += sum_rows dy * xhat
+// One warp per row, 16 consecutive rows per warp with the dw partials of the warp kept in registers, one
+// shared-memory reduction over the block's 8 warps and one atomicAdd per weight element per block.
+// ======================================================================================================
+namespace aum {
+
+constexpr int RNB_ROWS = 16;   // rows per warp
+
+template <typename TD, int NC>
+__global__ void __launch_bounds__(256)
+add_rmsnorm_bwd_kernel(const TD* __restrict__ dy, int64_t ld_dy, const float* __restrict__ dro, int64_t ld_dro,
+                       const float* __restrict__ r, int64_t ld_r, const float* __restrict__ rstd,
+                       const float* __restrict__ weight, TD* __restrict__ dx, int64_t ld_dx,
+                       float* __restrict__ dri, int64_t ld_dri, float* __restrict__ dweight, int rows, int dim) {
+  __shared__ float red[8][8 * 32];                      // per-warp dw partials of one 256-column slab
+  const int wrp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int nchunk = dim >> 3;
+  const int row0 = (blockIdx.x * 8 + wrp) * RNB_ROWS;
+  float dw[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c)
+#pragma unroll
+    for (int i = 0; i < 8; ++i) dw[c][i] = 0.f;
+  float wv[NC][8];
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    const int ch = lane + 32 * c;
+    if (ch < nchunk) { Vec8<float> t; t.load(weight + ch * 8); t.unpack(wv[c]); }
+  }
+  for (int rr = 0; rr < RNB_ROWS; ++rr) {
+    const int row = row0 + rr;
+    if (row >= rows) break;                               // warp-uniform
+    const float rs = rstd[row];
+    float xh[NC][8], wdy[NC][8];
+    float dot = 0.f;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        Vec8<TD> g; g.load(dy + (int64_t)row * ld_dy + ch * 8);
+        float gf[8]; g.unpack(gf);
+        Vec8<float> rv; rv.load(r + (int64_t)row * ld_r + ch * 8); rv.unpack(xh[c]);
+#pragma unroll
+        for (int i = 0; i < 8; ++i) {
+          xh[c][i] *= rs;
+          wdy[c][i] = gf[i] * wv[c][i];
+          dot = fmaf(xh[c][i], wdy[c][i], dot);
+          dw[c][i] = fmaf(gf[i], xh[c][i], dw[c][i]);
+        }
+      }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) dot += __shfl_xor_sync(0xffffffffu, dot, o);
+    const float c1 = dot / (float)dim;
+#pragma unroll
+    for (int c = 0; c < NC; ++c) {
+      const int ch = lane + 32 * c;
+      if (ch < nchunk) {
+        float dr[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) dr[i] = (wdy[c][i] - xh[c][i] * c1) * rs;
+        if (dro != nullptr) {
+          Vec8<float> t; t.load(dro + (int64_t)row * ld_dro + ch * 8);
+          float tf[8]; t.unpack(tf);
+#pragma unroll
+          for (int i = 0; i < 8; ++i) dr[i] += tf[i];
+        }
+        { Vec8<TD> t; t.pack(dr); t.store(dx + (int64_t)row * ld_dx + ch * 8); }
+        if (dri != nullptr) { Vec8<float> t; t.pack(dr); t.store(dri + (int64_t)row * ld_dri + ch * 8); }
+      }
+    }
+  }
+  // dweight: reduce the 8 warps of the block slab by slab (a slab = 32 lanes x 8 columns)
+#pragma unroll
+  for (int c = 0; c < NC; ++c) {
+    if (32 * c < nchunk) {                               // block-uniform
+#pragma unroll
+      for (int i = 0; i < 8; ++i) red[wrp][lane * 8 + i] = dw[c][i];
+      __syncthreads();
+      const int col = threadIdx.x;                       // 256 columns of this slab
+      float s = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) s += red[k][col];
+      const int gcol = c * 256 + col;
+      if (gcol < dim) atomicAdd(dweight + gcol, s);
+      __syncthreads();
+    }
+  }
+}
+
+}  // namespace aum
+
+extern "C" int aum_add_rmsnorm_bwd(const void* dy, int64_t ld_dy, int dy_dtype,
+                                   const float* dresidual_out, int64_t ld_dro,
+                                   const float* r, int64_t ld_r, const float* rstd, const float* weight,
+                                   void* dx, int64_t ld_dx, float* dresidual_in, int64_t ld_dri,
+                                   float* dweight, int rows, int dim, void* stream) {
+  using namespace aum;
+  AUM_REQUIRE(dy && r && rstd && weight && dx && dweight, "aum_add_rmsnorm_bwd: null pointer");
+  AUM_REQUIRE(rows >= 0 && dim > 0, "aum_add_rmsnorm_bwd: bad shape");
+  AUM_REQUIRE(dim % 8 == 0 && dim <= 8 * 32 * RN_MAXC, "aum_add_rmsnorm_bwd: dim must be a multiple of 8 and <= %d", 8 * 32 * RN_MAXC);
+  AUM_REQUIRE(ld_dy % 8 == 0 && ld_r % 8 == 0 && ld_dx % 8 == 0 && (!dresidual_out || ld_dro % 8 == 0) &&
+              (!dresidual_in || ld_dri % 8 == 0) && aligned16(dy) && aligned16(r) && aligned16(dx) && aligned16(weight) &&
+              (!dresidual_out || aligned16(dresidual_out)) && (!dresidual_in || aligned16(dresidual_in)),
+              "aum_add_rmsnorm_bwd: 16-byte aligned rows required");
+  if (rows == 0) return 0;
+  cudaStream_t st = (cudaStream_t)stream;
+  const int blocks = ceil_div(rows, 8 * RNB_ROWS);
+  const int nc = ceil_div(dim, 256);
+#define AUM_RNB(TD, NCV) add_rmsnorm_bwd_kernel<TD, NCV><<<blocks, 256, 0, st>>>((const TD*)dy, ld_dy, dresidual_out, ld_dro, r, ld_r, rstd, weight, (TD*)dx, ld_dx, dresidual_in, ld_dri, dweight, rows, dim)
+#define AUM_RNB_NC(TD) do { if (nc <= 1) AUM_RNB(TD, 1); else if (nc <= 2) AUM_RNB(TD, 2); else if (nc <= 3) AUM_RNB(TD, 3); else if (nc <= 4) AUM_RNB(TD, 4); else AUM_RNB(TD, 8); } while (0)
+  switch (dy_dtype) {
+    case AUM_F32:  AUM_RNB_NC(float); break;
+    case AUM_F16:  AUM_RNB_NC(__half); break;
+    case AUM_BF16: AUM_RNB_NC(__nv_bfloat16); break;
+    default: set_error("aum_add_rmsnorm_bwd: bad dtype %d", dy_dtype); return 1;
+  }
+#undef AUM_RNB_NC
+#undef AUM_RNB
+  return check_launch("aum_add_rmsnorm_bwd");
+}

@@ -27,6 +27,7 @@ namespace aum {
 
 constexpr int SB_CH = 64;     // channels per CTA
 constexpr int SB_TT = 8;      // checkpoint interval / chunk length
+constexpr int SB_WARPS = SB_CH / 32;   // warps per direction group
 
 struct ScanBwdDirDev {
   const void* u; int64_t ld_u;
@@ -38,6 +39,7 @@ struct ScanBwdDirDev {
   float* ddelta; int64_t ld_dd;
   float* dA; float* dD;
   float* dBC; int64_t ld_dbc;
+  float* dbc_ws;      // [part][batch*L][32] per-warp partial sums of dB|dC (no atomics), reduced by a second kernel
   float* ckpt;
   int ckpt_valid;
   int reverse;
@@ -53,6 +55,7 @@ struct ScanBwdParams {
   void* outz; int64_t ld_oz;
   int batch, L, Dch, nchunks;
   float scale;
+  int softplus_grad;
 };
 
 __device__ __forceinline__ void red_add(float* p, float v) {
@@ -101,6 +104,7 @@ scan_bwd_kernel(const ScanBwdParams p) {
   // state history of the current chunk: hist[j] = state BEFORE step j of the chunk, hist[j+1] = state after it
   extern __shared__ float hist_raw[];
   float (*hist)[SB_TT + 1][SCAN_NS][SB_CH] = reinterpret_cast<float (*)[SB_TT + 1][SCAN_NS][SB_CH]>(hist_raw);
+  const int64_t rows_total = (int64_t)p.batch * p.L;
 
   const int g = threadIdx.x / SB_CH;
   const int tig = threadIdx.x - g * SB_CH;
@@ -141,6 +145,7 @@ scan_bwd_kernel(const ScanBwdParams p) {
     if (c == 0) { s0 = 0; ns = first; } else { s0 = first + (c - 1) * SB_TT; ns = min(SB_TT, L - s0); }
   };
   float* hcol = &hist[g][0][0][tig];                 // this thread's column; [j][n] at hcol[(j*16 + n) * SB_CH]
+  const int part = blockIdx.x * SB_WARPS + (tig >> 5);   // this warp's slice of the dB|dC partial workspace
 
   // ---------------- sweep 1 (only when the forward did not leave checkpoints) ----------------
   if (!d.ckpt_valid) {
@@ -222,19 +227,28 @@ scan_bwd_kernel(const ScanBwdParams p) {
     }
     // (each thread only reads back its own column of hist: no barrier needed)
 
-    // ---- reverse-time recurrence over the chunk
-#pragma unroll 2
+    // ---- reverse-time recurrence over the chunk; the next step's operands are fetched one step ahead
+    float nu, ndl, ngo, nz = 0.f, nyp = 0.f;
+    {
+      const int64_t r = row0 + token(s0 + ns - 1);
+      nu = to_f(ub[r * d.ld_u]); ndl = db[r * d.ld_delta]; ngo = to_f(gb[r * p.ld_dout]);
+      if (zb) nz = to_f(zb[r * p.ld_z]);
+      if (yb) nyp = to_f(yb[r * p.ld_y]);
+    }
     for (int j = ns - 1; j >= 0; --j) {
       const int s = s0 + j;
       const int qv = L - 1 - s;                       // visit index of sweep 2
       if (shared && !synced && qv == Q1) { __syncthreads(); synced = true; }   // all partials are parked
       const bool finalize = !shared || qv >= Q1;
       const int64_t r = row0 + token(s);
-      const float u = to_f(ub[r * d.ld_u]);
-      const float dl = db[r * d.ld_delta];
-      const float go = to_f(gb[r * p.ld_dout]) * scale;
-      float sz = 1.f, zv = 0.f;
-      if (zb) { zv = to_f(zb[r * p.ld_z]); sz = silu_f(zv); }
+      const float u = nu, dl = ndl, go = ngo * scale, zv = nz, yp = nyp;
+      if (j > 0) {
+        const int64_t rn = row0 + token(s - 1);
+        nu = to_f(ub[rn * d.ld_u]); ndl = db[rn * d.ld_delta]; ngo = to_f(gb[rn * p.ld_dout]);
+        if (zb) nz = to_f(zb[rn * p.ld_z]);
+        if (yb) nyp = to_f(yb[rn * p.ld_y]);
+      }
+      const float sz = zb ? silu_f(zv) : 1.f;
       const float dy = go * sz;
       dD_acc = fmaf(dy, u, dD_acc);
       const float4* bq = reinterpret_cast<const float4*>(d.BC + r * d.ld_bc);
@@ -243,7 +257,6 @@ scan_bwd_kernel(const ScanBwdParams p) {
       const f32x2 dl2 = pk2(dl, dl), dy2 = pk2(dy, dy), dlu2 = pk2(dlu, dlu);
       f32x2 sB2 = pk2(0.f, 0.f), dd2 = pk2(0.f, 0.f);
       const float* hb = hcol + j * SCAN_NS * SB_CH;              // h_{s-1}
-      const float* ha = hb + SCAN_NS * SB_CH;                    // h_s
 #pragma unroll
       for (int q = 0; q < 4; ++q) {
         const float4 Bv = __ldg(bq + q);
@@ -258,14 +271,15 @@ scan_bwd_kernel(const ScanBwdParams p) {
           const f32x2 dh = fma2(Cp, dy2, gcar[k]);
           gcar[k] = mul2(a, dh);
           const f32x2 hprev = pk2(hb[(2 * k) * SB_CH], hb[(2 * k + 1) * SB_CH]);
+          const f32x2 hcur = fma2(a, hprev, mul2(dlu2, Bp));      // h_s recomputed (cheaper than two more LDS)
           const f32x2 t1 = mul2(gcar[k], hprev);                  // dh * a * h_{s-1}
           dA_acc[k] = fma2(t1, dl2, dA_acc[k]);
           dd2 = fma2(t1, Av2[k], dd2);
           sB2 = fma2(dh, Bp, sB2);
           float r0, r1; upk2(mul2(dh, dlu2), r0, r1);             // dB contributions
           red[2 * k] = r0; red[2 * k + 1] = r1;
-          red[SCAN_NS + 2 * k] = dy * ha[(2 * k) * SB_CH];        // dC contributions
-          red[SCAN_NS + 2 * k + 1] = dy * ha[(2 * k + 1) * SB_CH];
+          upk2(mul2(hcur, dy2), r0, r1);                          // dC contributions
+          red[SCAN_NS + 2 * k] = r0; red[SCAN_NS + 2 * k + 1] = r1;
         }
       }
       float s0_, s1_, d0_, d1_;
@@ -277,21 +291,22 @@ scan_bwd_kernel(const ScanBwdParams p) {
 #pragma unroll
         for (int i = 0; i < 32; ++i) red[i] = 0.f;
       }
-      // cross-channel sums of this token: lane i of each warp adds value i
+      // cross-channel sums of this token: lane i of each warp ends up with value i; one plain 128-byte store per
+      // warp into this warp's slice of the partial workspace (summed over warps by dbc_reduce_kernel)
       const float rsum = warp_transpose_reduce(red, lane);
-      red_add(d.dBC + r * d.ld_dbc + lane, rsum);
+      d.dbc_ws[((int64_t)part * rows_total + r) * 32 + lane] = rsum;
 
+      const float spg = p.softplus_grad ? (1.f - __expf(-dl)) : 1.f;     // softplus'(pre) = 1 - exp(-delta)
       if (shared) {
         if (active) {
-          if (finalize) { duv += dub[r * d.ld_du]; dd += ddb[r * d.ld_dd]; }
+          if (finalize) { duv += dub[r * d.ld_du]; dd = (dd + ddb[r * d.ld_dd]) * spg; }
           dub[r * d.ld_du] = duv; ddb[r * d.ld_dd] = dd;
         }
       } else if (active) {
-        dub[r * d.ld_du] = duv; ddb[r * d.ld_dd] = dd;
+        dub[r * d.ld_du] = duv; ddb[r * d.ld_dd] = dd * spg;
       }
       if (active && ((shared && finalize) || gate_here_always)) {
         if (zb && (dzb || ozb)) {
-          const float yp = yb ? to_f(yb[r * p.ld_y]) : 0.f;
           if (dzb) {
             const float sg = __fdividef(1.f, 1.f + __expf(-zv));             // sigmoid(z)
             dzb[r * p.ld_dz] = from_f<T>(go * yp * (sg * (1.f + zv * (1.f - sg))));
@@ -314,7 +329,21 @@ scan_bwd_kernel(const ScanBwdParams p) {
   }
 }
 
+// dBC[row][v] += sum over parts of ws[part][row][v]
+__global__ void __launch_bounds__(256)
+dbc_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dBC, int64_t ld_dbc, int64_t rows, int nparts) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= rows * 32) return;
+  float acc = 0.f;
+  for (int pp = 0; pp < nparts; ++pp) acc += ws[(int64_t)pp * rows * 32 + i];
+  dBC[(i >> 5) * ld_dbc + (i & 31)] += acc;
+}
+
 }  // namespace aum
+
+extern "C" int64_t aum_selective_scan_bwd_dbc_ws_floats(int batch, int L, int D) {
+  return (int64_t)aum::ceil_div(D, aum::SB_CH) * aum::SB_WARPS * (int64_t)batch * L * 32;
+}
 
 extern "C" int64_t aum_selective_scan_bwd_workspace_floats(int batch, int L, int D) {
   return (int64_t)batch * aum::scan_ck_count_max(L) * aum::SCAN_NS * D;
@@ -324,7 +353,8 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
                                       const void* z, int64_t ld_z, const void* y_pre, int64_t ld_y,
                                       const void* dout, int64_t ld_dout,
                                       void* dz, int64_t ld_dz, void* out_z, int64_t ld_oz,
-                                      int batch, int L, int D, int N, int dtype, float out_scale, void* stream) {
+                                      int batch, int L, int D, int N, int dtype, float out_scale,
+                                      int softplus_grad, void* stream) {
   using namespace aum;
   AUM_REQUIRE(fwd || bwd, "aum_selective_scan_bwd: at least one direction is required");
   AUM_REQUIRE(dout, "aum_selective_scan_bwd: null dout");
@@ -339,7 +369,7 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
   for (int i = 0; i < 2; ++i) {
     const aum_scan_bwd_dir_t* s = src[i];
     if (!s) continue;
-    AUM_REQUIRE(s->u && s->delta && s->A && s->BC && s->du && s->ddelta && s->dA && s->dBC && s->ckpt,
+    AUM_REQUIRE(s->u && s->delta && s->A && s->BC && s->du && s->ddelta && s->dA && s->dBC && s->ckpt && s->dbc_ws,
                 "aum_selective_scan_bwd: null pointer in direction %d", i);
     AUM_REQUIRE(s->ld_u >= D && s->ld_delta >= D && s->ld_du >= D && s->ld_dd >= D && s->ld_bc >= 2 * N && s->ld_dbc >= 2 * N,
                 "aum_selective_scan_bwd: leading dimension too small");
@@ -348,17 +378,19 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
     d.u = s->u; d.ld_u = s->ld_u; d.delta = s->delta; d.ld_delta = s->ld_delta; d.A = s->A;
     d.BC = s->BC; d.ld_bc = s->ld_bc; d.D = s->D; d.du = s->du; d.ld_du = s->ld_du;
     d.ddelta = s->ddelta; d.ld_dd = s->ld_dd; d.dA = s->dA; d.dD = s->dD; d.dBC = s->dBC; d.ld_dbc = s->ld_dbc;
-    d.ckpt = s->ckpt; d.ckpt_valid = s->ckpt_valid; d.reverse = i;
+    d.ckpt = s->ckpt; d.ckpt_valid = s->ckpt_valid; d.reverse = i; d.dbc_ws = s->dbc_ws;
   }
   if (p.ndirs == 2) {
     const bool same_du = p.dir[0].du == p.dir[1].du, same_dd = p.dir[0].ddelta == p.dir[1].ddelta;
     AUM_REQUIRE(same_du == same_dd, "aum_selective_scan_bwd: du and ddelta must be shared together or not at all");
-    AUM_REQUIRE(p.dir[0].ckpt != p.dir[1].ckpt, "aum_selective_scan_bwd: each direction needs its own checkpoint workspace");
+    AUM_REQUIRE(p.dir[0].ckpt != p.dir[1].ckpt && p.dir[0].dbc_ws != p.dir[1].dbc_ws,
+                "aum_selective_scan_bwd: each direction needs its own checkpoint and dB|dC workspaces");
     p.shared_du = same_du ? 1 : 0;
   }
   p.z = z; p.ld_z = ld_z; p.ypre = y_pre; p.ld_y = ld_y; p.dout = dout; p.ld_dout = ld_dout;
   p.dz = dz; p.ld_dz = ld_dz; p.outz = out_z; p.ld_oz = ld_oz;
   p.batch = batch; p.L = L; p.Dch = D; p.nchunks = scan_ck_count_max(L); p.scale = out_scale;
+  p.softplus_grad = softplus_grad;
   dim3 grid(ceil_div(D, SB_CH), batch);
   cudaStream_t st = (cudaStream_t)stream;
   const int smem = 2 * (SB_TT + 1) * SCAN_NS * SB_CH * (int)sizeof(float);     // 73 728 B
@@ -375,5 +407,10 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
     case AUM_F16:  scan_bwd_kernel<__half><<<grid, SB_CH * p.ndirs, smem, st>>>(p); break;
     case AUM_BF16: scan_bwd_kernel<__nv_bfloat16><<<grid, SB_CH * p.ndirs, smem, st>>>(p); break;
   }
-  return check_launch("aum_selective_scan_bwd");
+  if (int rc = check_launch("aum_selective_scan_bwd")) return rc;
+  const int64_t rows = (int64_t)batch * L;
+  const int nparts = ceil_div(D, SB_CH) * SB_WARPS;
+  for (int g = 0; g < p.ndirs; ++g)
+    dbc_reduce_kernel<<<(unsigned)ceil_div64(rows * 32, 256), 256, 0, st>>>(p.dir[g].dbc_ws, p.dir[g].dBC, p.dir[g].ld_dbc, rows, nparts);
+  return check_launch("aum_selective_scan_bwd(dbc reduce)");
 }

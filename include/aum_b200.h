@@ -79,10 +79,11 @@ AUM_API int aum_causal_conv1d_fwd(const void* x, int64_t ldx, const float* w, co
                           int dtype, int silu, int reverse, void* stream);
 
 /* Backward of the above.  replaces causal_conv1d_cuda.causal_conv1d_bwd(x, w, bias, dout, None, dx, silu)
- *   (selective_scan_interface.py:281-283, 425-427, 594-596).  dout: fp32 gradient w.r.t. the conv output
- *   (after the activation); dx: written (dtype); dw (D, W) and dbias (D) are ACCUMULATED (+=): zero them first. */
+ *   (selective_scan_interface.py:281-283, 425-427, 594-596).  dout (+ optional dout2, same pitch; the two are
+ *   summed on the fly — the scan's du and the x_proj term of :590): fp32 gradient w.r.t. the conv output (after the
+ *   activation); dx: written (dtype); dw (D, W) and dbias (D) are ACCUMULATED (+=): zero them first. */
 AUM_API int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w, const float* bias,
-                          const float* dout, int64_t ldd, void* dx, int64_t ld_dx,
+                          const float* dout, const float* dout2, int64_t ldd, void* dx, int64_t ld_dx,
                           float* dw, float* dbias, int batch, int L, int D, int W,
                           int dtype, int silu, int reverse, void* stream);
 
@@ -144,17 +145,22 @@ typedef struct aum_scan_bwd_dir {
   float* dA;                             /* += (D, N) */
   float* dD;                             /* += (D) or NULL */
   float* dBC;    int64_t ld_dbc;         /* += (batch*L, 2N) */
+  float* dbc_ws;                         /* workspace: aum_selective_scan_bwd_dbc_ws_floats() floats (per direction) */
   float* ckpt;                           /* workspace (same size as the forward's ckpt) */
   int ckpt_valid;                        /* 1: ckpt was filled by aum_selective_scan_fwd for the SAME direction slot and
                                             directionality (uni/bi) — the backward then skips its own forward sweep */
 } aum_scan_bwd_dir_t;
 
 AUM_API int64_t aum_selective_scan_bwd_workspace_floats(int batch, int L, int D);
+AUM_API int64_t aum_selective_scan_bwd_dbc_ws_floats(int batch, int L, int D);
 AUM_API int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_scan_bwd_dir_t* bwd,
                                    const void* z, int64_t ld_z, const void* y_pre, int64_t ld_y,
                                    const void* dout, int64_t ld_dout,
                                    void* dz, int64_t ld_dz, void* out_z, int64_t ld_oz,
-                                   int batch, int L, int D, int N, int dtype, float out_scale, void* stream);
+                                   int batch, int L, int D, int N, int dtype, float out_scale,
+                                   int softplus_grad, /* 1: ddelta := ddelta * (1 - exp(-delta)) = grad w.r.t. the
+                                                         pre-softplus dt_proj output (softplus'(x) = 1 - e^{-softplus(x)}) */
+                                   void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Fused residual-add + RMSNorm (fp32 residual stream) — the op on either side of the mixer.
@@ -169,6 +175,16 @@ AUM_API int aum_add_rmsnorm_fwd(const void* x, int64_t ldx, int x_dtype,
                         void* y, int64_t ldy, int y_dtype,
                         void* residual_out, int64_t ldro, int ro_dtype,
                         float* rstd_out, int rows, int dim, float eps, void* stream);
+
+/* Backward of the above (RMSNorm, no bias).  replaces Triton _layer_norm_bwd_kernel (layernorm.py:196-290).
+ *   dy: grad of y (dtype); dresidual_out: grad flowing into residual_out (fp32) or NULL; r: the saved residual_out
+ *   (x + residual_in, fp32); rstd: saved by the forward.  Writes dx (same dtype as dy) and, optionally, the fp32
+ *   dresidual_in (same values); dweight (dim) is ACCUMULATED (+=).  dim % 8 == 0, dim <= 2048. */
+AUM_API int aum_add_rmsnorm_bwd(const void* dy, int64_t ld_dy, int dy_dtype,
+                        const float* dresidual_out, int64_t ld_dro,
+                        const float* r, int64_t ld_r, const float* rstd, const float* weight,
+                        void* dx, int64_t ld_dx, float* dresidual_in, int64_t ld_dri,
+                        float* dweight, int rows, int dim, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layout adapters for the reference's channel-major (batch, C, L) tensors:

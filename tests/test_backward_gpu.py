@@ -46,6 +46,38 @@ def test_causal_conv1d_bwd(reverse, B, Lq, D, W):
     _close(db, b.grad, 1e-4, 1e-5, "dbias")
 
 
+@pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("rows,dim,prenorm,has_res", [(130, 768, True, True), (37, 96, True, False), (20, 384, False, True),
+                                                      (9, 100, True, True)])
+def test_add_rmsnorm_backward(dt, rows, dim, prenorm, has_res):
+    """rms_norm_fn under autograd (native aum_add_rmsnorm_bwd; dim=100 takes the generic formula path)."""
+    from mamba_ssm.ops.triton.layernorm import rms_norm_fn
+    g = gen(3)
+    x = rnd((rows, dim), g).to(dt)
+    res = rnd((rows, dim), g) if has_res else None
+    w = 1 + 0.1 * rnd((dim,), g)
+    Gy, Gr = rnd((rows, dim), g), rnd((rows, dim), g)
+    xr = x.float().clone().requires_grad_()
+    rr = res.clone().requires_grad_() if has_res else None
+    wr = w.clone().requires_grad_()
+    yo, ro = O.rms_norm_oracle(xr, wr, None, rr, 1e-5, prenorm=True)
+    loss = (yo * Gy).sum() + ((ro * Gr).sum() if prenorm else 0)
+    loss.backward()
+    xd = x.to(DEV).requires_grad_()
+    rd = res.to(DEV).requires_grad_() if has_res else None
+    wd = w.to(DEV).requires_grad_()
+    out = rms_norm_fn(xd, wd, None, residual=rd, prenorm=prenorm, residual_in_fp32=True, eps=1e-5)
+    if prenorm:
+        ((out[0].float() * Gy.to(DEV)).sum() + (out[1] * Gr.to(DEV)).sum()).backward()
+    else:
+        (out.float() * Gy.to(DEV)).sum().backward()
+    tol = {torch.float32: 1e-4, torch.float16: 4e-3, torch.bfloat16: 3e-2}[dt]
+    _close(xd.grad, xr.grad, tol, tol, "dx")
+    _close(wd.grad, wr.grad, max(tol, 1e-3), tol, "dweight")
+    if has_res:
+        _close(rd.grad, rr.grad, tol, tol, "dresidual")
+
+
 def _scan_ref(u, delta, A, A_b, Bm, Cm, Dv, z, scale, dirs):
     """token-major oracle: out = scale * (y_f + y_b) * silu(z) with differentiable torch ops."""
     uc, dc = u.permute(0, 2, 1), delta.permute(0, 2, 1)
