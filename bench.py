@@ -60,11 +60,12 @@ class _StdoutToStderr:
         os.close(self._saved)
 
 
-def scan_traffic():
-    """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch from the committed ncu --set full capture."""
+def scan_traffic(sequences_per_launch: int):
+    """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch, from the committed ncu --set full capture
+    (taken on a 64-sequence launch; traffic is linear in the number of sequences)."""
     try:
         t = json.load(open(os.path.join(ROOT, "profiles", "r1_scan_traffic.json")))
-        return t["dram__bytes_read.sum"] + t["dram__bytes_write.sum"]
+        return int((t["dram__bytes_read.sum"] + t["dram__bytes_write.sum"]) * sequences_per_launch / 64)
     except Exception:
         return None
 
@@ -293,7 +294,8 @@ def main():
     scan_ms = [s.elapsed_time(e) for (name, s, e) in prof if name == "selective_scan"] if prof else []
     Lq = (F_ // 16) * (T_ // 16) + 1
     Di, Nst = 2 * CFG["embed_dim"], 16
-    M = B * Lq
+    mb = args.micro_batches if (args.micro_batches > 1 and B % args.micro_batches == 0 and B >= 2 * args.micro_batches) else 1
+    M = (B // mb) * Lq            # rows one scan launch processes (one micro-batch)
     s_act = 2
     alg_bytes = M * Di * (3 * s_act + 4) + M * 2 * Nst * 4 + 4 * (2 * Di * Nst + Di)
     roof = None
@@ -301,9 +303,9 @@ def main():
         avg = sum(scan_ms) / len(scan_ms)
         ach = alg_bytes / (avg * 1e-3) / 1e9
         roof = {"kernel": "scan_fwd_kernel (fused forward+reverse selective scan)", "bound": "hbm", "achieved": ach,
-                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": scan_traffic(), "peak_source": peak_src,
+                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": scan_traffic(B // mb), "peak_source": peak_src,
                 "avg_launch_ms": avg, "launches_timed": len(scan_ms), "algorithmic_bytes_per_launch": alg_bytes,
-                "share_of_step": avg * CFG["depth"] / ms_step,
+                "share_of_step": avg * CFG["depth"] * mb / ms_step, "sequences_per_launch": B // mb,
                 "note": "16 ex2 per (token,channel,direction): MUFU-bound before HBM-bound, see DESIGN.md"}
 
     if rank == 0:
