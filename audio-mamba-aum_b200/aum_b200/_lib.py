@@ -14,7 +14,13 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 LIB_PATH = os.path.join(_HERE, "lib", "libaum_b200.so")
 
 F32, F16, BF16 = 0, 1, 2
-ACT_NONE, ACT_SOFTPLUS = 0, 1
+ACT_NONE, ACT_SOFTPLUS, ACT_SILU = 0, 1, 2
+SCAN_Z_PREGATED = 1
+
+
+def act_from(kind: int, col0: int) -> int:
+    """AUM_ACT_FROM(kind, col0): activation applied to output columns >= col0 only."""
+    return kind | (col0 << 8)
 GEMM_AUTO, GEMM_TCGEN05, GEMM_SIMT = 0, 1, 2
 
 _DT = {torch.float32: F32, torch.float16: F16, torch.bfloat16: BF16}
@@ -74,7 +80,7 @@ SIGNATURES = {
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "aum_selective_scan_fwd": (C.c_int, [C.POINTER(ScanDir), C.POINTER(ScanDir), C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
-                                         C.c_float, C.c_void_p, C.c_int64, C.c_void_p]),
+                                         C.c_float, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),
     "aum_selective_scan_bwd_workspace_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "aum_selective_scan_bwd_dbc_ws_floats": (C.c_int64, [C.c_int, C.c_int, C.c_int]),
     "aum_selective_scan_bwd": (C.c_int, [C.POINTER(ScanBwdDir), C.POINTER(ScanBwdDir), C.c_void_p, C.c_int64,

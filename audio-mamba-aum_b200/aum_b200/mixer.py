@@ -16,6 +16,7 @@ No flip, no (b d l) transpose, no B/C rearrange copy is ever made.
 """
 from __future__ import annotations
 
+import os
 import weakref
 from typing import Optional
 
@@ -23,6 +24,9 @@ import torch
 
 from . import _lib as L
 from . import ops
+
+
+_PREGATE_Z = os.environ.get("AUM_PREGATE_Z", "1") == "1"
 
 
 def _round_up(x: int, m: int) -> int:
@@ -121,7 +125,11 @@ def mamba_mixer_forward(m, hidden: torch.Tensor, *, backend: int = L.GEMM_AUTO,
     if h2.stride(-1) != 1:
         h2 = h2.contiguous()
     in_b = _f32(m.in_proj.bias) if m.in_proj.bias is not None else None
-    xz = ops.gemm_tn(h2, _w(m.in_proj.weight, act), bias=in_b, backend=backend).view(B, Lq, 2 * Di)   # (:185-191)
+    # in_proj; with pre-gating its epilogue already applies SiLU to the z half (columns >= Di), so that the
+    # MUFU-bound scan only multiplies
+    pregate = _PREGATE_Z
+    xz = ops.gemm_tn(h2, _w(m.in_proj.weight, act), bias=in_b, backend=backend,
+                     act=L.act_from(L.ACT_SILU, Di) if pregate else L.ACT_NONE).view(B, Lq, 2 * Di)    # (:185-191)
     z = xz[..., Di:]
     A = _neg_exp(m.A_log)
     Dv = _f32(m.D)
@@ -148,7 +156,7 @@ def mamba_mixer_forward(m, hidden: torch.Tensor, *, backend: int = L.GEMM_AUTO,
         fwd, bwd = ops.ScanDirection(u, delta, A, Bm, Cm, Dv), None
     else:
         raise ValueError(f"unknown bimamba_type {bt!r}")
-    out_z = ops.selective_scan(fwd, bwd, z, out_scale=scale)
+    out_z = ops.selective_scan(fwd, bwd, z, out_scale=scale, z_pregated=pregate)
     out_b = _f32(m.out_proj.bias) if m.out_proj.bias is not None else None
     out = ops.gemm_tn(out_z.view(M, Di), _w(m.out_proj.weight, act), bias=out_b, backend=backend).view(B, Lq, Dm)  # (:517)
     gamma = getattr(m, "gamma", None)

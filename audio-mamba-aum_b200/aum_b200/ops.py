@@ -129,9 +129,10 @@ class ScanDirection:
 
 def selective_scan(fwd: Optional[ScanDirection], bwd: Optional[ScanDirection], z: Optional[torch.Tensor], *,
                    out: Optional[torch.Tensor] = None, out_scale: float = 1.0,
-                   y_pre: Optional[torch.Tensor] = None) -> torch.Tensor:
+                   y_pre: Optional[torch.Tensor] = None, z_pregated: bool = False) -> torch.Tensor:
     """out = out_scale * (y_fwd + y_bwd) * silu(z); either direction may be None.  Token-major (B, L, D).
-    y_pre (optional, same shape/dtype/pitch as out) receives the pre-gate sum y_fwd + y_bwd for the backward pass."""
+    y_pre (optional, same shape/dtype/pitch as out) receives the pre-gate sum y_fwd + y_bwd for the backward pass.
+    z_pregated: z already holds silu(z) (the in_proj GEMM epilogue applied it)."""
     ref = fwd if fwd is not None else bwd
     if ref is None:
         raise L.AumError("selective_scan: no direction given")
@@ -152,7 +153,8 @@ def selective_scan(fwd: Optional[ScanDirection], bwd: Optional[ScanDirection], z
                                         C.byref(sb) if sb is not None else None,
                                         L.ptr(z), ldz, L.ptr(out), _as_rows(out)[2],
                                         B, Lq, Dch, N, L.dt(out.dtype), float(out_scale),
-                                        L.ptr(y_pre), _as_rows(y_pre)[2] if y_pre is not None else 0, L.stream())
+                                        L.ptr(y_pre), _as_rows(y_pre)[2] if y_pre is not None else 0,
+                                        L.SCAN_Z_PREGATED if z_pregated else 0, L.stream())
     L.check(rc, "aum_selective_scan_fwd")
     if PROFILE is not None:
         ev1 = torch.cuda.Event(enable_timing=True)

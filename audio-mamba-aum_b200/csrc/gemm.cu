@@ -8,12 +8,14 @@ extern "C" int aum_gemm_tn(const void* A, int64_t lda, const void* W, int64_t ld
                            const float* bias, const float* row_scale, int act,
                            int backend, void* stream) {
   using namespace aum;
+  if (M == 0 || N == 0) return 0;                     // empty output: nothing to do (pointers may be null)
   AUM_REQUIRE(A && W && C, "aum_gemm_tn: null pointer");
   AUM_REQUIRE(M >= 0 && N >= 0 && K >= 0, "aum_gemm_tn: negative size");
   AUM_REQUIRE(ab_dtype >= AUM_F32 && ab_dtype <= AUM_BF16, "aum_gemm_tn: bad ab_dtype %d", ab_dtype);
   AUM_REQUIRE(c_dtype >= AUM_F32 && c_dtype <= AUM_BF16, "aum_gemm_tn: bad c_dtype %d", c_dtype);
   AUM_REQUIRE(lda >= K && ldw >= K, "aum_gemm_tn: lda/ldw smaller than K");
-  AUM_REQUIRE(act == AUM_ACT_NONE || act == AUM_ACT_SOFTPLUS, "aum_gemm_tn: bad activation %d", act);
+  const int act_kind = act & 0xff, act_col0 = act >> 8;
+  AUM_REQUIRE(act_kind == AUM_ACT_NONE || act_kind == AUM_ACT_SOFTPLUS || act_kind == AUM_ACT_SILU, "aum_gemm_tn: bad activation %d", act);
   if (C2 == nullptr) { split = N; ldc2 = 0; c2_dtype = c_dtype; }
   AUM_REQUIRE(split >= 0 && split <= N, "aum_gemm_tn: split %d must lie in [0,N]", split);
   AUM_REQUIRE(ldc >= split, "aum_gemm_tn: ldc smaller than its column count");
@@ -24,7 +26,7 @@ extern "C" int aum_gemm_tn(const void* A, int64_t lda, const void* W, int64_t ld
   EpiParams ep;
   ep.C = C; ep.ldc = ldc; ep.c_dt = c_dtype;
   ep.C2 = C2; ep.ldc2 = ldc2; ep.c2_dt = c2_dtype; ep.split = split;
-  ep.bias = bias; ep.row_scale = row_scale; ep.act = act;
+  ep.bias = bias; ep.row_scale = row_scale; ep.act = act_kind; ep.act_col0 = act_col0;
   ep.M = M; ep.N = N;
   auto ok16 = [](const void* p, int64_t ld, int dt) {
     return aligned16(p) && ((ld * dtype_size(dt)) % 16 == 0);

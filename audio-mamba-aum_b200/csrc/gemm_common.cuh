@@ -9,7 +9,7 @@ namespace aum {
 struct EpiParams {
   void* C; int64_t ldc; int c_dt;
   void* C2; int64_t ldc2; int c2_dt; int split;
-  const float* bias; const float* row_scale; int act;
+  const float* bias; const float* row_scale; int act; int act_col0;
   int M, N;
   int vec_ok;   // all of: ldc/ldc2/base pointers allow 16-byte stores of 8-column groups
 };
@@ -17,7 +17,8 @@ struct EpiParams {
 __device__ __forceinline__ float epi_apply(const EpiParams& p, float acc, float rs, int col) {
   float v = acc * rs;
   if (p.bias != nullptr) v += __ldg(p.bias + col);
-  if (p.act == AUM_ACT_SOFTPLUS) v = softplus_f(v);
+  if (p.act == AUM_ACT_SOFTPLUS) { if (col >= p.act_col0) v = softplus_f(v); }
+  else if (p.act == AUM_ACT_SILU) { if (col >= p.act_col0) v = silu_f(v); }
   return v;
 }
 

@@ -255,14 +255,52 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
             tc_ld_32x32b_x32(t_row + (uint32_t)(c0 + cc), r);
             tc_wait_ld();
             if (!plain) {
+              // Every decision below is warp-uniform and hoisted out of the 32-element loops, so that each loop is
+              // straight-line code whose MUFU chains the compiler can interleave (a per-element predicate made this
+              // path latency-bound: 3x the MMA time per tile).
               const int colb = n0 + c0 + cc;
+              if (has_rs) {
 #pragma unroll
-              for (int i = 0; i < 32; ++i) {
-                float v = __uint_as_float(r[i]);
-                if (has_rs) v *= rs;
-                if (has_bias) v += (colb + i < N) ? __ldg(ep.bias + colb + i) : 0.f;
-                if (act == AUM_ACT_SOFTPLUS) v = softplus_fast(v);
-                r[i] = __float_as_uint(v);
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * rs);
+              }
+              if (has_bias) {
+                if (colb + 32 <= N) {
+                  const float4* bp = reinterpret_cast<const float4*>(ep.bias + colb);
+                  const bool al = (reinterpret_cast<uintptr_t>(bp) & 15) == 0;
+#pragma unroll
+                  for (int i = 0; i < 8; ++i) {
+                    float4 b4;
+                    if (al) b4 = __ldg(bp + i);
+                    else b4 = make_float4(__ldg(ep.bias + colb + 4 * i), __ldg(ep.bias + colb + 4 * i + 1),
+                                          __ldg(ep.bias + colb + 4 * i + 2), __ldg(ep.bias + colb + 4 * i + 3));
+                    r[4 * i]     = __float_as_uint(__uint_as_float(r[4 * i]) + b4.x);
+                    r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + b4.y);
+                    r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + b4.z);
+                    r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + b4.w);
+                  }
+                } else {
+#pragma unroll
+                  for (int i = 0; i < 32; ++i)
+                    if (colb + i < N) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(ep.bias + colb + i));
+                }
+              }
+              if (act != AUM_ACT_NONE && colb + 32 > ep.act_col0) {
+                if (colb >= ep.act_col0) {              // whole chunk inside the activated column range
+                  if (act == AUM_ACT_SILU) {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(silu_f(__uint_as_float(r[i])));
+                  } else {
+#pragma unroll
+                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(softplus_fast(__uint_as_float(r[i])));
+                  }
+                } else {                                // chunk straddles act_col0 (not 32-aligned): per element
+#pragma unroll
+                  for (int i = 0; i < 32; ++i) {
+                    float v = __uint_as_float(r[i]);
+                    if (colb + i >= ep.act_col0) v = (act == AUM_ACT_SILU) ? silu_f(v) : softplus_fast(v);
+                    r[i] = __float_as_uint(v);
+                  }
+                }
               }
             }
             if (c_sz == 4) {

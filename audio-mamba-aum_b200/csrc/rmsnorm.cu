@@ -118,6 +118,7 @@ extern "C" int aum_add_rmsnorm_fwd(const void* x, int64_t ldx, int x_dtype,
                                    void* residual_out, int64_t ldro, int ro_dtype,
                                    float* rstd_out, int rows, int dim, float eps, void* stream) {
   using namespace aum;
+  if (rows == 0) return 0;                            // empty input: nothing to do (pointers may be null)
   AUM_REQUIRE(x && weight && y, "aum_add_rmsnorm_fwd: null pointer");
   AUM_REQUIRE(rows >= 0 && dim > 0, "aum_add_rmsnorm_fwd: bad shape rows=%d dim=%d", rows, dim);
   AUM_REQUIRE(ldx >= dim && ldy >= dim, "aum_add_rmsnorm_fwd: leading dimension smaller than dim");

@@ -44,6 +44,7 @@ struct ScanParams {
   void* ypre; int64_t ld_ypre;   // optional: pre-gate y_fwd + y_bwd (saved for the backward pass), activation dtype
   int batch, L, Dch, N;
   float out_scale;
+  int z_pregated;                // z already holds silu(z)
 };
 
 // ---- small PTX helpers -------------------------------------------------------------------------------

@@ -42,7 +42,7 @@ __device__ __forceinline__ void scan_chunk(int ns, const float* bc_row, int row_
                                            float Dv, float dbias, float oscale,
                                            const T* ub, int ldu, const TD* db, int ldd,
                                            const T* zb, int ldz, T* ob, int ldo, T* ypb, int ldy, int r, int dr,
-                                           float* ck, int ck_stride, int s_glob, int ck_first) {
+                                           float* ck, int ck_stride, int s_glob, int ck_first, bool zpre) {
   Slots w;
   // r: row of the step being computed; rl: row of the step being loaded (4 steps ahead)
   int rl = r;
@@ -103,7 +103,7 @@ __device__ __forceinline__ void scan_chunk(int ns, const float* bc_row, int row_
       if (FINAL) {
         if (PARTIAL) y += w.p[i];
         if (ypb != nullptr && t < ns) ypb[(int64_t)r * ldy] = from_f<T>(y);
-        if (HASZ) y *= silu_f(w.z[i]);
+        if (HASZ) y *= zpre ? w.z[i] : silu_f(w.z[i]);
         y *= oscale;
       }
       if (t < ns) ob[(int64_t)r * ldo] = from_f<T>(y);
@@ -254,7 +254,7 @@ scan_fwd_kernel(const ScanParams p) {
     const float* bc_row0 = &bc[rev ? (ns - 1) : 0][0];
     const int row_step = rev ? -SCAN_ROW : SCAN_ROW;
     const bool finalize = k >= n1;
-#define AUM_SCAN_CHUNK(F, P, Z) scan_chunk<T, TD, F, P, Z, SP>(ns, bc_row0, row_step, h, a2, Dv, dbias, oscale, ub, ldu, db, ldd, zb, ldz, ob, ldo, ypb, ldy, r, dr, ckp, p.Dch, s0, ck_first)
+#define AUM_SCAN_CHUNK(F, P, Z) scan_chunk<T, TD, F, P, Z, SP>(ns, bc_row0, row_step, h, a2, Dv, dbias, oscale, ub, ldu, db, ldd, zb, ldz, ob, ldo, ypb, ldy, r, dr, ckp, p.Dch, s0, ck_first, p.z_pregated != 0)
     if (!finalize) AUM_SCAN_CHUNK(false, false, false);
     else if (bidir) { if (has_z) AUM_SCAN_CHUNK(true, true, true); else AUM_SCAN_CHUNK(true, true, false); }
     else            { if (has_z) AUM_SCAN_CHUNK(true, false, true); else AUM_SCAN_CHUNK(true, false, false); }
@@ -302,7 +302,7 @@ static int launch_scan_t(const ScanParams& p, int delta_dt, int dtype, int ch, b
 extern "C" int aum_selective_scan_fwd(const aum_scan_dir_t* fwd, const aum_scan_dir_t* bwd,
                                       const void* z, int64_t ld_z, void* out, int64_t ld_out,
                                       int batch, int L, int D, int N, int dtype,
-                                      float out_scale, void* y_pre, int64_t ld_ypre, void* stream) {
+                                      float out_scale, void* y_pre, int64_t ld_ypre, int flags, void* stream) {
   using namespace aum;
   AUM_REQUIRE(fwd || bwd, "aum_selective_scan_fwd: at least one direction is required");
   AUM_REQUIRE(out, "aum_selective_scan_fwd: null output");
@@ -339,6 +339,7 @@ extern "C" int aum_selective_scan_fwd(const aum_scan_dir_t* fwd, const aum_scan_
   }
   p.z = z; p.ld_z = ld_z; p.out = out; p.ld_out = ld_out;
   p.ypre = y_pre; p.ld_ypre = ld_ypre;
+  p.z_pregated = (flags & AUM_SCAN_Z_PREGATED) ? 1 : 0;
   AUM_REQUIRE(!y_pre || ld_ypre >= D, "aum_selective_scan_fwd: ld_ypre too small");
   p.batch = batch; p.L = L; p.Dch = D; p.N = N; p.out_scale = out_scale;
   AUM_REQUIRE(ld_out >= D && (!z || ld_z >= D), "aum_selective_scan_fwd: leading dimension too small");

@@ -33,13 +33,15 @@ template <typename T> struct StageLayout {
   static constexpr int D_BYTES = ST_TT * ST_CH * 4;
   static constexpr int Z_BYTES = U_BYTES;
   static constexpr int BC_BYTES = ST_TT * SCAN_ROW * 4;
+  static constexpr int P_BYTES = U_BYTES;                  // parked partials of the other direction (rows of `out`)
   static constexpr int OFF_U = 0, OFF_D = OFF_U + U_BYTES, OFF_Z = OFF_D + D_BYTES, OFF_BC = OFF_Z + Z_BYTES;
-  static constexpr int STAGE_BYTES = OFF_BC + BC_BYTES;
+  static constexpr int OFF_P = OFF_BC + BC_BYTES;
+  static constexpr int STAGE_BYTES = OFF_P + P_BYTES;
   static constexpr int GROUP_BYTES = ST_NSTG * STAGE_BYTES;
-  static constexpr int SMEM_BYTES = 2 * GROUP_BYTES + 128 /*align slack*/ + 2 * 2 * ST_NSTG * 8 /*mbarriers*/;
+  static constexpr int SMEM_BYTES = 2 * GROUP_BYTES + 128 /*align slack*/ + 2 * 3 * ST_NSTG * 8 /*mbarriers*/;
 };
 
-struct ScanTmaMaps { CUtensorMap u[2], d[2], z; };
+struct ScanTmaMaps { CUtensorMap u[2], d[2], z, o; };
 
 __device__ __forceinline__ void tma_tile_2d(uint32_t dst, const CUtensorMap* tm, int col, int row, uint32_t bar) {
   asm volatile(
@@ -88,52 +90,49 @@ __device__ __forceinline__ float scan_step(float u, float dl, uint32_t a_bc, flo
 }
 
 // A full 8-step tile, unguarded and fully unrolled.  po: output row of step 0 of the tile; ostep: signed row
-// stride (elements) in walk direction.  PARTIAL: pring[t] holds the parked partial of step t and is refilled
-// with step t+8 (if it exists) right after use.
+// stride (elements) in walk direction.  PARTIAL: the other direction's parked partial of each step sits in the
+// stage's P tile (TMA-loaded after the CTA barrier), addressed like u.
 template <typename T, bool FIN, bool PARTIAL, bool HASZ>
-__device__ __forceinline__ void scan_tile_full(uint32_t a_u, uint32_t a_d, uint32_t a_z, uint32_t a_bc,
+__device__ __forceinline__ void scan_tile_full(uint32_t a_u, uint32_t a_d, uint32_t a_z, uint32_t a_bc, uint32_t a_p,
                                                int su, int sd, int sbc, float Dv, float oscale, bool active,
                                                f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2],
-                                               float (&pring)[ST_TT], T* po, ptrdiff_t ostep, int steps_left_after_tile,
-                                               ptrdiff_t ypre_off) {
+                                               T* po, ptrdiff_t ostep, ptrdiff_t ypre_off, bool zpre) {
 #pragma unroll
   for (int t = 0; t < ST_TT; ++t) {
     float y = scan_step(lds_t<T>(a_u), lds_f(a_d), a_bc, Dv, h, a2);
     if (FIN) {
-      if (PARTIAL) {
-        y += pring[t];
-        if (t < steps_left_after_tile) pring[t] = to_f(po[ST_TT * ostep]);   // step t+8 of the walk
-      }
+      if (PARTIAL) y += lds_t<T>(a_p);
       if (ypre_off != 0 && active) po[ypre_off] = from_f<T>(y);   // pre-gate y saved for the backward pass
-      if (HASZ) y *= silu_f(lds_t<T>(a_z));
+      if (HASZ) { const float zv = lds_t<T>(a_z); y *= zpre ? zv : silu_f(zv); }
       y *= oscale;
     }
     if (active) *po = from_f<T>(y);
     po += ostep;
     a_u += su; a_d += sd; a_bc += sbc;
     if (FIN && HASZ) a_z += su;
+    if (PARTIAL) a_p += su;
   }
 }
 
 // A short tile (first tile of the walk or its last): rolled loop, parked partials read directly.
 template <typename T>
 __device__ __forceinline__ void scan_tile_tail(int nt, bool fin, bool partial, bool has_z,
-                                               uint32_t a_u, uint32_t a_d, uint32_t a_z, uint32_t a_bc,
+                                               uint32_t a_u, uint32_t a_d, uint32_t a_z, uint32_t a_bc, uint32_t a_p,
                                                int su, int sd, int sbc, float Dv, float oscale, bool active,
                                                f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2],
-                                               T* po, ptrdiff_t ostep, ptrdiff_t ypre_off) {
+                                               T* po, ptrdiff_t ostep, ptrdiff_t ypre_off, bool zpre) {
 #pragma unroll 1
   for (int t = 0; t < nt; ++t) {
     float y = scan_step(lds_t<T>(a_u), lds_f(a_d), a_bc, Dv, h, a2);
     if (fin) {
-      if (partial) y += to_f(*po);
+      if (partial) y += lds_t<T>(a_p);
       if (ypre_off != 0 && active) po[ypre_off] = from_f<T>(y);
-      if (has_z) y *= silu_f(lds_t<T>(a_z));
+      if (has_z) { const float zv = lds_t<T>(a_z); y *= zpre ? zv : silu_f(zv); }
       y *= oscale;
     }
     if (active) *po = from_f<T>(y);
     po += ostep;
-    a_u += su; a_d += sd; a_z += su; a_bc += sbc;
+    a_u += su; a_d += sd; a_z += su; a_bc += sbc; a_p += su;
   }
 }
 
@@ -157,14 +156,16 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   const bool rev = d.reverse != 0;
   const int row0 = b * L;
   const bool has_z = p.z != nullptr;
+  const bool zpre = p.z_pregated != 0;
 
   const uint32_t ring = smem0 + (uint32_t)g * SL::GROUP_BYTES;
-  const uint32_t bars = smem0 + 2u * SL::GROUP_BYTES + (uint32_t)g * (2 * ST_NSTG * 8);
+  const uint32_t bars = smem0 + (uint32_t)p.ndirs * SL::GROUP_BYTES + (uint32_t)g * (3 * ST_NSTG * 8);
   auto full_bar = [&](int s) { return bars + 8u * s; };
   auto empty_bar = [&](int s) { return bars + 8u * (ST_NSTG + s); };
+  auto pfull_bar = [&](int s) { return bars + 8u * (2 * ST_NSTG + s); };   // parked-partial tiles (phase 2 only)
 
   if (tig == 0) {
-    for (int s = 0; s < ST_NSTG; ++s) { sbar_init(full_bar(s), 1); sbar_init(empty_bar(s), ST_CH / 32); }
+    for (int s = 0; s < ST_NSTG; ++s) { sbar_init(full_bar(s), 1); sbar_init(empty_bar(s), ST_CH / 32); sbar_init(pfull_bar(s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -185,6 +186,15 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   };
 
   // ---- producer: one elected thread per direction
+  bool past_barrier = !bidir;       // parked partials may only be fetched after the CTA-wide phase barrier
+  int issued_upto = -1;             // highest tile whose main operands have been issued (producer thread only)
+  auto issue_partial = [&](int k) {
+    int s0, nt; tile_range(k, s0, nt);
+    const int stage = k % ST_NSTG;
+    const int brow = rev ? (row0 + L - s0 - ST_TT) : (row0 + s0);
+    sbar_expect_tx(pfull_bar(stage), SL::P_BYTES);
+    tma_tile_2d(ring + (uint32_t)stage * SL::STAGE_BYTES + SL::OFF_P, &maps.o, blockIdx.x * ST_CH, brow, pfull_bar(stage));
+  };
   auto issue_tile = [&](int k) {
     int s0, nt; tile_range(k, s0, nt);
     const int stage = k % ST_NSTG;
@@ -205,6 +215,8 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     const float* src = reinterpret_cast<const float*>(d.Bm) + (int64_t)(row0 + bc_row_lo) * SCAN_ROW;
     const uint32_t dst = st + SL::OFF_BC + (rev ? (uint32_t)(ST_TT - nt) * SCAN_ROW * 4u : 0u);
     bulk_g2s(dst, src, bc_bytes, bar);
+    issued_upto = k;
+    if (bidir && fin && past_barrier) issue_partial(k);
   };
   if (tig == 0) {
     for (int k = 0; k < ST_NSTG && k < ntiles; ++k) issue_tile(k);
@@ -235,9 +247,6 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   const int sbc = rev ? -(SCAN_ROW * 4) : (SCAN_ROW * 4);
 
   float* ckp = d.ckpt ? d.ckpt + (int64_t)b * scan_ck_count_max(L) * SCAN_NS * p.Dch + ch : nullptr;
-  float pring[ST_TT];                      // parked partials of the next 8 finalising steps
-#pragma unroll
-  for (int i = 0; i < ST_TT; ++i) pring[i] = 0.f;
 
   for (int k = 0; k < ntiles; ++k) {
     int s0, nt; tile_range(k, s0, nt);
@@ -246,15 +255,17 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     const bool fin = k >= n1t;
     const bool partial = fin && bidir;
     if (bidir && k == n1t) {
-      __syncthreads();                     // every partial of both directions is parked
+      // every partial of both directions is parked: make the generic-proxy stores visible to the async proxy
+      // (TMA) before any thread fetches them, then let the producer catch up on the tiles already in flight
+      asm volatile("fence.proxy.async.global;" ::: "memory");
+      __syncthreads();
+      if (tig == 0) {
+        for (int kk = n1t; kk <= issued_upto; ++kk) issue_partial(kk);
+        past_barrier = true;
+      }
     }
     const int r = row0 + (rev ? (L - 1 - s0) : s0);    // global row of step s0
     T* po = ob + (int64_t)r * ldo;
-    if (partial && k == n1t) {             // prime the ring with the first 8 finalising steps
-#pragma unroll
-      for (int i = 0; i < ST_TT; ++i)
-        if (s0 + i < L) pring[i] = to_f(po[i * ostep]);
-    }
     if (ckp != nullptr && active) {        // training: state before this tile (tiles == checkpoint chunks)
       float* c = ckp + (int64_t)k * SCAN_NS * p.Dch;
 #pragma unroll
@@ -264,6 +275,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
       }
     }
     sbar_wait(full_bar(stage), (uint32_t)((k / ST_NSTG) & 1));
+    if (partial) sbar_wait(pfull_bar(stage), (uint32_t)(((k - n1t) / ST_NSTG) & 1));
 
     // addresses inside the stage for this thread's channel; step t lives at tile row (rev ? TT-1-t : t)
     const int row_first = rev ? (ST_TT - 1) : 0;
@@ -271,15 +283,15 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     const uint32_t a_d = st + SL::OFF_D + (uint32_t)(row_first * ST_CH + tig) * 4u;
     const uint32_t a_z = st + SL::OFF_Z + (uint32_t)(row_first * ST_CH + tig) * (uint32_t)sizeof(T);
     const uint32_t a_bc = st + SL::OFF_BC + (uint32_t)row_first * SCAN_ROW * 4u;
+    const uint32_t a_p = st + SL::OFF_P + (uint32_t)(row_first * ST_CH + tig) * (uint32_t)sizeof(T);
     if (nt == ST_TT) {
-      const int left = L - (s0 + ST_TT);   // steps of the walk after this tile (ring refills stop there)
-#define AUM_TILE(F, P, Z) scan_tile_full<T, F, P, Z>(a_u, a_d, a_z, a_bc, su, sd, sbc, Dv, oscale, active, h, a2, pring, po, ostep, left, ypre_off)
+#define AUM_TILE(F, P, Z) scan_tile_full<T, F, P, Z>(a_u, a_d, a_z, a_bc, a_p, su, sd, sbc, Dv, oscale, active, h, a2, po, ostep, ypre_off, zpre)
       if (!fin) AUM_TILE(false, false, false);
       else if (partial) { if (has_z) AUM_TILE(true, true, true); else AUM_TILE(true, true, false); }
       else { if (has_z) AUM_TILE(true, false, true); else AUM_TILE(true, false, false); }
 #undef AUM_TILE
     } else {
-      scan_tile_tail<T>(nt, fin, partial, has_z, a_u, a_d, a_z, a_bc, su, sd, sbc, Dv, oscale, active, h, a2, po, ostep, ypre_off);
+      scan_tile_tail<T>(nt, fin, partial, has_z, a_u, a_d, a_z, a_bc, a_p, su, sd, sbc, Dv, oscale, active, h, a2, po, ostep, ypre_off, zpre);
     }
 
     // hand the stage back; one thread refills the stage released one tile earlier
@@ -294,7 +306,10 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     }
     (void)warp_in_group;
   }
-  if (bidir && n2t == 0) __syncthreads();   // (degenerate) keep the CTA barrier count equal across directions
+  if (bidir && n2t == 0) {                  // (degenerate) keep the CTA barrier count equal across directions
+    asm volatile("fence.proxy.async.global;" ::: "memory");
+    __syncthreads();
+  }
 
   if (active && d.last_state != nullptr) {
 #pragma unroll
@@ -310,18 +325,15 @@ template <typename T>
 static int launch_t(const ScanTmaMaps& maps, const ScanParams& p, cudaStream_t st) {
   using SL = StageLayout<T>;
   static bool attr_set = false;
-  static int occ = 3;       // resident CTAs per SM the kernel is compiled for (2: 128 regs, 3: 80 regs)
+  // two resident CTAs per SM (128 registers, ~90 KB of stages each); a 3-CTA / 80-register build measured slower
   if (!attr_set) {
-    if (const char* e = getenv("AUM_SCAN_OCC")) { const int v = atoi(e); if (v == 2 || v == 3) occ = v; }
-    if (sizeof(T) == 4) occ = 2;        // fp32 stages are too large for three CTAs per SM
     cudaError_t e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, 3>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("aum_selective_scan_fwd: cudaFuncSetAttribute(smem=%d): %s", SL::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
     attr_set = true;
   }
   dim3 grid(ceil_div(p.Dch, ST_CH), p.batch);
-  if (occ == 3) scan_fwd_tma_kernel<T, 3><<<grid, ST_CH * p.ndirs, SL::SMEM_BYTES, st>>>(maps, p);
-  else scan_fwd_tma_kernel<T, 2><<<grid, ST_CH * p.ndirs, SL::SMEM_BYTES, st>>>(maps, p);
+  const int smem = p.ndirs * SL::GROUP_BYTES + 128 + 2 * 3 * ST_NSTG * 8;     // one ring per direction actually launched
+  scan_fwd_tma_kernel<T, 2><<<grid, ST_CH * p.ndirs, smem, st>>>(maps, p);
   return check_launch("aum_selective_scan_fwd(tma)");
 }
 
@@ -346,6 +358,7 @@ int launch_scan_tma(const ScanParams& p, int dtype, int delta_dt, cudaStream_t s
   }
   if (p.z) { if (int rc = tma_encode_2d(&maps.z, p.z, dtype, rows, p.Dch, p.ld_z, ST_TT, ST_CH, false, "aum_selective_scan_fwd(z)")) return rc; }
   else maps.z = maps.u[0];
+  if (int rc = tma_encode_2d(&maps.o, p.out, dtype, rows, p.Dch, p.ld_out, ST_TT, ST_CH, false, "aum_selective_scan_fwd(out)")) return rc;
   switch (dtype) {
     case AUM_F32:  return launch_t<float>(maps, p, st);
     case AUM_F16:  return launch_t<__half>(maps, p, st);

@@ -39,7 +39,13 @@ extern "C" {
 enum aum_dtype { AUM_F32 = 0, AUM_F16 = 1, AUM_BF16 = 2 };
 
 /* GEMM epilogue activation */
-enum aum_act { AUM_ACT_NONE = 0, AUM_ACT_SOFTPLUS = 1 /* torch softplus, threshold 20 */ };
+enum aum_act { AUM_ACT_NONE = 0, AUM_ACT_SOFTPLUS = 1 /* torch softplus, threshold 20 */, AUM_ACT_SILU = 2 };
+/* act argument of aum_gemm_tn: low 8 bits = aum_act, upper bits = first column the activation applies to
+ * (AUM_ACT_FROM(AUM_ACT_SILU, Di) gates only the z half of in_proj's output). */
+#define AUM_ACT_FROM(kind, col0) ((int)(kind) | ((int)(col0) << 8))
+
+/* flags of aum_selective_scan_fwd */
+enum aum_scan_flags { AUM_SCAN_Z_PREGATED = 1 /* z already holds silu(z) (in_proj epilogue applied it) */ };
 
 /* GEMM backend selection */
 enum aum_gemm_backend { AUM_GEMM_AUTO = 0, AUM_GEMM_TCGEN05 = 1, AUM_GEMM_SIMT = 2 };
@@ -120,6 +126,7 @@ AUM_API int aum_selective_scan_fwd(const aum_scan_dir_t* fwd, const aum_scan_dir
                            int batch, int L, int D, int N, int dtype,
                            float out_scale,
                            void* y_pre, int64_t ld_ypre,   /* optional (training): pre-gate y_fwd+y_bwd, dtype */
+                           int flags,                      /* aum_scan_flags */
                            void* stream);
 
 /* ---------------------------------------------------------------------------------------------

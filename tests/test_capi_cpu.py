@@ -41,7 +41,7 @@ def test_argument_errors_are_reported_not_crashed():
     lib = _lib.lib()
     rc = lib.aum_causal_conv1d_fwd(None, 0, None, None, None, 0, 1, 1, 1, 4, 0, 1, 0, None)
     assert rc != 0 and b"null" in lib.aum_last_error()
-    rc = lib.aum_selective_scan_fwd(None, None, None, 0, None, 0, 1, 1, 1, 16, 0, 1.0, None, 0, None)
+    rc = lib.aum_selective_scan_fwd(None, None, None, 0, None, 0, 1, 1, 1, 16, 0, 1.0, None, 0, 0, None)
     assert rc != 0 and b"direction" in lib.aum_last_error()
 
 

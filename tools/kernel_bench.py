@@ -92,6 +92,8 @@ def main():
             os.environ["AUM_SCAN_CH"] = ch
             ms = timeit(lambda: ops.selective_scan(mk(A), mk(A_b), z, out=out), flush=flush)
             report(f"biscan_ch{ch}", ms, bytes_=alg, exp_per_s_T=round(M * Di * 32 / ms / 1e9, 3))
+            ms = timeit(lambda: ops.selective_scan(mk(A), mk(A_b), z, out=out, z_pregated=True), flush=flush)
+            report(f"biscan_pregated_ch{ch}", ms, bytes_=alg, exp_per_s_T=round(M * Di * 32 / ms / 1e9, 3))
             ms = timeit(lambda: ops.selective_scan(mk(A), None, z, out=out), flush=flush)
             report(f"uniscan_ch{ch}", ms, bytes_=alg, exp_per_s_T=round(M * Di * 16 / ms / 1e9, 3))
     if "bwd" in only:
@@ -140,6 +142,10 @@ def main():
             if name in ("in_proj", "out_proj"):
                 ms = timeit(lambda: torch.matmul(a, w.t(), out=out), flush=flush)
                 report("cublas_" + name, ms, flops=2.0 * m_ * n_ * k_)
+            if name == "in_proj":
+                ms = timeit(lambda: ops.gemm_tn(a, w, out=out, k=k_, backend=L.GEMM_TCGEN05,
+                                                act=L.act_from(L.ACT_SILU, n_ // 2)), flush=flush)
+                report("gemm_in_proj+silu(z)", ms, flops=2.0 * m_ * n_ * k_)
 
 
 if __name__ == "__main__":

@@ -17,6 +17,6 @@ Dv = torch.ones(Di, device=dev)
 mk = lambda Ax: ops.ScanDirection(u, delta, Ax, bc[..., :N], bc[..., N:], Dv)
 out = torch.empty_like(u)
 for _ in range(4):
-    ops.selective_scan(mk(A), mk(A_b), z, out=out)
+    ops.selective_scan(mk(A), mk(A_b), z, out=out, z_pregated=os.environ.get("PREGATED", "0") == "1")
 torch.cuda.synchronize()
 print("ok")
