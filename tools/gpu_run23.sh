@@ -1,0 +1,9 @@
+#!/bin/bash
+cd "${GRAFT_REPO_ROOT:-/root/repo}"
+mkdir -p gpurun_out
+timeout 900 python -m pytest tests -q -m gpu -p no:cacheprovider -x > gpurun_out/t_all.log 2>&1; echo "pytest rc=$?"; grep -E "passed|failed|Error" gpurun_out/t_all.log | tail -8
+for n in 4 5; do
+AUM_SCAN_NSTG=$n AUM_SCAN_CH=128 timeout 300 python tools/kernel_bench.py --only scan > gpurun_out/kb_n$n.log 2>&1; echo "kb nstg=$n rc=$?"; grep -E "ch128" gpurun_out/kb_n$n.log
+AUM_SCAN_NSTG=$n timeout 600 python bench.py --steps 20 --warmup 5 --no-cpu-baseline > gpurun_out/bench14_n$n.json 2> gpurun_out/bench14.err; echo "bench rc=$?"; python -c "
+import json; d=json.load(open('gpurun_out/bench14_n$n.json')); print('nstg=$n', {k:d[k] for k in ('value','ms_per_step')}, d['e2e']['value'], d['roofline']['frac'], d['roofline']['avg_launch_ms'])"
+done
