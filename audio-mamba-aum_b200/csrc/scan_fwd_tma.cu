@@ -413,7 +413,7 @@ static int launch_n(const ScanTmaMaps& maps, const ScanParams& p, cudaStream_t s
 template <typename T>
 static int launch_t(const ScanTmaMaps& maps, const ScanParams& p, cudaStream_t st) {
   static int nstg = 0;
-  if (nstg == 0) { const char* e = getenv("AUM_SCAN_NSTG"); nstg = (e && atoi(e) == 5) ? 5 : 4;   // 4 measured best (5: -1..3%) }
+  if (nstg == 0) { const char* e = getenv("AUM_SCAN_NSTG"); nstg = (e && atoi(e) == 5) ? 5 : 4; }   // 4 measured best (5: 1-3% slower)
   return nstg == 4 ? launch_n<T, 4>(maps, p, st) : launch_n<T, 5>(maps, p, st);
 }
 
