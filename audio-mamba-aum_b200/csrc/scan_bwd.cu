@@ -20,61 +20,14 @@
 // dB/dC are sums over channels: a 31-shuffle butterfly leaves lane i with value i of the warp's 32 channels,
 // one red.global.add.f32 per lane and token.  du / ddelta of the two directions (shared u, delta in Fo-Bi) meet
 // through the same park-in-the-output trick as the forward kernel (one CTA barrier at the midpoint).
-// This is the first, correctness-oriented version of the kernel (plain global loads, no TMA ring yet).
-#include "scan_common.cuh"
+// This generic kernel (plain global loads) is the fallback of the TMA-streamed kernel in scan_bwd_tma.cu; it also
+// regenerates the checkpoints when the forward pass did not leave them (ckpt_valid == 0).
+#include "scan_bwd_common.cuh"
 
 namespace aum {
 
-constexpr int SB_CH = 64;     // channels per CTA
-constexpr int SB_TT = 8;      // checkpoint interval / chunk length
-constexpr int SB_WARPS = SB_CH / 32;   // warps per direction group
-
-struct ScanBwdDirDev {
-  const void* u; int64_t ld_u;
-  const float* delta; int64_t ld_delta;
-  const float* A;
-  const float* BC; int64_t ld_bc;
-  const float* D;
-  float* du; int64_t ld_du;
-  float* ddelta; int64_t ld_dd;
-  float* dA; float* dD;
-  float* dBC; int64_t ld_dbc;
-  float* dbc_ws;      // [part][batch*L][32] per-warp partial sums of dB|dC (no atomics), reduced by a second kernel
-  float* ckpt;
-  int ckpt_valid;
-  int reverse;
-};
-
-struct ScanBwdParams {
-  ScanBwdDirDev dir[2];
-  int ndirs, shared_du;
-  const void* z; int64_t ld_z;
-  const void* ypre; int64_t ld_y;
-  const void* dout; int64_t ld_dout;
-  void* dz; int64_t ld_dz;
-  void* outz; int64_t ld_oz;
-  int batch, L, Dch, nchunks;
-  float scale;
-  int softplus_grad;
-};
-
 __device__ __forceinline__ void red_add(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
-}
-
-// 32 values per lane -> lane i ends up with sum over the warp's lanes of value i (31 shuffles).
-__device__ __forceinline__ float warp_transpose_reduce(float (&v)[32], int lane) {
-#pragma unroll
-  for (int half = 16; half >= 1; half >>= 1) {
-    const bool upper = (lane & half) != 0;
-#pragma unroll
-    for (int i = 0; i < half; ++i) {
-      const float keep = upper ? v[i + half] : v[i];
-      const float send = upper ? v[i] : v[i + half];
-      v[i] = keep + __shfl_xor_sync(0xffffffffu, send, half);
-    }
-  }
-  return v[0];
 }
 
 // ---- per-step pieces (packed fp32x2: two states per instruction) --------------------------------------
@@ -402,12 +355,16 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
     if (e != cudaSuccess) { set_error("aum_selective_scan_bwd: cudaFuncSetAttribute: %s", cudaGetErrorString(e)); return 2; }
     attr_set = true;
   }
-  switch (dtype) {
-    case AUM_F32:  scan_bwd_kernel<float><<<grid, SB_CH * p.ndirs, smem, st>>>(p); break;
-    case AUM_F16:  scan_bwd_kernel<__half><<<grid, SB_CH * p.ndirs, smem, st>>>(p); break;
-    case AUM_BF16: scan_bwd_kernel<__nv_bfloat16><<<grid, SB_CH * p.ndirs, smem, st>>>(p); break;
+  const int fast = launch_scan_bwd_tma(p, dtype, st);     // TMA-streamed kernel when eligible
+  if (fast > 0) return fast;
+  if (fast < 0) {
+    switch (dtype) {
+      case AUM_F32:  scan_bwd_kernel<float><<<grid, SB_CH * p.ndirs, smem, st>>>(p); break;
+      case AUM_F16:  scan_bwd_kernel<__half><<<grid, SB_CH * p.ndirs, smem, st>>>(p); break;
+      case AUM_BF16: scan_bwd_kernel<__nv_bfloat16><<<grid, SB_CH * p.ndirs, smem, st>>>(p); break;
+    }
+    if (int rc = check_launch("aum_selective_scan_bwd")) return rc;
   }
-  if (int rc = check_launch("aum_selective_scan_bwd")) return rc;
   const int64_t rows = (int64_t)batch * L;
   const int nparts = ceil_div(D, SB_CH) * SB_WARPS;
   for (int g = 0; g < p.ndirs; ++g)

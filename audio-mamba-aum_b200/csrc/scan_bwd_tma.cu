@@ -1,0 +1,373 @@
+// Selective scan backward — TMA-streamed kernel (the production path; math and reference citations: scan_bwd.cu).
+//
+// What changes against the generic kernel is how operands move and how the two directions are combined:
+//   * grid = (ceil(D/64), batch, directions): a CTA owns 64 channels of one sequence in ONE time direction (one
+//     thread per channel, the 16 states as 8 packed fp32x2 pairs).  The directions no longer meet inside a CTA:
+//     where du / ddelta are shared (Fo-Bi) both directions red.global.add into buffers the entry point zeroes
+//     first (two commutative fp32 additions per element: deterministic); dz / out_z are written by direction 0.
+//   * per 8-step checkpoint chunk one elected thread issues bulk tensor copies into a 2-stage ring: the
+//     checkpoint tile (16 x 64 fp32, state before the chunk, left by the forward kernel), delta, u, dout, z and
+//     (direction 0) y_pre tiles (8 x 64) and the packed [B|C] rows; all complete on the stage's mbarrier.  The
+//     loads of chunk c-1 are in flight while chunk c is processed, so no thread ever waits on a global load.
+//   * the chunk's state history lives in shared memory as [slot][n/4][ch][4]: one conflict-free 16-byte store
+//     per four states in the replay, one 16-byte load in the reverse-time walk.
+//   * shared memory (32 KB of history + 2 x 11 KB of stages at 16-bit activations) bounds residency at four CTAs
+//     = eight warps per SM, which is why nothing here may stall on memory.
+// Eligibility (launch_scan_bwd_tma): d_state == 16, forward checkpoints present, packed fp32 [B|C] rows,
+// 16-byte aligned bases and row pitches.  Anything else runs scan_bwd.cu.
+#include <cuda.h>
+
+#include "scan_bwd_common.cuh"
+#include "tma.cuh"
+
+namespace aum {
+
+constexpr int BT_CH = 64;     // channels per CTA
+constexpr int BT_TT = 8;      // steps per checkpoint chunk (== SCAN_CK)
+static_assert(BT_TT == SCAN_CK, "chunk length must match the forward kernels' checkpoint interval");
+
+template <typename T> struct BwdLayout {
+  static constexpr int CK_BYTES = SCAN_NS * BT_CH * 4;             // checkpoint tile [n][ch]
+  static constexpr int D_BYTES = BT_TT * BT_CH * 4;                // delta tile
+  static constexpr int BC_BYTES = BT_TT * SCAN_ROW * 4;            // [B|C] rows
+  static constexpr int A_BYTES = BT_TT * BT_CH * (int)sizeof(T);   // u, dout, z, y_pre tiles
+  static constexpr int OFF_CK = 0, OFF_D = OFF_CK + CK_BYTES, OFF_BC = OFF_D + D_BYTES, OFF_U = OFF_BC + BC_BYTES;
+  static constexpr int OFF_G = OFF_U + A_BYTES, OFF_Z = OFF_G + A_BYTES, OFF_Y = OFF_Z + A_BYTES;
+  static constexpr int STAGE_BYTES = OFF_Y + A_BYTES;
+  static constexpr int SLOT_BYTES = SCAN_NS * BT_CH * 4;           // one history slot [n/4][ch][4]
+  static constexpr int HIST_BYTES = BT_TT * SLOT_BYTES;
+  static constexpr int SMEM_BYTES = HIST_BYTES + 2 * STAGE_BYTES + 128 /*align slack*/ + 64 /*mbarriers*/;
+};
+
+struct ScanBwdMaps { CUtensorMap u[2], d[2], ck[2], g, z, y; };
+
+__device__ __forceinline__ void tma_load_2d(uint32_t dst, const CUtensorMap* tm, int col, int row, uint32_t bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.tile.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tm), "r"(col), "r"(row), "r"(bar) : "memory");
+}
+__device__ __forceinline__ float ldsf(uint32_t a) { float v; asm volatile("ld.shared.f32 %0, [%1];" : "=f"(v) : "r"(a)); return v; }
+__device__ __forceinline__ float4 ldsf4(uint32_t a) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
+__device__ __forceinline__ void lds_pair2(uint32_t a, f32x2& p0, f32x2& p1) {
+  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(p0), "=l"(p1) : "r"(a));
+}
+__device__ __forceinline__ void sts_pair2(uint32_t a, f32x2 p0, f32x2 p1) {
+  asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a), "l"(p0), "l"(p1) : "memory");
+}
+template <typename T> __device__ __forceinline__ float ldst(uint32_t a);
+template <> __device__ __forceinline__ float ldst<float>(uint32_t a) { return ldsf(a); }
+template <> __device__ __forceinline__ float ldst<__half>(uint32_t a) {
+  unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return __half2float(__ushort_as_half(v));
+}
+template <> __device__ __forceinline__ float ldst<__nv_bfloat16>(uint32_t a) {
+  unsigned short v; asm volatile("ld.shared.u16 %0, [%1];" : "=h"(v) : "r"(a)); return __uint_as_float(((uint32_t)v) << 16);
+}
+__device__ __forceinline__ void red_add_f32(float* p, float v) {
+  asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
+}
+
+// Replay one forward step: h <- exp(dl A) h + dl u B; the new state goes to history slot `slot` (this thread's
+// 16-byte column inside each of the slot's four 1 KB planes).
+__device__ __forceinline__ void replay_step(float u, float dl, uint32_t a_bc, uint32_t slot,
+                                            f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2]) {
+  const float du_ = dl * u;
+  const f32x2 dl2 = pk2(dl, dl), du2 = pk2(du_, du_);
+#pragma unroll
+  for (int q = 0; q < 4; ++q) {
+    const float4 Bv = ldsf4(a_bc + 16u * q);
+    float e0, e1, e2, e3;
+    upk2(mul2(dl2, a2[2 * q]), e0, e1); upk2(mul2(dl2, a2[2 * q + 1]), e2, e3);
+    h[2 * q] = fma2(pk2(ex2_approx(e0), ex2_approx(e1)), h[2 * q], mul2(du2, pk2(Bv.x, Bv.y)));
+    h[2 * q + 1] = fma2(pk2(ex2_approx(e2), ex2_approx(e3)), h[2 * q + 1], mul2(du2, pk2(Bv.z, Bv.w)));
+    sts_pair2(slot + (uint32_t)q * (BT_CH * 16), h[2 * q], h[2 * q + 1]);
+  }
+}
+
+template <typename T>
+__global__ void __launch_bounds__(BT_CH)
+scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParams p) {
+  using BL = BwdLayout<T>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem0 = (s_u32(smem_raw) + 127u) & ~127u;
+  const uint32_t hist = smem0;
+  const uint32_t stages = smem0 + BL::HIST_BYTES;
+  const uint32_t bars = stages + 2 * BL::STAGE_BYTES;
+
+  const int g = blockIdx.z;
+  const ScanBwdDirDev& d = p.dir[g];
+  const int tig = threadIdx.x, lane = tig & 31;
+  const int ch_raw = blockIdx.x * BT_CH + tig;
+  const bool active = ch_raw < p.Dch;
+  const int ch = active ? ch_raw : (p.Dch - 1);
+  const int b = blockIdx.y;
+  const int L = p.L;
+  const bool rev = d.reverse != 0;
+  const int row0 = b * L;
+  const bool bidir = p.ndirs == 2;
+  const bool accumulate = bidir && p.shared_du;
+  const bool has_z = p.z != nullptr;
+  const bool gate = (g == 0) && has_z && (p.dz != nullptr || p.outz != nullptr);
+  const bool want_y = gate && p.ypre != nullptr;
+  const float scale = p.scale;
+  const int64_t rows_total = (int64_t)p.batch * L;
+
+  if (tig == 0) {
+    sbar_init(bars, 1); sbar_init(bars + 8, 1);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  __syncthreads();
+
+  // checkpoint chunking (identical to the forward kernels'): chunk 0 = [0, first), chunk c = [first + 8(c-1), +8)
+  const int first = min(scan_ck_first(L, bidir, rev), L);
+  const int nchunks = 1 + (L - first + BT_TT - 1) / BT_TT;
+  const int nck_max = scan_ck_count_max(L);
+  auto chunk_range = [&](int c, int& s0, int& ns) {
+    if (c == 0) { s0 = 0; ns = first; } else { s0 = first + (c - 1) * BT_TT; ns = min(BT_TT, L - s0); }
+  };
+
+  // ---- producer (thread 0): chunk c -> stage (nchunks-1-c) & 1
+  auto issue = [&](int c) {
+    int s0, ns; chunk_range(c, s0, ns);
+    const int stage = (nchunks - 1 - c) & 1;
+    const uint32_t st = stages + (uint32_t)stage * BL::STAGE_BYTES;
+    const uint32_t bar = bars + 8u * stage;
+    // box rows: forward [row0+s0, +8); reverse [row0+L-s0-8, +8) so that step j sits at tile row 7-j
+    const int brow = rev ? (row0 + L - s0 - BT_TT) : (row0 + s0);
+    const int col = blockIdx.x * BT_CH;
+    const uint32_t bc_bytes = (uint32_t)ns * SCAN_ROW * 4u;
+    const uint32_t tx = BL::CK_BYTES + BL::D_BYTES + 2 * BL::A_BYTES + (has_z ? BL::A_BYTES : 0) +
+                        (want_y ? BL::A_BYTES : 0) + bc_bytes;
+    sbar_expect_tx(bar, tx);
+    tma_load_2d(st + BL::OFF_CK, &maps.ck[g], col, (b * nck_max + c) * SCAN_NS, bar);
+    tma_load_2d(st + BL::OFF_D, &maps.d[g], col, brow, bar);
+    tma_load_2d(st + BL::OFF_U, &maps.u[g], col, brow, bar);
+    tma_load_2d(st + BL::OFF_G, &maps.g, col, brow, bar);
+    if (has_z) tma_load_2d(st + BL::OFF_Z, &maps.z, col, brow, bar);
+    if (want_y) tma_load_2d(st + BL::OFF_Y, &maps.y, col, brow, bar);
+    const int bc_row_lo = rev ? (L - s0 - ns) : s0;
+    const float* src = d.BC + (int64_t)(row0 + bc_row_lo) * SCAN_ROW;
+    const uint32_t dst = st + BL::OFF_BC + (rev ? (uint32_t)(BT_TT - ns) * SCAN_ROW * 4u : 0u);
+    bulk_g2s(dst, src, bc_bytes, bar);
+  };
+  if (tig == 0) {
+    issue(nchunks - 1);
+    if (nchunks > 1) issue(nchunks - 2);
+  }
+
+  // ---- per-channel constants and accumulators
+  f32x2 a2[SCAN_NS / 2], Av2[SCAN_NS / 2];
+  {
+    const float4* ap = reinterpret_cast<const float4*>(d.A + (int64_t)ch * SCAN_NS);
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const float4 v = __ldg(ap + i);
+      Av2[2 * i] = pk2(v.x, v.y); Av2[2 * i + 1] = pk2(v.z, v.w);
+      a2[2 * i] = pk2(v.x * 1.4426950408889634f, v.y * 1.4426950408889634f);
+      a2[2 * i + 1] = pk2(v.z * 1.4426950408889634f, v.w * 1.4426950408889634f);
+    }
+  }
+  const float Dv = d.D ? __ldg(d.D + ch) : 0.f;
+  f32x2 gcar[SCAN_NS / 2], dA_acc[SCAN_NS / 2];
+#pragma unroll
+  for (int k = 0; k < SCAN_NS / 2; ++k) { gcar[k] = pk2(0.f, 0.f); dA_acc[k] = pk2(0.f, 0.f); }
+  float dD_acc = 0.f;
+
+  // signed strides of one step forwards in time (tile rows / global rows run backwards for the reverse direction)
+  const int s16 = rev ? -(BT_CH * (int)sizeof(T)) : (BT_CH * (int)sizeof(T));
+  const int s32 = rev ? -(BT_CH * 4) : (BT_CH * 4);
+  const int sbc = rev ? -(SCAN_ROW * 4) : (SCAN_ROW * 4);
+  const int rstep = rev ? -1 : 1;
+  const int part = blockIdx.x * (BT_CH / 32) + (tig >> 5);     // this warp's slice of the dB|dC partial workspace
+  const uint32_t hcol = hist + (uint32_t)tig * 16u;            // this thread's 16-byte column in plane 0 of slot 0
+  const bool spg_on = p.softplus_grad != 0;
+
+  for (int q = 0; q < nchunks; ++q) {
+    const int c = nchunks - 1 - q;
+    int s0, ns; chunk_range(c, s0, ns);
+    const int stage = q & 1;
+    const uint32_t st = stages + (uint32_t)stage * BL::STAGE_BYTES;
+    sbar_wait(bars + 8u * stage, (uint32_t)((q >> 1) & 1));
+
+    const int row_first = rev ? (BT_TT - 1) : 0;                 // tile row of step 0 of the chunk
+    const uint32_t e16 = (uint32_t)(row_first * BT_CH + tig) * (uint32_t)sizeof(T);
+    const uint32_t e32 = (uint32_t)(row_first * BT_CH + tig) * 4u;
+    const uint32_t t_u = st + BL::OFF_U + e16, t_d = st + BL::OFF_D + e32;
+    const uint32_t t_bc = st + BL::OFF_BC + (uint32_t)row_first * SCAN_ROW * 4u;
+
+    // ---- replay: slot j = state before step j (slot 0 = the forward kernel's checkpoint)
+    {
+      f32x2 h[SCAN_NS / 2];
+      const uint32_t ck = st + BL::OFF_CK + (uint32_t)tig * 4u;
+#pragma unroll
+      for (int k = 0; k < SCAN_NS / 2; ++k) h[k] = pk2(ldsf(ck + (uint32_t)(2 * k) * (BT_CH * 4)), ldsf(ck + (uint32_t)(2 * k + 1) * (BT_CH * 4)));
+#pragma unroll
+      for (int qq = 0; qq < 4; ++qq) sts_pair2(hcol + (uint32_t)qq * (BT_CH * 16), h[2 * qq], h[2 * qq + 1]);
+      uint32_t a_u = t_u, a_d = t_d, a_bc = t_bc, slot = hcol + BL::SLOT_BYTES;
+#pragma unroll 1
+      for (int j = 0; j < ns - 1; ++j) {
+        replay_step(ldst<T>(a_u), ldsf(a_d), a_bc, slot, h, a2);
+        a_u += s16; a_d += s32; a_bc += sbc; slot += BL::SLOT_BYTES;
+      }
+    }
+    // (each thread only reads back its own column of the history: no barrier needed)
+
+    // ---- reverse-time recurrence over the chunk, j = ns-1 .. 0
+    {
+      const int jl = ns - 1;
+      uint32_t a_u = t_u + (uint32_t)(jl * s16), a_d = t_d + (uint32_t)(jl * s32), a_bc = t_bc + (uint32_t)(jl * sbc);
+      uint32_t a_g = st + BL::OFF_G + e16 + (uint32_t)(jl * s16);
+      uint32_t a_z = st + BL::OFF_Z + e16 + (uint32_t)(jl * s16);
+      uint32_t a_y = st + BL::OFF_Y + e16 + (uint32_t)(jl * s16);
+      uint32_t slot = hcol + (uint32_t)jl * BL::SLOT_BYTES;
+      const int64_t r_last = (int64_t)row0 + (rev ? (L - 1 - (s0 + jl)) : (s0 + jl));      // global row of step s0+jl
+      float* dup = d.du + r_last * d.ld_du + ch;
+      float* ddp = d.ddelta + r_last * d.ld_dd + ch;
+      float* wsp = d.dbc_ws + ((int64_t)part * rows_total + r_last) * 32 + lane;
+      T* dzp = p.dz ? reinterpret_cast<T*>(p.dz) + r_last * p.ld_dz + ch : nullptr;
+      T* ozp = p.outz ? reinterpret_cast<T*>(p.outz) + r_last * p.ld_oz + ch : nullptr;
+      // one step backwards in time moves one global row against the walk direction
+      const int64_t gdu = -(int64_t)rstep * d.ld_du, gdd = -(int64_t)rstep * d.ld_dd;
+      const int64_t gdz = -(int64_t)rstep * p.ld_dz, goz = -(int64_t)rstep * p.ld_oz;
+      const int gws = -rstep * 32;
+#pragma unroll 2
+      for (int j = jl; j >= 0; --j) {
+        const float u = ldst<T>(a_u), dl = ldsf(a_d), go = ldst<T>(a_g) * scale;
+        const float zv = has_z ? ldst<T>(a_z) : 0.f;
+        const float sz = has_z ? silu_f(zv) : 1.f;
+        const float dy = go * sz;
+        dD_acc = fmaf(dy, u, dD_acc);
+        float red[32];
+        const float dlu = dl * u;
+        const f32x2 dl2 = pk2(dl, dl), dy2 = pk2(dy, dy), dlu2 = pk2(dlu, dlu);
+        f32x2 sB2 = pk2(0.f, 0.f), dd2 = pk2(0.f, 0.f);
+#pragma unroll
+        for (int qq = 0; qq < 4; ++qq) {
+          const float4 Bv = ldsf4(a_bc + 16u * qq);
+          const float4 Cv = ldsf4(a_bc + 16u * (4 + qq));
+          f32x2 hp[2];
+          lds_pair2(slot + (uint32_t)qq * (BT_CH * 16), hp[0], hp[1]);          // h_{s-1}, states 4qq .. 4qq+3
+#pragma unroll
+          for (int hq = 0; hq < 2; ++hq) {
+            const int k = 2 * qq + hq;                              // state pair (2k, 2k+1)
+            const f32x2 Bp = hq ? pk2(Bv.z, Bv.w) : pk2(Bv.x, Bv.y);
+            const f32x2 Cp = hq ? pk2(Cv.z, Cv.w) : pk2(Cv.x, Cv.y);
+            float e0, e1; upk2(mul2(dl2, a2[k]), e0, e1);
+            const f32x2 a = pk2(ex2_approx(e0), ex2_approx(e1));
+            const f32x2 dh = fma2(Cp, dy2, gcar[k]);
+            gcar[k] = mul2(a, dh);
+            const f32x2 hcur = fma2(a, hp[hq], mul2(dlu2, Bp));     // h_s recomputed (cheaper than another load)
+            const f32x2 t1 = mul2(gcar[k], hp[hq]);                 // dh * a * h_{s-1}
+            dA_acc[k] = fma2(t1, dl2, dA_acc[k]);
+            dd2 = fma2(t1, Av2[k], dd2);
+            sB2 = fma2(dh, Bp, sB2);
+            float r0, r1; upk2(mul2(dh, dlu2), r0, r1);             // dB contributions
+            red[2 * k] = r0; red[2 * k + 1] = r1;
+            upk2(mul2(hcur, dy2), r0, r1);                          // dC contributions
+            red[SCAN_NS + 2 * k] = r0; red[SCAN_NS + 2 * k + 1] = r1;
+          }
+        }
+        float s0_, s1_, d0_, d1_;
+        upk2(sB2, s0_, s1_); upk2(dd2, d0_, d1_);
+        const float sB = s0_ + s1_;
+        float dd = fmaf(sB, u, d0_ + d1_);
+        const float duv = fmaf(dl, sB, Dv * dy);
+        // cross-channel sums of this token: lane i of each warp ends up with value i; one plain 128-byte store per
+        // warp into this warp's slice of the partial workspace (summed over warps by dbc_reduce_kernel).
+        // Channels past D read zero-filled tiles, so their contributions are exact zeros.
+        *wsp = warp_transpose_reduce(red, lane);
+        if (spg_on) dd *= 1.f - __expf(-dl);                       // softplus'(pre) = 1 - exp(-delta)
+        if (active) {
+          if (accumulate) { red_add_f32(dup, duv); red_add_f32(ddp, dd); }
+          else { *dup = duv; *ddp = dd; }
+          if (gate) {
+            const float yp = want_y ? ldst<T>(a_y) : 0.f;
+            if (dzp) {
+              const float sg = __fdividef(1.f, 1.f + __expf(-zv));             // sigmoid(z)
+              *dzp = from_f<T>(go * yp * (sg * (1.f + zv * (1.f - sg))));
+            }
+            if (ozp) *ozp = from_f<T>(scale * yp * sz);
+          }
+        }
+        a_u -= s16; a_g -= s16; a_z -= s16; a_y -= s16; a_d -= s32; a_bc -= sbc; slot -= BL::SLOT_BYTES;
+        dup += gdu; ddp += gdd; wsp += gws;
+        if (dzp) dzp += gdz;
+        if (ozp) ozp += goz;
+      }
+    }
+
+    // stage free: refill it with the chunk after next
+    __syncthreads();
+    if (tig == 0 && c >= 2) issue(c - 2);
+  }
+
+  if (active) {
+#pragma unroll
+    for (int k = 0; k < SCAN_NS / 2; ++k) {
+      float lo, hi; upk2(dA_acc[k], lo, hi);
+      atomicAdd(d.dA + (int64_t)ch * SCAN_NS + 2 * k, lo);
+      atomicAdd(d.dA + (int64_t)ch * SCAN_NS + 2 * k + 1, hi);
+    }
+    if (d.dD) atomicAdd(d.dD + ch, dD_acc);
+  }
+}
+
+template <typename T>
+static int launch_bt(const ScanBwdMaps& maps, const ScanBwdParams& p, cudaStream_t st) {
+  using BL = BwdLayout<T>;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("aum_selective_scan_bwd: cudaFuncSetAttribute(smem=%d): %s", BL::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
+    attr_set = true;
+  }
+  dim3 grid(ceil_div(p.Dch, BT_CH), p.batch, p.ndirs);
+  scan_bwd_tma_kernel<T><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
+  return check_launch("aum_selective_scan_bwd(tma)");
+}
+
+int launch_scan_bwd_tma(const ScanBwdParams& p, int dtype, cudaStream_t st) {
+  if (!tma_available() || getenv("AUM_SCAN_BWD_GENERIC") != nullptr) return -1;
+  const int esz = dtype_size(dtype);
+  auto ok_mat = [](const void* base, int64_t ld, int sz) { return aligned16(base) && (ld * sz) % 16 == 0; };
+  if (!ok_mat(p.dout, p.ld_dout, esz)) return -1;
+  if (p.z && !ok_mat(p.z, p.ld_z, esz)) return -1;
+  if (p.ypre && !ok_mat(p.ypre, p.ld_y, esz)) return -1;
+  if (p.Dch % 4 != 0) return -1;                                   // checkpoint rows [.., D] fp32 must be 16-byte pitched
+  for (int g = 0; g < p.ndirs; ++g) {
+    const ScanBwdDirDev& d = p.dir[g];
+    if (!d.ckpt_valid || d.ld_bc != SCAN_ROW || !aligned16(d.BC) || !aligned16(d.ckpt)) return -1;
+    if (!ok_mat(d.u, d.ld_u, esz) || !ok_mat(d.delta, d.ld_delta, 4)) return -1;
+  }
+  ScanBwdMaps maps;
+  const int64_t rows = (int64_t)p.batch * p.L;
+  const int64_t ck_rows = (int64_t)p.batch * scan_ck_count_max(p.L) * SCAN_NS;
+  for (int g = 0; g < 2; ++g) {
+    const ScanBwdDirDev& d = p.dir[g < p.ndirs ? g : 0];
+    if (int rc = tma_encode_2d(&maps.u[g], d.u, dtype, rows, p.Dch, d.ld_u, BT_TT, BT_CH, false, "aum_selective_scan_bwd(u)")) return rc;
+    if (int rc = tma_encode_2d(&maps.d[g], d.delta, AUM_F32, rows, p.Dch, d.ld_delta, BT_TT, BT_CH, false, "aum_selective_scan_bwd(delta)")) return rc;
+    if (int rc = tma_encode_2d(&maps.ck[g], d.ckpt, AUM_F32, ck_rows, p.Dch, p.Dch, SCAN_NS, BT_CH, false, "aum_selective_scan_bwd(ckpt)")) return rc;
+  }
+  if (int rc = tma_encode_2d(&maps.g, p.dout, dtype, rows, p.Dch, p.ld_dout, BT_TT, BT_CH, false, "aum_selective_scan_bwd(dout)")) return rc;
+  if (p.z) { if (int rc = tma_encode_2d(&maps.z, p.z, dtype, rows, p.Dch, p.ld_z, BT_TT, BT_CH, false, "aum_selective_scan_bwd(z)")) return rc; }
+  else maps.z = maps.g;
+  if (p.ypre) { if (int rc = tma_encode_2d(&maps.y, p.ypre, dtype, rows, p.Dch, p.ld_y, BT_TT, BT_CH, false, "aum_selective_scan_bwd(y_pre)")) return rc; }
+  else maps.y = maps.g;
+  // shared du / ddelta: both directions add into zeroed buffers
+  if (p.ndirs == 2 && p.shared_du) {
+    const ScanBwdDirDev& d = p.dir[0];
+    cudaError_t e = cudaMemset2DAsync(d.du, (size_t)d.ld_du * 4, 0, (size_t)p.Dch * 4, (size_t)rows, st);
+    if (e == cudaSuccess) e = cudaMemset2DAsync(d.ddelta, (size_t)d.ld_dd * 4, 0, (size_t)p.Dch * 4, (size_t)rows, st);
+    if (e != cudaSuccess) { set_error("aum_selective_scan_bwd: cudaMemset2DAsync: %s", cudaGetErrorString(e)); return 2; }
+  }
+  switch (dtype) {
+    case AUM_F32:  return launch_bt<float>(maps, p, st);
+    case AUM_F16:  return launch_bt<__half>(maps, p, st);
+    case AUM_BF16: return launch_bt<__nv_bfloat16>(maps, p, st);
+  }
+  return -1;
+}
+
+}  // namespace aum

@@ -133,6 +133,68 @@ def test_selective_scan_bwd_vs_oracle_autograd(dirs, B, Lq, D):
         _close(dAb, A_b.grad, msg="dA_b", **tol)
 
 
+@pytest.mark.parametrize("generic", [False, True])
+@pytest.mark.parametrize("dirs", ["fb", "f", "b"])
+@pytest.mark.parametrize("B,Lq,D,dt", [(2, 37, 40, torch.float32), (1, 8, 64, torch.float32), (2, 70, 96, torch.float32),
+                                       (1, 1, 16, torch.float32), (2, 513, 192, torch.float32),
+                                       (2, 130, 128, torch.float16), (2, 130, 128, torch.bfloat16)])
+def test_selective_scan_bwd_from_forward_checkpoints(dirs, B, Lq, D, dt, generic, monkeypatch):
+    """The training pair as the autograd function uses it: the forward kernel leaves state checkpoints and the
+    pre-gate output, the backward kernel (TMA-streamed, or generic with AUM_SCAN_BWD_GENERIC) consumes them.
+    Fo-Bi sharing: both directions accumulate into the same du / ddelta."""
+    from aum_b200 import ops
+    if generic:
+        monkeypatch.setenv("AUM_SCAN_BWD_GENERIC", "1")
+    N = 16
+    g = gen(3)
+    q = lambda t: t.to(dt).float()                      # values exactly representable in the activation dtype
+    u = q(rnd((B, Lq, D), g)).requires_grad_()
+    delta = (0.05 + 0.3 * torch.rand((B, Lq, D), generator=g)).requires_grad_()
+    A = (-torch.exp(torch.log(torch.arange(1, N + 1.0)).repeat(D, 1) + 0.1 * rnd((D, N), g))).requires_grad_()
+    A_b = (-torch.exp(torch.log(torch.arange(1, N + 1.0)).repeat(D, 1) + 0.1 * rnd((D, N), g))).requires_grad_()
+    Bm, Cm = rnd((B, Lq, N), g).requires_grad_(), rnd((B, Lq, N), g).requires_grad_()
+    Dv = (1 + 0.1 * rnd((D,), g)).requires_grad_()
+    z = q(rnd((B, Lq, D), g)).requires_grad_()
+    G = q(rnd((B, Lq, D), g))
+    scale = 0.5 if dirs == "fb" else 1.0
+    out, ypre_ref = _scan_ref(u, delta, A, A_b, Bm, Cm, Dv, z, scale, dirs)
+    (out * G).sum().backward()
+
+    cu = lambda t: t.detach().to(DEV).contiguous()
+    ud, zd, dl = cu(u).to(dt), cu(z).to(dt), cu(delta)
+    bc = torch.cat([cu(Bm), cu(Cm)], dim=-1).contiguous()
+    ck = {k: ops.scan_bwd_workspace(B, Lq, D, DEV) for k in "fb"}
+    mkf = lambda Ax, k: ops.ScanDirection(ud, dl, cu(Ax), bc[..., :N], bc[..., N:], cu(Dv), ckpt=ck[k])
+    y_pre = torch.empty((B, Lq, D), device=DEV, dtype=dt)
+    out_d = ops.selective_scan(mkf(A, "f") if "f" in dirs else None, mkf(A_b, "b") if "b" in dirs else None, zd,
+                               out_scale=scale, y_pre=y_pre)
+    lo = dt != torch.float32
+    ftol = dict(rtol=2e-2, atol=2e-2) if lo else dict(rtol=2e-4, atol=2e-5)
+    _close(out_d.float(), out.detach(), msg="out", **ftol)
+
+    du = torch.full((B, Lq, D), float("nan"), device=DEV); dd = torch.full_like(du, float("nan"))
+    dbc = torch.zeros((B, Lq, 2 * N), device=DEV)
+    dA = torch.zeros((D, N), device=DEV); dAb = torch.zeros((D, N), device=DEV); dD = torch.zeros((D,), device=DEV)
+    dz = torch.empty((B, Lq, D), device=DEV, dtype=dt); oz = torch.empty_like(dz)
+    mk = lambda Ax, dAx, k: ops.ScanBwdDirection(ud, dl, cu(Ax), bc, cu(Dv), du, dd, dAx, dD, dbc, ck[k], ckpt_valid=True)
+    ops.selective_scan_bwd(mk(A, dA, "f") if "f" in dirs else None, mk(A_b, dAb, "b") if "b" in dirs else None,
+                           zd, y_pre, G.to(DEV).to(dt), dz, oz, out_scale=scale)
+    # 16-bit tiers: y_pre is stored rounded, so dz / out_z carry that rounding; the fp32 outputs do not
+    tol = dict(rtol=2e-2, atol=2e-2) if lo else dict(rtol=2e-4, atol=2e-5)
+    gt = dict(rtol=2e-4, atol=5e-5)
+    _close(oz.float(), out.detach(), msg="out_z", **tol)
+    _close(dz.float(), z.grad, msg="dz", **tol)
+    _close(du, u.grad, msg="du", **gt)
+    _close(dd, delta.grad, msg="ddelta", **gt)
+    _close(dbc[..., :N], Bm.grad, msg="dB", **gt)
+    _close(dbc[..., N:], Cm.grad, msg="dC", **gt)
+    _close(dD, Dv.grad, msg="dD", **gt)
+    if "f" in dirs:
+        _close(dA, A.grad, msg="dA", **gt)
+    if "b" in dirs:
+        _close(dAb, A_b.grad, msg="dA_b", **gt)
+
+
 @pytest.mark.parametrize("bt,kw", [("v1", {}), ("none", {}), ("v2", {"if_devide_out": True}), ("v1", {"bias": True, "init_layer_scale": 0.5})])
 def test_mamba_module_backward_vs_oracle_autograd(bt, kw):
     """All parameter gradients and d(hidden) of one mixer, fp32 tier, against autograd through the oracle."""
@@ -164,6 +226,13 @@ def test_mamba_module_backward_vs_oracle_autograd(bt, kw):
     for n, p in m.named_parameters():
         assert p.grad is not None, n
         _close(p.grad, ref_p[n].grad, 1e-3, 1e-4, n)
+
+
+def test_mamba_module_backward_with_generic_scan_bwd_kernel(monkeypatch):
+    """Same gradients through the generic (non-TMA) backward kernel."""
+    monkeypatch.setenv("AUM_SCAN_BWD_GENERIC", "1")
+    test_mamba_module_backward_vs_oracle_autograd("v1", {})
+    test_mamba_module_backward_vs_oracle_autograd("v2", {"if_devide_out": True})
 
 
 def test_mamba_module_backward_with_generic_scan_kernel(monkeypatch):
