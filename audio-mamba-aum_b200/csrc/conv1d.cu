@@ -7,7 +7,7 @@
 // TL+3 input rows of a thread are independent loads issued up front (one DRAM latency per thread), kept PACKED
 // in registers (19 regs) so the kernel runs at full occupancy, and the 3-row halo is served by L1/L2.
 // Algorithmic bytes per (token, channel): read s + write s (s = itemsize).
-#include "common.cuh"
+#include "scan_common.cuh"   // packed fp32x2 helpers
 
 namespace aum {
 
@@ -109,6 +109,121 @@ conv1d_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
   }
 }
 
+// ---- fast path: 4 adjacent channels per thread --------------------------------------------------------------
+// The generic kernel above spends ~44 instructions per element (it re-converts every packed row once per tap and
+// works on scalar lanes), which makes it issue-bound at 2.5 TB/s.  This one converts each input row once into two
+// packed fp32x2 pairs, runs the taps as FFMA2 on the pairs (2 per element) and stores 8 or 16 bytes per thread:
+// ~10 instructions per element, so the kernel is bound by HBM again.  Needs D, pitches and bases 4-element aligned.
+// x * sigmoid(x) with flush-to-zero MUFU ops: FMUL + EX2 + FADD + RCP + FMUL (the non-ftz forms add a range fix-up
+// of 3 instructions per MUFU).  exp2 overflow -> rcp(inf) = 0 -> -0, underflow -> x.
+__device__ __forceinline__ float silu_ftz(float x) {
+  float r;
+  const float e = ex2_approx(-1.4426950408889634f * x);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return x * r;
+}
+
+template <typename T> struct Quad;      // 4 adjacent channels as loaded
+template <> struct Quad<float> {
+  float4 v;
+  __device__ __forceinline__ void load(const float* p) { v = *reinterpret_cast<const float4*>(p); }
+  __device__ __forceinline__ void zero() { v = make_float4(0.f, 0.f, 0.f, 0.f); }
+  __device__ __forceinline__ void f(f32x2& a, f32x2& b) const { a = pk2(v.x, v.y); b = pk2(v.z, v.w); }
+  static __device__ __forceinline__ void store(float* p, float a, float b, float c, float d) {
+    *reinterpret_cast<float4*>(p) = make_float4(a, b, c, d);
+  }
+};
+template <> struct Quad<__half> {
+  uint2 v;
+  __device__ __forceinline__ void load(const __half* p) { v = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ void zero() { v = make_uint2(0u, 0u); }
+  __device__ __forceinline__ void f(f32x2& a, f32x2& b) const {
+    const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&v.x));
+    const float2 hi = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+    a = pk2(lo.x, lo.y); b = pk2(hi.x, hi.y);
+  }
+  static __device__ __forceinline__ void store(__half* p, float a, float b, float c, float d) {
+    __half2 lo = __floats2half2_rn(a, b), hi = __floats2half2_rn(c, d);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+};
+template <> struct Quad<__nv_bfloat16> {
+  uint2 v;
+  __device__ __forceinline__ void load(const __nv_bfloat16* p) { v = *reinterpret_cast<const uint2*>(p); }
+  __device__ __forceinline__ void zero() { v = make_uint2(0u, 0u); }
+  __device__ __forceinline__ void f(f32x2& a, f32x2& b) const {   // bf16 -> fp32 is a 16-bit shift
+    a = pk2(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u));
+    b = pk2(__uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+  }
+  static __device__ __forceinline__ void store(__nv_bfloat16* p, float a, float b, float c, float d) {
+    __nv_bfloat162 lo = __floats2bfloat162_rn(a, b), hi = __floats2bfloat162_rn(c, d);
+    *reinterpret_cast<uint2*>(p) = make_uint2(*reinterpret_cast<uint32_t*>(&lo), *reinterpret_cast<uint32_t*>(&hi));
+  }
+};
+
+template <typename T>
+__global__ void __launch_bounds__(128)
+conv1d_fwd_vec4_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w,
+                       const float* __restrict__ bias, T* __restrict__ out, int64_t ldo,
+                       int batch, int L, int D, int W, int silu, int reverse, int n_cvec, int n_ltile) {
+  // grid: x = (sequence, 16-token tile), y = 128-thread slice of the channel quads (32-bit index math only)
+  const int cv = blockIdx.y * blockDim.x + threadIdx.x;
+  if (cv >= n_cvec) return;
+  const int lt = (int)(blockIdx.x % (unsigned)n_ltile);
+  const int b = (int)(blockIdx.x / (unsigned)n_ltile);
+  const int c0 = cv * 4;
+
+  // taps as channel pairs, zero-padded at the front to CONV_MAXW
+  f32x2 wa[CONV_MAXW], wb[CONV_MAXW];
+#pragma unroll
+  for (int j = 0; j < CONV_MAXW; ++j) {
+    const int k = j - (CONV_MAXW - W);
+    float t[4];
+#pragma unroll
+    for (int v = 0; v < 4; ++v) t[v] = k >= 0 ? __ldg(w + (int64_t)(c0 + v) * W + k) : 0.f;
+    wa[j] = pk2(t[0], t[1]); wb[j] = pk2(t[2], t[3]);
+  }
+  f32x2 ba = pk2(0.f, 0.f), bb = ba;
+  if (bias != nullptr) { const float4 t = __ldg(reinterpret_cast<const float4*>(bias + c0)); ba = pk2(t.x, t.y); bb = pk2(t.z, t.w); }
+
+  const int l_begin = lt * CONV_TL;
+  const int l_end = min(L, l_begin + CONV_TL);
+  const int n = l_end - l_begin;
+  const int step = reverse ? -1 : 1;
+  const int l_first = reverse ? (l_end - 1) : l_begin;
+  const int64_t xstep = (int64_t)step * ldx, ostep = (int64_t)step * ldo;
+  const T* xp = x + ((int64_t)b * L + l_first) * ldx + c0 - (CONV_MAXW - 1) * xstep;   // row of walk position -(MAXW-1)
+  T* op = out + ((int64_t)b * L + l_first) * ldo + c0;
+
+  constexpr int NR = CONV_TL + CONV_MAXW - 1;
+  Quad<T> rows[NR];        // rows[j] = x at walk position (j - (MAXW-1)) relative to the first token; all loads up front
+#pragma unroll
+  for (int j = 0; j < NR; ++j) {
+    const int pos = j - (CONV_MAXW - 1);
+    const int l = l_first + step * pos;
+    rows[j].zero();
+    if ((pos < n) && (l >= 0) && (l < L)) rows[j].load(xp);
+    xp += xstep;
+  }
+  f32x2 fa[NR], fb[NR];    // converted once; only a 4-row window is live at a time
+#pragma unroll
+  for (int j = 0; j < CONV_MAXW - 1; ++j) rows[j].f(fa[j], fb[j]);
+#pragma unroll
+  for (int i = 0; i < CONV_TL; ++i) {
+    rows[i + CONV_MAXW - 1].f(fa[i + CONV_MAXW - 1], fb[i + CONV_MAXW - 1]);
+    if (i < n) {
+      f32x2 a = ba, c = bb;
+#pragma unroll
+      for (int j = 0; j < CONV_MAXW; ++j) { a = fma2(wa[j], fa[i + j], a); c = fma2(wb[j], fb[i + j], c); }
+      float y0, y1, y2, y3;
+      upk2(a, y0, y1); upk2(c, y2, y3);
+      if (silu) { y0 = silu_ftz(y0); y1 = silu_ftz(y1); y2 = silu_ftz(y2); y3 = silu_ftz(y3); }
+      Quad<T>::store(op, y0, y1, y2, y3);
+    }
+    op += ostep;
+  }
+}
+
 template <typename T>
 static int launch_conv(const void* x, int64_t ldx, const float* w, const float* bias, void* out, int64_t ldo,
                        int batch, int L, int D, int W, int silu, int reverse, cudaStream_t st) {
@@ -116,7 +231,15 @@ static int launch_conv(const void* x, int64_t ldx, const float* w, const float* 
   const int esz = (int)sizeof(T);
   const bool vec_ok = (D % 2 == 0) && (ldx % 2 == 0) && (ldo % 2 == 0) &&
                       (reinterpret_cast<uintptr_t>(x) % (2 * esz) == 0) && (reinterpret_cast<uintptr_t>(out) % (2 * esz) == 0);
-  if (vec_ok) {
+  const bool vec4_ok = (D % 4 == 0) && (ldx % 4 == 0) && (ldo % 4 == 0) &&
+                       (reinterpret_cast<uintptr_t>(x) % (4 * esz) == 0) && (reinterpret_cast<uintptr_t>(out) % (4 * esz) == 0) &&
+                       (bias == nullptr || reinterpret_cast<uintptr_t>(bias) % 16 == 0);
+  if (vec4_ok && (int64_t)batch * n_ltile < (1ll << 31)) {
+    const int n_cvec = D / 4;
+    const dim3 grid((unsigned)(batch * n_ltile), (unsigned)ceil_div(n_cvec, 128));
+    conv1d_fwd_vec4_kernel<T><<<grid, 128, 0, st>>>(
+        (const T*)x, ldx, w, bias, (T*)out, ldo, batch, L, D, W, silu, reverse, n_cvec, n_ltile);
+  } else if (vec_ok) {
     const int n_cvec = D / 2;
     const int64_t total = (int64_t)batch * n_ltile * n_cvec;
     conv1d_fwd_kernel<T, 2><<<(unsigned)ceil_div64(total, 256), 256, 0, st>>>(

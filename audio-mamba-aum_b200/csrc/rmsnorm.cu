@@ -11,7 +11,9 @@ namespace aum {
 
 constexpr int RN_MAXC = 8;   // 8 chunks * 32 lanes * 8 elems = dim <= 2048 on the vector path
 
-template <typename T, typename TY, typename RT>
+// MAXC: row chunks a lane may hold (32 lanes x 8 elements each); instantiated per width class so that a 768-wide row
+// costs 24 value registers, not 64 (full occupancy = more loads in flight for this latency-bound kernel).
+template <typename T, typename TY, typename RT, int MAXC>
 __global__ void __launch_bounds__(256)
 add_rmsnorm_vec_kernel(const T* __restrict__ x, int64_t ldx, const RT* __restrict__ rin, int64_t ldr,
                        const float* __restrict__ weight, const float* __restrict__ bias,
@@ -22,10 +24,10 @@ add_rmsnorm_vec_kernel(const T* __restrict__ x, int64_t ldx, const RT* __restric
   if (warp >= rows) return;
   const int nchunk = dim >> 3;
   const T* xr = x + (int64_t)warp * ldx;
-  float v[RN_MAXC][8];
+  float v[MAXC][8];
   float ss = 0.f;
 #pragma unroll
-  for (int c = 0; c < RN_MAXC; ++c) {
+  for (int c = 0; c < MAXC; ++c) {
     const int ch = lane + 32 * c;
     if (ch < nchunk) {
       Vec8<T> t; t.load(xr + ch * 8); t.unpack(v[c]);
@@ -45,7 +47,7 @@ add_rmsnorm_vec_kernel(const T* __restrict__ x, int64_t ldx, const RT* __restric
   const float rstd = rsqrtf(ss / (float)dim + eps);
   if (rstd_out != nullptr && lane == 0) rstd_out[warp] = rstd;
 #pragma unroll
-  for (int c = 0; c < RN_MAXC; ++c) {
+  for (int c = 0; c < MAXC; ++c) {
     const int ch = lane + 32 * c;
     if (ch < nchunk) {
       Vec8<float> wv; wv.load(weight + ch * 8);
@@ -105,8 +107,14 @@ static void launch_vec(const void* x, int64_t ldx, const void* rin, int64_t ldr,
                        void* y, int64_t ldy, void* rout, int64_t ldro, float* rstd, int rows, int dim, float eps,
                        cudaStream_t st) {
   const int warps_per_block = 8;
-  add_rmsnorm_vec_kernel<T, TY, float><<<ceil_div(rows, warps_per_block), warps_per_block * 32, 0, st>>>(
-      (const T*)x, ldx, (const float*)rin, ldr, w, b, (TY*)y, ldy, (float*)rout, ldro, rstd, rows, dim, eps);
+#define AUM_RN_LAUNCH(C) add_rmsnorm_vec_kernel<T, TY, float, C><<<ceil_div(rows, warps_per_block), warps_per_block * 32, 0, st>>>( \
+      (const T*)x, ldx, (const float*)rin, ldr, w, b, (TY*)y, ldy, (float*)rout, ldro, rstd, rows, dim, eps)
+  const int per_lane = ceil_div(dim >> 3, 32);
+  if (per_lane <= 2) AUM_RN_LAUNCH(2);
+  else if (per_lane <= 3) AUM_RN_LAUNCH(3);
+  else if (per_lane <= 4) AUM_RN_LAUNCH(4);
+  else AUM_RN_LAUNCH(RN_MAXC);
+#undef AUM_RN_LAUNCH
 }
 
 }  // namespace aum
