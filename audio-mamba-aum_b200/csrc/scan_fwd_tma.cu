@@ -28,13 +28,18 @@
 
 namespace aum {
 
-constexpr int ST_CH = 128;    // channels per CTA
 constexpr int ST_TT = 8;      // tokens per tile
+// channels per CTA (= threads per direction) is a template parameter CH: 128 (default: two CTAs = 16 warps per SM, the
+// kernel owns the register file) or 192 (AUM_SCAN_TMA_CH=192: one 12-warp CTA per SM that leaves 16 K registers and
+// ~95 KB of shared memory free).  Measured at config 2 (fp16, pre-gated z): 0.541 ms vs 0.582 ms - the XU pipe needs
+// the 16 warps; 10 warps (CH = 160) do not divide over the 4 schedulers and take 0.73 ms.  Running one 8-warp scan CTA
+// next to a half-size tcgen05 GEMM CTA on every SM (so that the XU and the tensor pipe overlap) was tried as well:
+// the scan loses more (8 warps: -35 %) than the overlap wins, whole-model throughput -5 %; see DESIGN.md.
 
 // NSTG: ring depth per direction
-template <typename T, int NSTG> struct StageLayout {
-  static constexpr int U_BYTES = ST_TT * ST_CH * (int)sizeof(T);
-  static constexpr int D_BYTES = ST_TT * ST_CH * 4;
+template <typename T, int NSTG, int CH> struct StageLayout {
+  static constexpr int U_BYTES = ST_TT * CH * (int)sizeof(T);
+  static constexpr int D_BYTES = ST_TT * CH * 4;
   static constexpr int Z_BYTES = U_BYTES;
   static constexpr int BC_BYTES = ST_TT * SCAN_ROW * 4;
   static constexpr int P_BYTES = U_BYTES;                  // parked partials of the other direction (rows of `out`)
@@ -118,13 +123,13 @@ __device__ __forceinline__ float scan_step(float u, float dl, uint32_t a_bc, flo
 // The body is unrolled by 4 steps and run twice: ~5.5 KB of SASS per instantiation, so that the four bodies a
 // resident CTA pair can be in at once (2 directions x 2 phases) stay inside the 32 KB L1.5 instruction cache; the
 // fully unrolled 8-step bodies did not and lost 7% to instruction-fetch stalls.
-template <typename T, bool FIN, bool PARTIAL, int ZM, bool REV, bool YPRE>
+template <typename T, int CH, bool FIN, bool PARTIAL, int ZM, bool REV, bool YPRE>
 __device__ __forceinline__ void scan_tile_full(uint32_t a_u, uint32_t a_d, uint32_t a_z, uint32_t a_bc, uint32_t a_p,
                                                float Dv, float oscale, bool active,
                                                f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2],
                                                T* pyp, ptrdiff_t ostep) {
   constexpr int HALF = ST_TT / 2;
-  constexpr int P16 = ST_CH * (int)sizeof(T), P32 = ST_CH * 4, PBC = SCAN_ROW * 4;
+  constexpr int P16 = CH * (int)sizeof(T), P32 = CH * 4, PBC = SCAN_ROW * 4;
   if (REV) { a_u += HALF * P16; a_z += HALF * P16; a_p += HALF * P16; a_d += HALF * P32; a_bc += HALF * PBC; }
 #pragma unroll 1
   for (int hf = 0; hf < 2; ++hf) {
@@ -169,10 +174,11 @@ __device__ __forceinline__ void scan_tile_tail(int nt, bool fin, bool partial, b
   }
 }
 
-template <typename T, int MINB, int NSTG>
-__global__ void __launch_bounds__(2 * ST_CH, MINB)
+template <typename T, int MINB, int NSTG, int CH>
+__global__ void __launch_bounds__(CH <= 128 ? 2 * CH : 512, MINB)      // either way: at most 128 registers per thread
 scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p) {
-  using SL = StageLayout<T, NSTG>;
+  using SL = StageLayout<T, NSTG, CH>;
+  constexpr int NW = CH / 32;                 // warps per direction
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (s_u32(smem_raw) + 127u) & ~127u;
 
@@ -184,7 +190,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   const int warp_in_group = (p.ndirs == 2) ? (wid >> 1) : wid;
   const int tig = warp_in_group * 32 + lane;
   const ScanDirDev& d = p.dir[g];
-  const int ch_raw = blockIdx.x * ST_CH + tig;
+  const int ch_raw = blockIdx.x * CH + tig;
   const bool active = ch_raw < p.Dch;
   const int ch = active ? ch_raw : (p.Dch - 1);
   const int b = blockIdx.y;
@@ -203,7 +209,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   auto pfull_bar = [&](int s) { return bars + 8u * (2 * NSTG + s); };   // parked-partial tiles (phase 2 only)
 
   if (tig == 0) {
-    for (int s = 0; s < NSTG; ++s) { sbar_init(full_bar(s), 1); sbar_init(empty_bar(s), ST_CH / 32); sbar_init(pfull_bar(s), 1); }
+    for (int s = 0; s < NSTG; ++s) { sbar_init(full_bar(s), 1); sbar_init(empty_bar(s), NW); sbar_init(pfull_bar(s), 1); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -218,9 +224,11 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   const int n1t = S1 > 0 ? 1 + (S1 - first + ST_TT - 1) / ST_TT : 0;
   const int n2t = (L - S1 + ST_TT - 1) / ST_TT;
   const int ntiles = n1t + n2t;
+  // S1 = first + 8 (n1t - 1), so one formula serves both phases: tile k >= 1 starts at first8 + 8 (k - 1)
+  const int first8 = S1 > 0 ? first : ST_TT;
   auto tile_range = [&](int k, int& s0, int& nt) {
-    if (k < n1t) { s0 = k == 0 ? 0 : first + (k - 1) * ST_TT; nt = k == 0 ? min(first, S1) : min(ST_TT, S1 - s0); }
-    else { s0 = S1 + (k - n1t) * ST_TT; nt = min(ST_TT, L - s0); }
+    s0 = k == 0 ? 0 : first8 + (k - 1) * ST_TT;
+    nt = min(k == 0 ? first8 : ST_TT, (k < n1t ? S1 : L) - s0);
   };
 
   // ---- producers.  Tile j's bulk store and the refill of its stage are the job of lane 0 of warp (j mod 4) of the
@@ -231,7 +239,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     const int stage = k % NSTG;
     const int brow = rev ? (row0 + L - s0 - ST_TT) : (row0 + s0);
     sbar_expect_tx(pfull_bar(stage), SL::P_BYTES);
-    tma_tile_2d(ring + (uint32_t)stage * SL::STAGE_BYTES + SL::OFF_P, &maps.o, blockIdx.x * ST_CH, brow, pfull_bar(stage));
+    tma_tile_2d(ring + (uint32_t)stage * SL::STAGE_BYTES + SL::OFF_P, &maps.o, blockIdx.x * CH, brow, pfull_bar(stage));
   };
   // with_partial: the CTA is past its phase barrier, so a finalising tile may fetch its parked partials right away
   auto issue_tile = [&](int k, bool with_partial) {
@@ -245,7 +253,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     const uint32_t bc_bytes = (uint32_t)nt * SCAN_ROW * 4u;
     const uint32_t tx = SL::U_BYTES + SL::D_BYTES + ((fin && has_z) ? SL::Z_BYTES : 0) + bc_bytes;
     sbar_expect_tx(bar, tx);
-    const int col = blockIdx.x * ST_CH;
+    const int col = blockIdx.x * CH;
     tma_tile_2d(st + SL::OFF_U, &maps.u[g], col, brow, bar);
     tma_tile_2d(st + SL::OFF_D, &maps.d[g], col, brow, bar);
     if (fin && has_z) tma_tile_2d(st + SL::OFF_Z, &maps.z, col, brow, bar);
@@ -263,12 +271,12 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     int s0, nt; tile_range(j, s0, nt);
     if (nt == ST_TT) {
       const int brow = rev ? (row0 + L - s0 - ST_TT) : (row0 + s0);
-      tma_store_tile_2d(&maps.o, ring + (uint32_t)(j % NSTG) * SL::STAGE_BYTES + SL::OFF_U, blockIdx.x * ST_CH, brow);
+      tma_store_tile_2d(&maps.o, ring + (uint32_t)(j % NSTG) * SL::STAGE_BYTES + SL::OFF_U, blockIdx.x * CH, brow);
       bulk_commit();
     }
   };
   const bool my_lane0 = lane == 0;
-  auto owns = [&](int j) { return my_lane0 && (j & 3) == warp_in_group; };
+  auto owns = [&](int j) { return my_lane0 && (j % NW) == warp_in_group; };
   if (tig == 0) {
     for (int k = 0; k < NSTG && k < ntiles; ++k) issue_tile(k, !bidir);
   }
@@ -295,17 +303,25 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   const ptrdiff_t ostep = rev ? -(ptrdiff_t)ldo : (ptrdiff_t)ldo;
   // the pre-gate output (if requested) shares out's row pitch: address it as an element offset from the out row
   const ptrdiff_t ypre_off = p.ypre ? (reinterpret_cast<T*>(p.ypre) - reinterpret_cast<T*>(p.out)) : 0;
-  const int su = rev ? -(int)(ST_CH * sizeof(T)) : (int)(ST_CH * sizeof(T));
-  const int sd = rev ? -(ST_CH * 4) : (ST_CH * 4);
+  const int su = rev ? -(int)(CH * sizeof(T)) : (int)(CH * sizeof(T));
+  const int sd = rev ? -(CH * 4) : (CH * 4);
   const int sbc = rev ? -(SCAN_ROW * 4) : (SCAN_ROW * 4);
 
   float* ckp = d.ckpt ? d.ckpt + (int64_t)b * scan_ck_count_max(L) * SCAN_NS * p.Dch + ch : nullptr;
 
+  // Loop state kept incrementally (no division / modulo / re-derivation of the tiling per trip: the bookkeeping
+  // between two tile bodies is pure latency for the warp, and with four warps per scheduler it showed up as 19 % of
+  // all stall samples): walk position, ring stage, the parity bits of the stage barriers, k mod NW.
+  const int m_store = (warp_in_group + 1) % NW, m_refill = (warp_in_group + 2) % NW;   // k mod NW at which this warp stores / refills
+  const uint32_t o_u = SL::OFF_U + (uint32_t)tig * (uint32_t)sizeof(T), o_d = SL::OFF_D + (uint32_t)tig * 4u;
+  const uint32_t o_z = SL::OFF_Z + (uint32_t)tig * (uint32_t)sizeof(T), o_p = SL::OFF_P + (uint32_t)tig * (uint32_t)sizeof(T);
+  const bool save_ypre = ypre_off != 0;
+  int s0 = 0, stage = 0, m = 0;
+  uint32_t fpar = 0, ppar = 0;                     // bit s: parity of the next wait on full / partial barrier of stage s
   for (int k = 0; k < ntiles; ++k) {
-    int s0, nt; tile_range(k, s0, nt);
-    const int stage = k % NSTG;
-    const uint32_t st = ring + (uint32_t)stage * SL::STAGE_BYTES;
     const bool fin = k >= n1t;
+    const int nt = min(k == 0 ? first8 : ST_TT, (fin ? L : S1) - s0);
+    const uint32_t st = ring + (uint32_t)stage * SL::STAGE_BYTES;
     const bool partial = fin && bidir;
     if (bidir && k == n1t) {
       // every partial of both directions must be parked before anyone fetches one: the producer drains its bulk
@@ -320,8 +336,6 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
         for (int kk = n1t; kk <= upto; ++kk) issue_partial(kk);
       }
     }
-    const int r = row0 + (rev ? (L - 1 - s0) : s0);    // global row of step s0
-    T* po = ob + (int64_t)r * ldo;
     if (ckp != nullptr && active) {        // training: state before this tile (tiles == checkpoint chunks)
       float* c = ckp + (int64_t)k * SCAN_NS * p.Dch;
 #pragma unroll
@@ -330,20 +344,18 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
         c[(int64_t)(2 * i) * p.Dch] = lo; c[(int64_t)(2 * i + 1) * p.Dch] = hi;
       }
     }
-    sbar_wait(full_bar(stage), (uint32_t)((k / NSTG) & 1));
-    if (partial) sbar_wait(pfull_bar(stage), (uint32_t)(((k - n1t) / NSTG) & 1));
+    sbar_wait(full_bar(stage), (fpar >> stage) & 1u);
+    fpar ^= 1u << stage;
+    if (partial) { sbar_wait(pfull_bar(stage), (ppar >> stage) & 1u); ppar ^= 1u << stage; }
 
     // this thread's element in tile row 0 of each operand tile of the stage
-    const uint32_t b_u = st + SL::OFF_U + (uint32_t)tig * (uint32_t)sizeof(T);
-    const uint32_t b_d = st + SL::OFF_D + (uint32_t)tig * 4u;
-    const uint32_t b_z = st + SL::OFF_Z + (uint32_t)tig * (uint32_t)sizeof(T);
-    const uint32_t b_bc = st + SL::OFF_BC;
-    const uint32_t b_p = st + SL::OFF_P + (uint32_t)tig * (uint32_t)sizeof(T);
+    const uint32_t b_u = st + o_u, b_d = st + o_d, b_z = st + o_z, b_bc = st + SL::OFF_BC, b_p = st + o_p;
     if (nt == ST_TT) {
-      T* pyp = (fin && ypre_off != 0) ? po + ypre_off : nullptr;
-#define AUM_TILE(F, P, Z, R, Y) scan_tile_full<T, F, P, Z, R, Y>(b_u, b_d, b_z, b_bc, b_p, Dv, oscale, active, h, a2, pyp, ostep)
+      T* pyp = nullptr;
+      if (fin && save_ypre) pyp = ob + (int64_t)(row0 + (rev ? (L - 1 - s0) : s0)) * ldo + ypre_off;
+#define AUM_TILE(F, P, Z, R, Y) scan_tile_full<T, CH, F, P, Z, R, Y>(b_u, b_d, b_z, b_bc, b_p, Dv, oscale, active, h, a2, pyp, ostep)
 #define AUM_TILE_Z(F, P, R) do { if (zmode == 0) AUM_TILE(F, P, 0, R, false); else if (zmode == 2) AUM_TILE(F, P, 2, R, false); \
-                                 else if (pyp != nullptr) AUM_TILE(F, P, 1, R, true); else AUM_TILE(F, P, 1, R, false); } while (0)
+                                 else if (save_ypre) AUM_TILE(F, P, 1, R, true); else AUM_TILE(F, P, 1, R, false); } while (0)
       if (rev) {
         if (!fin) AUM_TILE(false, false, 0, true, false);
         else if (partial) AUM_TILE_Z(true, true, true);
@@ -358,24 +370,30 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // y tile (generic proxy) -> bulk store (async proxy)
     } else {
       const int row_first = rev ? (ST_TT - 1) : 0;
-      scan_tile_tail<T>(nt, fin, partial, has_z, b_u + (uint32_t)(row_first * ST_CH * (int)sizeof(T)),
-                        b_d + (uint32_t)(row_first * ST_CH * 4), b_z + (uint32_t)(row_first * ST_CH * (int)sizeof(T)),
-                        b_bc + (uint32_t)(row_first * SCAN_ROW * 4), b_p + (uint32_t)(row_first * ST_CH * (int)sizeof(T)),
+      T* po = ob + (int64_t)(row0 + (rev ? (L - 1 - s0) : s0)) * ldo;    // global row of step s0
+      scan_tile_tail<T>(nt, fin, partial, has_z, b_u + (uint32_t)(row_first * CH * (int)sizeof(T)),
+                        b_d + (uint32_t)(row_first * CH * 4), b_z + (uint32_t)(row_first * CH * (int)sizeof(T)),
+                        b_bc + (uint32_t)(row_first * SCAN_ROW * 4), b_p + (uint32_t)(row_first * CH * (int)sizeof(T)),
                         su, sd, sbc, Dv, oscale, active, h, a2, po, ostep, ypre_off, zpre);
     }
 
     // hand the stage back.  The elected thread then (a) bulk-stores the tile finished one iteration ago, once all
     // four warps have released it, and (b) refills the stage of the tile before that, once its store has drained.
     __syncwarp();
-    if (lane == 0) sbar_arrive(empty_bar(stage));
-    if (k >= 1 && owns(k - 1) && !(bidir && k == n1t)) store_tile(k - 1);     // (tile n1t-1 left at the phase barrier)
-    if (k >= 2 && owns(k - 2)) {
-      const int kk = k - 2 + NSTG;                    // tile that reuses the stage of tile k-2
-      if (kk < ntiles) {
-        bulk_wait_read<0>();                          // this thread's store of tile k-2 has left shared memory
-        issue_tile(kk, k >= n1t);
+    if (my_lane0) {
+      sbar_arrive(empty_bar(stage));
+      if (m == m_store && k >= 1 && !(bidir && k == n1t)) store_tile(k - 1);     // (tile n1t-1 left at the phase barrier)
+      if (m == m_refill && k >= 2) {
+        const int kk = k - 2 + NSTG;                  // tile that reuses the stage of tile k-2
+        if (kk < ntiles) {
+          bulk_wait_read<0>();                        // this thread's store of tile k-2 has left shared memory
+          issue_tile(kk, k >= n1t);
+        }
       }
     }
+    s0 += nt;
+    stage = (stage + 1 == NSTG) ? 0 : stage + 1;
+    m = (m + 1 == NW) ? 0 : m + 1;
   }
   if (ntiles > 0 && owns(ntiles - 1)) store_tile(ntiles - 1);
   if (my_lane0) bulk_wait_all<0>();           // shared memory must outlive the bulk stores
@@ -394,27 +412,36 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   }
 }
 
-template <typename T, int NSTG>
+template <typename T, int NSTG, int CH>
 static int launch_n(const ScanTmaMaps& maps, const ScanParams& p, cudaStream_t st) {
-  using SL = StageLayout<T, NSTG>;
+  using SL = StageLayout<T, NSTG, CH>;
+  constexpr int MINB = CH <= 128 ? 2 : 1;
   static bool attr_set = false;
-  // two resident CTAs per SM (128 registers, 90-110 KB of stages each); a 3-CTA / 80-register build measured slower
+  // CH = 128: two resident CTAs per SM (128 registers, 90-110 KB of stages each); a 3-CTA / 80-register build measured slower
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, 2, NSTG>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, MINB, NSTG, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("aum_selective_scan_fwd: cudaFuncSetAttribute(smem=%d): %s", SL::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
     attr_set = true;
   }
-  dim3 grid(ceil_div(p.Dch, ST_CH), p.batch);
+  dim3 grid(ceil_div(p.Dch, CH), p.batch);
   const int smem = p.ndirs * SL::GROUP_BYTES + 128 + 2 * 3 * NSTG * 8;     // one ring per direction actually launched
-  scan_fwd_tma_kernel<T, 2, NSTG><<<grid, ST_CH * p.ndirs, smem, st>>>(maps, p);
+  scan_fwd_tma_kernel<T, MINB, NSTG, CH><<<grid, CH * p.ndirs, smem, st>>>(maps, p);
   return check_launch("aum_selective_scan_fwd(tma)");
+}
+
+// AUM_SCAN_TMA_CH=192 selects the one-CTA-per-SM build (see the note on CH above); ring depth 3 there (98 KB).
+int scan_tma_ch() {
+  static int ch = 0;
+  if (ch == 0) { const char* e = getenv("AUM_SCAN_TMA_CH"); ch = (e && atoi(e) == 192) ? 192 : 128; }
+  return ch;
 }
 
 template <typename T>
 static int launch_t(const ScanTmaMaps& maps, const ScanParams& p, cudaStream_t st) {
   static int nstg = 0;
-  if (nstg == 0) { const char* e = getenv("AUM_SCAN_NSTG"); nstg = (e && atoi(e) == 5) ? 5 : 4; }   // 4 measured best (5: 1-3% slower)
-  return nstg == 4 ? launch_n<T, 4>(maps, p, st) : launch_n<T, 5>(maps, p, st);
+  if (nstg == 0) { const char* e = getenv("AUM_SCAN_NSTG"); nstg = (e && atoi(e) == 5) ? 5 : (e && atoi(e) == 3) ? 3 : 4; }   // 4 measured best (5: 1-3% slower)
+  if (scan_tma_ch() == 192) return nstg == 3 ? launch_n<T, 3, 192>(maps, p, st) : launch_n<T, 4, 192>(maps, p, st);
+  return nstg == 4 ? launch_n<T, 4, 128>(maps, p, st) : nstg == 3 ? launch_n<T, 3, 128>(maps, p, st) : launch_n<T, 5, 128>(maps, p, st);
 }
 
 int launch_scan_tma(const ScanParams& p, int dtype, int delta_dt, cudaStream_t st) {
@@ -431,15 +458,16 @@ int launch_scan_tma(const ScanParams& p, int dtype, int delta_dt, cudaStream_t s
     if (!ok_mat(d.u, d.ld_u, esz) || !ok_mat(d.delta, d.ld_delta, 4) || !aligned16(d.A)) return -1;
   }
   ScanTmaMaps maps;
+  const int CH = scan_tma_ch();
   const int64_t rows = (int64_t)p.batch * p.L;
   for (int g = 0; g < 2; ++g) {
     const ScanDirDev& d = p.dir[g < p.ndirs ? g : 0];
-    if (int rc = tma_encode_2d(&maps.u[g], d.u, dtype, rows, p.Dch, d.ld_u, ST_TT, ST_CH, false, "aum_selective_scan_fwd(u)")) return rc;
-    if (int rc = tma_encode_2d(&maps.d[g], d.delta, AUM_F32, rows, p.Dch, d.ld_delta, ST_TT, ST_CH, false, "aum_selective_scan_fwd(delta)")) return rc;
+    if (int rc = tma_encode_2d(&maps.u[g], d.u, dtype, rows, p.Dch, d.ld_u, ST_TT, CH, false, "aum_selective_scan_fwd(u)")) return rc;
+    if (int rc = tma_encode_2d(&maps.d[g], d.delta, AUM_F32, rows, p.Dch, d.ld_delta, ST_TT, CH, false, "aum_selective_scan_fwd(delta)")) return rc;
   }
-  if (p.z) { if (int rc = tma_encode_2d(&maps.z, p.z, dtype, rows, p.Dch, p.ld_z, ST_TT, ST_CH, false, "aum_selective_scan_fwd(z)")) return rc; }
+  if (p.z) { if (int rc = tma_encode_2d(&maps.z, p.z, dtype, rows, p.Dch, p.ld_z, ST_TT, CH, false, "aum_selective_scan_fwd(z)")) return rc; }
   else maps.z = maps.u[0];
-  if (int rc = tma_encode_2d(&maps.o, p.out, dtype, rows, p.Dch, p.ld_out, ST_TT, ST_CH, false, "aum_selective_scan_fwd(out)")) return rc;
+  if (int rc = tma_encode_2d(&maps.o, p.out, dtype, rows, p.Dch, p.ld_out, ST_TT, CH, false, "aum_selective_scan_fwd(out)")) return rc;
   switch (dtype) {
     case AUM_F32:  return launch_t<float>(maps, p, st);
     case AUM_F16:  return launch_t<__half>(maps, p, st);
