@@ -21,20 +21,25 @@ namespace aum {
 constexpr int TC_BM = 128;
 constexpr int TC_BK = 64;              // 64 x 2 B = 128 B = one swizzle row
 constexpr int TC_UMMA_K = 16;
-constexpr int TC_THREADS = 320;             // 2 control warps + 8 epilogue warps
 constexpr int TC_SMEM_BUDGET = 192 * 1024;     // operand ring
 constexpr int TC_CSTAGE_BYTES = 128 * 128;      // one epilogue staging buffer: 128 rows x 128 B (swizzled)
 constexpr int TC_EPI_BAR = 1;                   // named barriers 1,2: the two epilogue warp-sets
 
-template <int BN> struct TcCfg {
+// NSETS: epilogue warp-sets of 4 warps (one warp per TMEM lane quarter); each set owns a staging buffer, a named
+// barrier and a store thread and takes every NSETS-th column slab of a tile.  2 sets for the MMA-bound projections;
+// 4 sets (16 epilogue warps, four per scheduler) for dt_proj, whose tile is ONE k-block of MMA followed by 32 K
+// bias + softplus evaluations: with 8 epilogue warps that epilogue ran at 0.25 IPC per scheduler and took 3x the
+// time of the 202 MB delta write it feeds.
+template <int BN, int NSETS = 2> struct TcCfg {
   static constexpr int A_BYTES = TC_BM * TC_BK * 2;          // 16 KB
   static constexpr int B_BYTES = BN * TC_BK * 2;
   static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
-  static constexpr int STAGES_RAW = TC_SMEM_BUDGET / STAGE_BYTES;
+  static constexpr int THREADS = 64 + 128 * NSETS;           // 2 control warps + 4 NSETS epilogue warps
+  static constexpr int STAGES_RAW = (TC_SMEM_BUDGET - (NSETS - 2) * TC_CSTAGE_BYTES) / STAGE_BYTES;
   static constexpr int STAGES = STAGES_RAW > 8 ? 8 : STAGES_RAW;
   static constexpr int ACC_STRIDE = BN <= 32 ? 32 : BN <= 64 ? 64 : BN <= 128 ? 128 : 256;   // TMEM columns / buffer
   static constexpr int TMEM_COLS = 2 * ACC_STRIDE;
-  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + 2 * TC_CSTAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NSETS * TC_CSTAGE_BYTES + 1024 /*align slack*/ + 256 /*barriers*/;
   static_assert(BN % 16 == 0 && BN >= 16 && BN <= 256, "UMMA N constraint for M=128");
   static_assert(B_BYTES % 1024 == 0, "W tile must keep 1024-byte stage alignment");
 };
@@ -82,12 +87,17 @@ template <int N> __device__ __forceinline__ void tma_store_wait_read() {
   asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
 }
 __device__ __forceinline__ void epi_barrier(int set) { asm volatile("bar.sync %0, %1;" ::"r"(TC_EPI_BAR + set), "n"(128) : "memory"); }
-// softplus for the dt_proj epilogue: ~10 instructions, relative error < 1e-5 over the whole range
-// (log1p series below t = 0.01 where 1 + t would lose the low bits; matches torch's threshold-20 semantics)
+// softplus for the dt_proj epilogue, branch-free: max(x, 0) + log1p(e), e = exp(-|x|) in (0, 1].  log1p(e) is
+// ln(1 + e) above e = 0.01 and its series below it (where 1 + e would lose the low bits of e); flush-to-zero MUFU
+// forms (the default ones carry a 3-instruction range fix-up each).  Relative error < 1e-5 over the whole range;
+// x > 20 returns x to fp32 precision, which is torch's threshold-20 behaviour.
 __device__ __forceinline__ float softplus_fast(float x) {
-  if (x > 20.f) return x;
-  const float t = __expf(x);
-  return t < 0.01f ? t * (1.f - t * (0.5f - t * 0.33333334f)) : __logf(1.f + t);
+  const float e = ex2_approx(-1.4426950408889634f * fabsf(x));
+  float l;
+  asm("lg2.approx.ftz.f32 %0, %1;" : "=f"(l) : "f"(1.f + e));
+  const float series = e * (1.f - e * (0.5f - e * 0.33333334f));
+  const float lp = e < 0.01f ? series : l * 0.6931471805599453f;
+  return fmaxf(x, 0.f) + lp;
 }
 __device__ __forceinline__ void st_shared_v4(uint32_t addr, uint32_t a, uint32_t b, uint32_t c, uint32_t d) {
   asm volatile("st.shared.v4.b32 [%0], {%1, %2, %3, %4};" ::"r"(addr), "r"(a), "r"(b), "r"(c), "r"(d) : "memory");
@@ -133,18 +143,18 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
-template <int BN>
-__global__ void __launch_bounds__(TC_THREADS, 1)
+template <int BN, int NSETS>
+__global__ void __launch_bounds__(TcCfg<BN, NSETS>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
                     const __grid_constant__ CUtensorMap tmC, int tma_store,
                     EpiParams ep, int M, int N, int K, uint32_t idesc) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, NSETS>;
   constexpr int STAGES = Cfg::STAGES;
   extern __shared__ uint8_t smem_raw[];
   // 1024-byte alignment required by the 128-byte swizzle atoms
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t cstage_base = smem_base + STAGES * Cfg::STAGE_BYTES;     // 2 x 16 KB, 1024-aligned
-  const uint32_t bar_base = cstage_base + 2 * TC_CSTAGE_BYTES;
+  const uint32_t cstage_base = smem_base + STAGES * Cfg::STAGE_BYTES;     // NSETS x 16 KB, 1024-aligned
+  const uint32_t bar_base = cstage_base + NSETS * TC_CSTAGE_BYTES;
   auto full_bar = [&](int s) { return bar_base + 8u * s; };
   auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
   auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
@@ -158,7 +168,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
-    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 256); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 128 * NSETS); }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
@@ -219,7 +229,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     }
     __syncwarp();
   } else {
-    // ================= epilogue warps (2..9): two independent sets of 4 warps =================
+    // ================= epilogue warps (2..): NSETS independent sets of 4 warps =================
     // Each set covers all 128 accumulator rows (one warp per TMEM lane quarter) and takes every other
     // 128-byte-wide column slab of the tile; it owns one staging buffer, one named barrier and one store thread.
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
@@ -245,7 +255,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
         const uint32_t srow = buf + (uint32_t)row_in_tile * 128u;
         const uint32_t sw = (uint32_t)(row_in_tile & 7);
 #pragma unroll 1
-        for (int c0 = set * slab_cols; c0 < BN; c0 += 2 * slab_cols) {
+        for (int c0 = set * slab_cols; c0 < BN; c0 += NSETS * slab_cols) {
           if (n0 + c0 >= N) break;                   // warp-uniform
           if (store_thread) tma_store_wait_read<0>();   // this set's previous store has drained its buffer
           epi_barrier(set);
@@ -329,7 +339,7 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       } else {
         // per-thread vector stores (split outputs, odd pitches): each set takes alternate 32-column chunks
 #pragma unroll 1
-        for (int c0 = set * 32; c0 < BN; c0 += 64) {
+        for (int c0 = set * 32; c0 < BN; c0 += 32 * NSETS) {
           if (n0 + c0 >= N) break;                     // warp-uniform
           uint32_t r[32];
           tc_ld_32x32b_x32(t_row + (uint32_t)c0, r);
@@ -419,10 +429,10 @@ bool tcgen05_eligible(const void* A, int64_t lda, const void* W, int64_t ldw, in
 
 static int g_sm_count = 0;
 
-template <int BN>
+template <int BN, int NSETS = 2>
 static int launch_bn(const CUtensorMap& tmA, const void* W, int64_t ldw, int ab_dt, const EpiParams& ep,
                      int M, int N, int K, cudaStream_t st) {
-  using Cfg = TcCfg<BN>;
+  using Cfg = TcCfg<BN, NSETS>;
   CUtensorMap tmW, tmC;
   if (int rc = make_tmap(&tmW, W, N, K, ldw, BN, ab_dt)) return rc;
   // TMA-store epilogue when there is a single, 16-byte-pitched output; otherwise per-thread vector stores
@@ -431,7 +441,7 @@ static int launch_bn(const CUtensorMap& tmA, const void* W, int64_t ldw, int ab_
   else tmC = tmW;
   static bool attr_set = false;
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_kernel<BN, NSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("aum_gemm_tn: cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
     attr_set = true;
   }
@@ -444,7 +454,7 @@ static int launch_bn(const CUtensorMap& tmA, const void* W, int64_t ldw, int ab_
                        | ((uint32_t)(TC_BM >> 4) << 24);  // M >> 4
   const int tiles = ceil_div(M, TC_BM) * ceil_div(N, BN);
   const int grid = tiles < g_sm_count ? tiles : g_sm_count;
-  gemm_tcgen05_kernel<BN><<<grid, TC_THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, tmC, tma_store, ep, M, N, K, idesc);
+  gemm_tcgen05_kernel<BN, NSETS><<<grid, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, tmC, tma_store, ep, M, N, K, idesc);
   return check_launch("aum_gemm_tn(tcgen05)");
 }
 
@@ -462,6 +472,8 @@ int launch_gemm_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, 
   if (N <= 64)  return launch_bn<64>(tmA, W, ldw, ab_dt, ep, M, N, K, st);
   if (N <= 96)  return launch_bn<96>(tmA, W, ldw, ab_dt, ep, M, N, K, st);
   if (N <= 128) return launch_bn<128>(tmA, W, ldw, ab_dt, ep, M, N, K, st);
+  // one k-block of MMA per tile and a wide output: the epilogue is the kernel (dt_proj) -> 16 epilogue warps
+  if (K <= TC_BK && N >= 512 && getenv("AUM_GEMM_EPI2") == nullptr) return launch_bn<256, 4>(tmA, W, ldw, ab_dt, ep, M, N, K, st);
   if (N % 256 == 0 || N > 1024) return launch_bn<256>(tmA, W, ldw, ab_dt, ep, M, N, K, st);
   return launch_bn<128>(tmA, W, ldw, ab_dt, ep, M, N, K, st);
 }

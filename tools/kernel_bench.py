@@ -142,6 +142,16 @@ def main():
             if name in ("in_proj", "out_proj"):
                 ms = timeit(lambda: torch.matmul(a, w.t(), out=out), flush=flush)
                 report("cublas_" + name, ms, flops=2.0 * m_ * n_ * k_)
+            if name == "x_proj":      # as the mixer calls it: dt (16-bit, padded pitch) | [B|C] (fp32) split epilogue
+                rp = (R + 7) // 8 * 8
+                dt_o = torch.empty(m_, rp, device=dev, dtype=dt)
+                bc_o = torch.empty(m_, 2 * N, device=dev, dtype=torch.float32)
+                ms = timeit(lambda: ops.gemm_tn(a, w, out=dt_o, out2=bc_o, split=R, backend=L.GEMM_TCGEN05), flush=flush)
+                report("gemm_x_proj(split dt|BC)", ms, bytes_=(m_ * k_ + n_ * k_) * 2 + m_ * (R * 2 + 2 * N * 4))
+            if name == "dt_proj":     # as the mixer calls it: + bias + softplus, fp32 delta
+                bias = rn(n_, dtype=torch.float32)
+                ms = timeit(lambda: ops.gemm_tn(a, w, out=out, k=k_, bias=bias, act=L.ACT_SOFTPLUS, backend=L.GEMM_TCGEN05), flush=flush)
+                report("gemm_dt_proj(+bias+softplus)", ms, bytes_=by)
             if name == "in_proj":
                 ms = timeit(lambda: ops.gemm_tn(a, w, out=out, k=k_, backend=L.GEMM_TCGEN05,
                                                 act=L.act_from(L.ACT_SILU, n_ // 2)), flush=flush)
