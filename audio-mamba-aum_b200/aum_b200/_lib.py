@@ -103,6 +103,29 @@ SIGNATURES = {
 
 _lib = None
 
+# bench.py hook: when set to a list, every kernel-launching C-ABI call appends (symbol, start_event, end_event)
+# (CUDA events on the launching stream), so that a kernel's share of a step can be computed from like-for-like times.
+PROFILE_ALL = None
+_NO_LAUNCH = {"aum_version", "aum_last_error", "aum_device_info", "aum_selective_scan_bwd_workspace_floats",
+              "aum_selective_scan_bwd_dbc_ws_floats"}
+
+
+class _Lib:
+    pass
+
+
+def _timed(name, fn):
+    def call(*args):
+        if PROFILE_ALL is None:
+            return fn(*args)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        PROFILE_ALL.append((name, e0, e1))
+        return rc
+    return call
+
 
 def lib():
     """Load (once) and return the shared library; raises if it has not been built."""
@@ -113,11 +136,14 @@ def lib():
                 f"{LIB_PATH} not found: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
                 "or `make -C audio-mamba-aum_b200/csrc`. There is no CPU / PyTorch fallback.")
         L = C.CDLL(LIB_PATH)
+        ns = _Lib()
         for name, (res, args) in SIGNATURES.items():
             fn = getattr(L, name)     # AttributeError if the symbol is not exported
             fn.restype = res
             fn.argtypes = args
-        _lib = L
+            setattr(ns, name, fn if name in _NO_LAUNCH else _timed(name, fn))
+        ns._cdll = L
+        _lib = ns
     return _lib
 
 

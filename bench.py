@@ -284,12 +284,19 @@ def main():
     # bracketed by events); also counts this repo's kernel launches per step.
     calls0 = _lib.launch_count()
     ops.PROFILE = []
+    _lib.PROFILE_ALL = []
     barrier()
     for _ in range(args.steps):
         step_resident()
     barrier()
     prof, ops.PROFILE = ops.PROFILE, None
+    prof_all, _lib.PROFILE_ALL = _lib.PROFILE_ALL, None
     launches = (_lib.launch_count() - calls0)
+    # the scan's share of the step from like-for-like numbers: event-bracketed duration of every kernel this repo
+    # launched in the same instrumented pass (with two sequence groups on two streams the per-kernel durations
+    # overlap, so their sum exceeds the wall time and "scan time / wall time" would overstate the share)
+    all_ms = sum(s.elapsed_time(e) for (_, s, e) in prof_all) if prof_all else 0.0
+    scan_all_ms = sum(s.elapsed_time(e) for (n, s, e) in prof_all if n == "aum_selective_scan_fwd") if prof_all else 0.0
     peak, peak_src = peaks()
     scan_ms = [s.elapsed_time(e) for (name, s, e) in prof if name == "selective_scan"] if prof else []
     Lq = (F_ // 16) * (T_ // 16) + 1
@@ -305,8 +312,13 @@ def main():
         roof = {"kernel": "scan_fwd_kernel (fused forward+reverse selective scan)", "bound": "hbm", "achieved": ach,
                 "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": scan_traffic(B // mb), "peak_source": peak_src,
                 "avg_launch_ms": avg, "launches_timed": len(scan_ms), "algorithmic_bytes_per_launch": alg_bytes,
-                "share_of_step": avg * CFG["depth"] * mb / ms_step, "sequences_per_launch": B // mb,
-                "note": "16 ex2 per (token,channel,direction): MUFU-bound before HBM-bound, see DESIGN.md"}
+                "share_of_step": (scan_all_ms / all_ms) if all_ms > 0 else None, "sequences_per_launch": B // mb,
+                # the ceiling that actually binds this kernel: one MUFU.EX2 per (token, channel, state, direction);
+                # peak = 15.8 results/clk/SM measured (profiles/r1_microbench_pipe_rates.txt) x 148 SMs x max SM clock
+                "xu_pipe": {"achieved_Texp_per_s": M * Di * Nst * 2 / (avg * 1e-3) / 1e12,
+                            "peak_Texp_per_s": 15.8 * 148 * 1.965e9 / 1e12,
+                            "frac": (M * Di * Nst * 2 / (avg * 1e-3) / 1e12) / (15.8 * 148 * 1.965e9 / 1e12)},
+                "note": "16 ex2 per (token,channel,direction): MUFU-bound before HBM-bound (xu_pipe), see DESIGN.md section 5"}
 
     if rank == 0:
         cpu = None
