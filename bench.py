@@ -282,19 +282,22 @@ def main():
     # ---- roofline of the dominant kernel (bidirectional scan): CUDA-event pairs around every scan launch of an
     # instrumented, eagerly-launched repeat of the same K steps (kernels inside a replayed CUDA graph cannot be
     # bracketed by events); also counts this repo's kernel launches per step.
+    # The pass launches the SAME kernels on the SAME sizes, but with the two sequence groups on one stream, so that each
+    # launch runs alone: a launch duration measured while another stream's kernels share the SMs is not the kernel's.
     calls0 = _lib.launch_count()
     ops.PROFILE = []
     _lib.PROFILE_ALL = []
+    model.serialize_groups = True
     barrier()
     for _ in range(args.steps):
         step_resident()
     barrier()
+    model.serialize_groups = False
     prof, ops.PROFILE = ops.PROFILE, None
     prof_all, _lib.PROFILE_ALL = _lib.PROFILE_ALL, None
     launches = (_lib.launch_count() - calls0)
-    # the scan's share of the step from like-for-like numbers: event-bracketed duration of every kernel this repo
-    # launched in the same instrumented pass (with two sequence groups on two streams the per-kernel durations
-    # overlap, so their sum exceeds the wall time and "scan time / wall time" would overstate the share)
+    # the scan's share of the step: its event-bracketed time over that of every kernel this repo launched in the pass
+    # (the quantity the committed ncu launch list gives as well)
     all_ms = sum(s.elapsed_time(e) for (_, s, e) in prof_all) if prof_all else 0.0
     scan_all_ms = sum(s.elapsed_time(e) for (n, s, e) in prof_all if n == "aum_selective_scan_fwd") if prof_all else 0.0
     peak, peak_src = peaks()

@@ -27,7 +27,9 @@ def rnd(shape, g, dt=torch.float32, scale=1.0):
 
 # ----------------------------------------------------------------------------------------------------
 @pytest.mark.parametrize("dt", DTYPES)
-@pytest.mark.parametrize("B,Lq,D,W", [(2, 64, 384, 4), (3, 37, 40, 4), (1, 5, 7, 3), (2, 9, 16, 2), (1, 1, 8, 4)])
+@pytest.mark.parametrize("B,Lq,D,W", [(2, 64, 384, 4), (3, 37, 40, 4), (1, 5, 7, 3), (2, 9, 16, 2), (1, 1, 8, 4),
+                                      (2, 33, 38, 4),      # D % 4 != 0: two-channel kernel
+                                      (1, 513, 1536, 4)])  # one config-2 sequence (4-channel kernel, 33 token tiles)
 def test_causal_conv1d(dt, B, Lq, D, W):
     from aum_b200 import ops
     g = gen(1)
@@ -164,6 +166,17 @@ def test_gemm_tcgen05_epilogues(dt):
     delta = ops.gemm_tn(dtb, wdt.to(DEV), k=R, bias=bias.to(DEV), act=L.ACT_SOFTPLUS, out_dtype=torch.float32,
                         backend=L.GEMM_TCGEN05)
     torch.testing.assert_close(delta.cpu(), refd, rtol=1e-4, atol=1e-5)
+    # the whole softplus range (torch threshold 20, tiny values below -20) and more tiles than SMs through the
+    # 16-epilogue-warp kernel: relative error everywhere
+    M2 = 20000
+    a2 = torch.zeros((M2, 64), dtype=dt)
+    a2[:, :R] = rnd((M2, R), g, dt)
+    bias2 = torch.linspace(-45.0, 45.0, Di)
+    refw = _gemm_ref(a2[:, :R].float(), wdt[:, :R].float(), bias2, None, True)
+    dw = ops.gemm_tn(a2.to(DEV), wdt.to(DEV), k=R, bias=bias2.to(DEV), act=L.ACT_SOFTPLUS, out_dtype=torch.float32,
+                     backend=L.GEMM_TCGEN05).cpu()
+    assert torch.isfinite(dw).all()
+    assert ((dw - refw).abs() <= 1e-4 * refw.abs() + 1e-30).all()
     # row scaling
     rs = 1 + 0.2 * rnd((M,), g)
     out = ops.gemm_tn(u.to(DEV), wx.to(DEV), row_scale=rs.to(DEV), out_dtype=torch.float32, backend=L.GEMM_TCGEN05)
@@ -303,3 +316,16 @@ def test_empty_batch_and_zero_length_are_noops():
     assert ops.gemm_tn(torch.zeros(0, 16, device=DEV), torch.zeros(4, 16, device=DEV)).shape == (0, 4)
     y = ops.add_rmsnorm(torch.zeros(0, 16, device=DEV), torch.ones(16, device=DEV))
     assert y.shape == (0, 16)
+
+
+def test_scan_192_channel_build():
+    """The one-CTA-per-SM build of the TMA-streamed scan (AUM_SCAN_TMA_CH=192, 6 warps per direction) is selected per
+    process, so it runs in a child: every scan parity case again."""
+    import os
+    import subprocess
+    import sys
+    env = dict(os.environ, AUM_SCAN_TMA_CH="192")
+    r = subprocess.run([sys.executable, "-m", "pytest", __file__, "-q", "-x", "-p", "no:cacheprovider", "-m", "gpu",
+                        "-k", "selective_scan_all_modes or length_sweep or properties_at_full_size"],
+                       env=env, capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
