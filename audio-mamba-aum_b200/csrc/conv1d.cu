@@ -114,15 +114,6 @@ conv1d_fwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
 // works on scalar lanes), which makes it issue-bound at 2.5 TB/s.  This one converts each input row once into two
 // packed fp32x2 pairs, runs the taps as FFMA2 on the pairs (2 per element) and stores 8 or 16 bytes per thread:
 // ~10 instructions per element, so the kernel is bound by HBM again.  Needs D, pitches and bases 4-element aligned.
-// x * sigmoid(x) with flush-to-zero MUFU ops: FMUL + EX2 + FADD + RCP + FMUL (the non-ftz forms add a range fix-up
-// of 3 instructions per MUFU).  exp2 overflow -> rcp(inf) = 0 -> -0, underflow -> x.
-__device__ __forceinline__ float silu_ftz(float x) {
-  float r;
-  const float e = ex2_approx(-1.4426950408889634f * x);
-  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
-  return x * r;
-}
-
 template <typename T> struct Quad;      // 4 adjacent channels as loaded
 template <> struct Quad<float> {
   float4 v;

@@ -143,6 +143,128 @@ __device__ __forceinline__ uint64_t make_smem_desc_sw128(uint32_t smem_addr) {
   return d;
 }
 
+// Epilogue of one 128 x BN accumulator tile (TMEM lanes = rows), run by the NSETS warp-sets of a CTA: TMEM -> registers
+// -> (row scale, bias, activation) -> convert -> 128B-swizzled staging slab -> TMA store, or per-thread vector stores
+// (split outputs, odd pitches).  t_acc: TMEM address of the tile's accumulator (lane 0, first column).
+template <int BN, int NSETS>
+__device__ __forceinline__ void tc_epilogue_tile(const EpiParams& ep, const CUtensorMap* tmC, int tma_store,
+                                                 uint32_t t_acc, int m0, int n0, int M, int N,
+                                                 int q, int set, int lane, bool store_thread, uint32_t cstage_base) {
+  const bool has_bias = ep.bias != nullptr, has_rs = ep.row_scale != nullptr;
+  const int act = ep.act;
+  const bool plain = !has_bias && !has_rs && act == AUM_ACT_NONE;
+  const int row_in_tile = q * 32 + lane;
+  const int row = m0 + row_in_tile;
+  const float rs = (has_rs && row < M) ? __ldg(ep.row_scale + row) : 1.f;
+  const uint32_t t_row = t_acc + ((uint32_t)(q * 32) << 16);
+  if (tma_store) {
+    // TMEM -> registers -> (scale, bias, activation) -> convert -> 128B-swizzled smem slab -> TMA store
+    const int c_sz = (ep.c_dt == AUM_F32) ? 4 : 2;
+    const int slab_cols = 128 / c_sz;            // 64 16-bit or 32 fp32 columns
+    const uint32_t buf = cstage_base + (uint32_t)set * TC_CSTAGE_BYTES;
+    const uint32_t srow = buf + (uint32_t)row_in_tile * 128u;
+    const uint32_t sw = (uint32_t)(row_in_tile & 7);
+#pragma unroll 1
+    for (int c0 = set * slab_cols; c0 < BN; c0 += NSETS * slab_cols) {
+      if (n0 + c0 >= N) break;                   // warp-uniform
+      if (store_thread) tma_store_wait_read<0>();   // this set's previous store has drained its buffer
+      epi_barrier(set);
+#pragma unroll 1
+      for (int cc = 0; cc < slab_cols; cc += 32) {
+        uint32_t r[32];
+        tc_ld_32x32b_x32(t_row + (uint32_t)(c0 + cc), r);
+        tc_wait_ld();
+        if (!plain) {
+          // Every decision below is warp-uniform and hoisted out of the 32-element loops, so that each loop is
+          // straight-line code whose MUFU chains the compiler can interleave (a per-element predicate made this
+          // path latency-bound: 3x the MMA time per tile).
+          const int colb = n0 + c0 + cc;
+          if (has_rs) {
+#pragma unroll
+            for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * rs);
+          }
+          if (has_bias) {
+            if (colb + 32 <= N) {
+              const float4* bp = reinterpret_cast<const float4*>(ep.bias + colb);
+              const bool al = (reinterpret_cast<uintptr_t>(bp) & 15) == 0;
+#pragma unroll
+              for (int i = 0; i < 8; ++i) {
+                float4 b4;
+                if (al) b4 = __ldg(bp + i);
+                else b4 = make_float4(__ldg(ep.bias + colb + 4 * i), __ldg(ep.bias + colb + 4 * i + 1),
+                                      __ldg(ep.bias + colb + 4 * i + 2), __ldg(ep.bias + colb + 4 * i + 3));
+                r[4 * i]     = __float_as_uint(__uint_as_float(r[4 * i]) + b4.x);
+                r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + b4.y);
+                r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + b4.z);
+                r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + b4.w);
+              }
+            } else {
+#pragma unroll
+              for (int i = 0; i < 32; ++i)
+                if (colb + i < N) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(ep.bias + colb + i));
+            }
+          }
+          if (act != AUM_ACT_NONE && colb + 32 > ep.act_col0) {
+            if (colb >= ep.act_col0) {              // whole chunk inside the activated column range
+              if (act == AUM_ACT_SILU) {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(silu_ftz(__uint_as_float(r[i])));
+              } else {
+#pragma unroll
+                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(softplus_fast(__uint_as_float(r[i])));
+              }
+            } else {                                // chunk straddles act_col0 (not 32-aligned): per element
+#pragma unroll
+              for (int i = 0; i < 32; ++i) {
+                float v = __uint_as_float(r[i]);
+                if (colb + i >= ep.act_col0) v = (act == AUM_ACT_SILU) ? silu_ftz(v) : softplus_fast(v);
+                r[i] = __float_as_uint(v);
+              }
+            }
+          }
+        }
+        if (c_sz == 4) {
+#pragma unroll
+          for (int k = 0; k < 8; ++k)            // 8 chunks of 4 floats (slab_cols == 32: cc == 0)
+            st_shared_v4(srow + ((((uint32_t)k) ^ sw) << 4), r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
+        } else {
+          const bool f16 = ep.c_dt == AUM_F16;
+#pragma unroll
+          for (int k = 0; k < 4; ++k) {          // 4 chunks of 8 halves per 32 columns
+            uint32_t pk[4];
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float lo = __uint_as_float(r[8 * k + 2 * j]), hi = __uint_as_float(r[8 * k + 2 * j + 1]);
+              if (f16) { __half2 h = __floats2half2_rn(lo, hi); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
+              else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
+            }
+            st_shared_v4(srow + ((((uint32_t)((cc >> 3) + k)) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
+          }
+        }
+      }
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+      epi_barrier(set);
+      if (store_thread) { tma_store_2d(tmC, buf, n0 + c0, m0); tma_store_commit(); }
+    }
+  } else {
+    // per-thread vector stores (split outputs, odd pitches): each set takes alternate 32-column chunks
+#pragma unroll 1
+    for (int c0 = set * 32; c0 < BN; c0 += 32 * NSETS) {
+      if (n0 + c0 >= N) break;                     // warp-uniform
+      uint32_t r[32];
+      tc_ld_32x32b_x32(t_row + (uint32_t)c0, r);
+      tc_wait_ld();
+#pragma unroll
+      for (int g = 0; g < 4; ++g) {
+        float v[8];
+#pragma unroll
+        for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+        epi_store8(ep, row, n0 + c0 + g * 8, v, rs);
+      }
+    }
+  }
+}
+
 template <int BN, int NSETS>
 __global__ void __launch_bounds__(TcCfg<BN, NSETS>::THREADS, 1)
 gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
@@ -235,124 +357,13 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
     const int q = warp & 3;                         // TMEM lane quarter this warp may access
     const int set = (warp - 2) >> 2;                // 0 or 1
     const bool store_thread = (lane == 0) && (((warp - 2) & 3) == 0);
-    const bool has_bias = ep.bias != nullptr, has_rs = ep.row_scale != nullptr;
-    const int act = ep.act;
-    const bool plain = !has_bias && !has_rs && act == AUM_ACT_NONE;
     int acc = 0; uint32_t acc_phase = 0;
     for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
       const int m0 = (tile / n_tiles) * TC_BM, n0 = (tile % n_tiles) * BN;
       mbar_wait(tfull_bar(acc), acc_phase);
       tc_fence_after();
-      const int row_in_tile = q * 32 + lane;
-      const int row = m0 + row_in_tile;
-      const float rs = (has_rs && row < M) ? __ldg(ep.row_scale + row) : 1.f;
-      const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16) + (uint32_t)(acc * Cfg::ACC_STRIDE);
-      if (tma_store) {
-        // TMEM -> registers -> (scale, bias, activation) -> convert -> 128B-swizzled smem slab -> TMA store
-        const int c_sz = (ep.c_dt == AUM_F32) ? 4 : 2;
-        const int slab_cols = 128 / c_sz;            // 64 16-bit or 32 fp32 columns
-        const uint32_t buf = cstage_base + (uint32_t)set * TC_CSTAGE_BYTES;
-        const uint32_t srow = buf + (uint32_t)row_in_tile * 128u;
-        const uint32_t sw = (uint32_t)(row_in_tile & 7);
-#pragma unroll 1
-        for (int c0 = set * slab_cols; c0 < BN; c0 += NSETS * slab_cols) {
-          if (n0 + c0 >= N) break;                   // warp-uniform
-          if (store_thread) tma_store_wait_read<0>();   // this set's previous store has drained its buffer
-          epi_barrier(set);
-#pragma unroll 1
-          for (int cc = 0; cc < slab_cols; cc += 32) {
-            uint32_t r[32];
-            tc_ld_32x32b_x32(t_row + (uint32_t)(c0 + cc), r);
-            tc_wait_ld();
-            if (!plain) {
-              // Every decision below is warp-uniform and hoisted out of the 32-element loops, so that each loop is
-              // straight-line code whose MUFU chains the compiler can interleave (a per-element predicate made this
-              // path latency-bound: 3x the MMA time per tile).
-              const int colb = n0 + c0 + cc;
-              if (has_rs) {
-#pragma unroll
-                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(__uint_as_float(r[i]) * rs);
-              }
-              if (has_bias) {
-                if (colb + 32 <= N) {
-                  const float4* bp = reinterpret_cast<const float4*>(ep.bias + colb);
-                  const bool al = (reinterpret_cast<uintptr_t>(bp) & 15) == 0;
-#pragma unroll
-                  for (int i = 0; i < 8; ++i) {
-                    float4 b4;
-                    if (al) b4 = __ldg(bp + i);
-                    else b4 = make_float4(__ldg(ep.bias + colb + 4 * i), __ldg(ep.bias + colb + 4 * i + 1),
-                                          __ldg(ep.bias + colb + 4 * i + 2), __ldg(ep.bias + colb + 4 * i + 3));
-                    r[4 * i]     = __float_as_uint(__uint_as_float(r[4 * i]) + b4.x);
-                    r[4 * i + 1] = __float_as_uint(__uint_as_float(r[4 * i + 1]) + b4.y);
-                    r[4 * i + 2] = __float_as_uint(__uint_as_float(r[4 * i + 2]) + b4.z);
-                    r[4 * i + 3] = __float_as_uint(__uint_as_float(r[4 * i + 3]) + b4.w);
-                  }
-                } else {
-#pragma unroll
-                  for (int i = 0; i < 32; ++i)
-                    if (colb + i < N) r[i] = __float_as_uint(__uint_as_float(r[i]) + __ldg(ep.bias + colb + i));
-                }
-              }
-              if (act != AUM_ACT_NONE && colb + 32 > ep.act_col0) {
-                if (colb >= ep.act_col0) {              // whole chunk inside the activated column range
-                  if (act == AUM_ACT_SILU) {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(silu_f(__uint_as_float(r[i])));
-                  } else {
-#pragma unroll
-                    for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(softplus_fast(__uint_as_float(r[i])));
-                  }
-                } else {                                // chunk straddles act_col0 (not 32-aligned): per element
-#pragma unroll
-                  for (int i = 0; i < 32; ++i) {
-                    float v = __uint_as_float(r[i]);
-                    if (colb + i >= ep.act_col0) v = (act == AUM_ACT_SILU) ? silu_f(v) : softplus_fast(v);
-                    r[i] = __float_as_uint(v);
-                  }
-                }
-              }
-            }
-            if (c_sz == 4) {
-#pragma unroll
-              for (int k = 0; k < 8; ++k)            // 8 chunks of 4 floats (slab_cols == 32: cc == 0)
-                st_shared_v4(srow + ((((uint32_t)k) ^ sw) << 4), r[4 * k], r[4 * k + 1], r[4 * k + 2], r[4 * k + 3]);
-            } else {
-              const bool f16 = ep.c_dt == AUM_F16;
-#pragma unroll
-              for (int k = 0; k < 4; ++k) {          // 4 chunks of 8 halves per 32 columns
-                uint32_t pk[4];
-#pragma unroll
-                for (int j = 0; j < 4; ++j) {
-                  const float lo = __uint_as_float(r[8 * k + 2 * j]), hi = __uint_as_float(r[8 * k + 2 * j + 1]);
-                  if (f16) { __half2 h = __floats2half2_rn(lo, hi); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
-                  else { __nv_bfloat162 h = __floats2bfloat162_rn(lo, hi); pk[j] = *reinterpret_cast<uint32_t*>(&h); }
-                }
-                st_shared_v4(srow + ((((uint32_t)((cc >> 3) + k)) ^ sw) << 4), pk[0], pk[1], pk[2], pk[3]);
-              }
-            }
-          }
-          asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-          epi_barrier(set);
-          if (store_thread) { tma_store_2d(&tmC, buf, n0 + c0, m0); tma_store_commit(); }
-        }
-      } else {
-        // per-thread vector stores (split outputs, odd pitches): each set takes alternate 32-column chunks
-#pragma unroll 1
-        for (int c0 = set * 32; c0 < BN; c0 += 32 * NSETS) {
-          if (n0 + c0 >= N) break;                     // warp-uniform
-          uint32_t r[32];
-          tc_ld_32x32b_x32(t_row + (uint32_t)c0, r);
-          tc_wait_ld();
-#pragma unroll
-          for (int g = 0; g < 4; ++g) {
-            float v[8];
-#pragma unroll
-            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
-            epi_store8(ep, row, n0 + c0 + g * 8, v, rs);
-          }
-        }
-      }
+      tc_epilogue_tile<BN, NSETS>(ep, &tmC, tma_store, tmem_base + (uint32_t)(acc * Cfg::ACC_STRIDE), m0, n0, M, N,
+                                  q, set, lane, store_thread, cstage_base);
       tc_fence_before();
       mbar_arrive(tempty_bar(acc));
       if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
@@ -365,6 +376,176 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
   tc_fence_after();
   if (warp == 1) {
     asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+// =====================================================================================================
+// CTA-pair variant (cta_group::2) for the two MMA-bound projections (in_proj, out_proj).
+// The single-CTA kernel above is bound by the shared-memory operand reads of its 128 x 256 x 16 MMAs (narrower tiles
+// lose proportionally more); a pair of CTAs on the two SMs of a TPC computes a 256 x 256 tile with
+// each SM holding 128 rows of A and 128 of the 256 rows of W, so every SM reads half as many operand bytes per FLOP.
+//   * cluster (2,1,1); rank r loads A rows [m0 + 128 r, +128) and W rows [n0 + 128 r, +128) of every k-block into its
+//     own ring (cp.async.bulk.tensor ... cta_group::2: the transaction bytes of both CTAs complete on the LEADER's
+//     "full" barrier, whose expect_tx the leader posts for the pair);
+//   * only the leader (rank 0) issues tcgen05.mma.cta_group::2 (M = 256, N = 256, K = 16); its tcgen05.commit is
+//     multicast to both CTAs' "empty" (ring stage free) and "tmem_full" (accumulator ready) barriers;
+//   * each CTA runs the usual epilogue on its own 128 TMEM lanes = its 128 rows; one thread per epilogue warp of both
+//     CTAs arrives on the leader's "tmem_empty" barrier (remote mbarrier.arrive for the peer).
+// Barrier layout and shared-memory offsets are identical in both CTAs: a shared::cta address with bit 24 cleared is the
+// same location in the leader (cute::Sm100MmaPeerBitMask).
+// =====================================================================================================
+constexpr uint32_t TC_PEER_MASK = 0xFEFFFFFFu;
+constexpr int TC2_BN = 256;                       // output tile 256 (pair) x 256
+constexpr int TC2_BHALF = TC2_BN / 2;             // W rows per CTA
+
+template <int NSETS_> struct Tc2Cfg {
+  static constexpr int NSETS = NSETS_;
+  static constexpr int A_BYTES = TC_BM * TC_BK * 2;             // 16 KB
+  static constexpr int B_BYTES = TC2_BHALF * TC_BK * 2;         // 16 KB
+  static constexpr int STAGE_BYTES = A_BYTES + B_BYTES;
+  static constexpr int STAGES = (TC_SMEM_BUDGET - (NSETS - 2) * TC_CSTAGE_BYTES) / STAGE_BYTES;   // 6 / 5
+  static constexpr int THREADS = 64 + 128 * NSETS;
+  static constexpr int ACC_STRIDE = 256;
+  static constexpr int TMEM_COLS = 512;
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + NSETS * TC_CSTAGE_BYTES + 1024 + 256;
+};
+
+__device__ __forceinline__ uint32_t cluster_ctarank() { uint32_t r; asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r)); return r; }
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tma_load_2d_pair(uint32_t dst, const CUtensorMap* tm, int c0, int c1, uint32_t leader_bar) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];"
+      ::"r"(dst), "l"(tm), "r"(c0), "r"(c1), "r"(leader_bar) : "memory");
+}
+__device__ __forceinline__ void tc_commit_pair(uint32_t bar) {     // arrives on `bar` in both CTAs of the pair
+  asm volatile("tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;"
+               ::"r"(bar), "h"((uint16_t)3) : "memory");
+}
+__device__ __forceinline__ void tc_mma_f16_pair(uint32_t d_tmem, uint64_t a_desc, uint64_t b_desc, uint32_t idesc, uint32_t accumulate) {
+  asm volatile(
+      "{\n\t.reg .pred p;\n\t"
+      "setp.ne.b32 p, %4, 0;\n\t"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+      ::"r"(d_tmem), "l"(a_desc), "l"(b_desc), "r"(idesc), "r"(accumulate) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_leader(uint32_t bar) {   // from either CTA: the leader's copy of `bar`
+  asm volatile("mbarrier.arrive.release.cluster.shared::cluster.b64 _, [%0];" ::"r"(bar & TC_PEER_MASK) : "memory");
+}
+
+template <int NSETS_>
+__global__ void __cluster_dims__(2, 1, 1) __launch_bounds__(Tc2Cfg<NSETS_>::THREADS, 1)
+gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_constant__ CUtensorMap tmW,
+                         const __grid_constant__ CUtensorMap tmC, int tma_store,
+                         EpiParams ep, int M, int N, int K, uint32_t idesc) {
+  using Cfg = Tc2Cfg<NSETS_>;
+  constexpr int STAGES = Cfg::STAGES, NSETS = Cfg::NSETS;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t cstage_base = smem_base + STAGES * Cfg::STAGE_BYTES;
+  const uint32_t bar_base = cstage_base + NSETS * TC_CSTAGE_BYTES;
+  auto full_bar = [&](int s) { return bar_base + 8u * s; };
+  auto empty_bar = [&](int s) { return bar_base + 8u * (STAGES + s); };
+  auto tfull_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + a); };
+  auto tempty_bar = [&](int a) { return bar_base + 8u * (2 * STAGES + 2 + a); };
+  const uint32_t tmem_slot = bar_base + 8u * (2 * STAGES + 4);
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const uint32_t rank = cluster_ctarank();
+  const bool leader = rank == 0;
+  const int pair = blockIdx.x >> 1, n_pairs = gridDim.x >> 1;
+  const int m_tiles = (M + 2 * TC_BM - 1) / (2 * TC_BM), n_tiles = (N + TC2_BN - 1) / TC2_BN;
+  const int num_tiles = m_tiles * n_tiles;
+  const int k_blocks = (K + TC_BK - 1) / TC_BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < STAGES; ++s) { mbar_init(full_bar(s), 1); mbar_init(empty_bar(s), 1); }
+    for (int a = 0; a < 2; ++a) { mbar_init(tfull_bar(a), 1); mbar_init(tempty_bar(a), 2 * 4 * NSETS); }   // one arrival per epilogue warp of the pair
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  cluster_sync_all();          // both CTAs' barriers initialised and TMEM allocated before anyone signals across the pair
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================= TMA producer (both CTAs: own halves of A and W) =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+        const int m0 = (tile / n_tiles) * (2 * TC_BM) + (int)rank * TC_BM;
+        const int n0 = (tile % n_tiles) * TC2_BN + (int)rank * TC2_BHALF;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(empty_bar(stage), phase ^ 1u);
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint32_t sb = sa + Cfg::A_BYTES;
+          const uint32_t lbar = full_bar(stage) & TC_PEER_MASK;
+          if (leader) mbar_arrive_expect_tx(full_bar(stage), 2 * Cfg::STAGE_BYTES);
+          tma_load_2d_pair(sa, &tmA, kb * TC_BK, m0, lbar);
+          tma_load_2d_pair(sb, &tmW, kb * TC_BK, n0, lbar);
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer (leader CTA only) =================
+    if (leader && lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      int acc = 0; uint32_t acc_phase = 0;
+      for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+        mbar_wait(tempty_bar(acc), acc_phase ^ 1u);
+        tc_fence_after();
+        const uint32_t d_tmem = tmem_base + (uint32_t)(acc * Cfg::ACC_STRIDE);
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(full_bar(stage), phase);
+          tc_fence_after();
+          const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
+          const uint64_t da = make_smem_desc_sw128(sa);
+          const uint64_t db = make_smem_desc_sw128(sa + Cfg::A_BYTES);
+#pragma unroll
+          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+            tc_mma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit_pair(empty_bar(stage));
+          if (kb == k_blocks - 1) tc_commit_pair(tfull_bar(acc));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        }
+        if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+      }
+    }
+    __syncwarp();
+  } else {
+    // ================= epilogue (both CTAs: own 128 rows) =================
+    const int q = warp & 3;
+    const int set = (warp - 2) >> 2;
+    const bool store_thread = (lane == 0) && (((warp - 2) & 3) == 0);
+    int acc = 0; uint32_t acc_phase = 0;
+    for (int tile = pair; tile < num_tiles; tile += n_pairs) {
+      const int m0 = (tile / n_tiles) * (2 * TC_BM) + (int)rank * TC_BM, n0 = (tile % n_tiles) * TC2_BN;
+      mbar_wait(tfull_bar(acc), acc_phase);
+      tc_fence_after();
+      tc_epilogue_tile<TC2_BN, NSETS>(ep, &tmC, tma_store, tmem_base + (uint32_t)(acc * Cfg::ACC_STRIDE), m0, n0, M, N,
+                                      q, set, lane, store_thread, cstage_base);
+      tc_fence_before();
+      __syncwarp();
+      if (lane == 0) mbar_arrive_leader(tempty_bar(acc));
+      if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
+    }
+    if (tma_store && store_thread) tma_store_wait_read<0>();
+  }
+
+  tc_fence_before();
+  cluster_sync_all();          // the leader's MMAs read the peer's shared memory and both TMEMs: leave together
+  tc_fence_after();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
   }
 }
 
@@ -458,6 +639,30 @@ static int launch_bn(const CUtensorMap& tmA, const void* W, int64_t ldw, int ab_
   return check_launch("aum_gemm_tn(tcgen05)");
 }
 
+template <int NSETS>
+static int launch_pair(const CUtensorMap& tmA, const void* W, int64_t ldw, int ab_dt, const EpiParams& ep,
+                       int M, int N, int K, cudaStream_t st) {
+  using Cfg = Tc2Cfg<NSETS>;
+  CUtensorMap tmW, tmC;
+  if (int rc = make_tmap(&tmW, W, N, K, ldw, TC2_BHALF, ab_dt)) return rc;
+  if (int rc = make_tmap_out(&tmC, ep.C, M, N, ep.ldc, ep.c_dt)) return rc;
+  static bool attr_set = false;
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(gemm_tcgen05_pair_kernel<NSETS>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("aum_gemm_tn: cudaFuncSetAttribute(pair, smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
+    attr_set = true;
+  }
+  const int fmt = (ab_dt == AUM_F16) ? 0 : 1;
+  const uint32_t idesc = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10)
+                       | ((uint32_t)(TC2_BN >> 3) << 17)          // N >> 3
+                       | ((uint32_t)((2 * TC_BM) >> 4) << 24);    // M >> 4 (256: the pair)
+  const int tiles = ceil_div(M, 2 * TC_BM) * ceil_div(N, TC2_BN);
+  int pairs = g_sm_count / 2;
+  if (tiles < pairs) pairs = tiles;
+  gemm_tcgen05_pair_kernel<NSETS><<<2 * pairs, Cfg::THREADS, Cfg::SMEM_BYTES, st>>>(tmA, tmW, tmC, 1, ep, M, N, K, idesc);
+  return check_launch("aum_gemm_tn(tcgen05 pair)");
+}
+
 int launch_gemm_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, int ab_dt, const EpiParams& ep,
                         int M, int N, int K, cudaStream_t st) {
   if (g_sm_count == 0) {
@@ -467,6 +672,13 @@ int launch_gemm_tcgen05(const void* A, int64_t lda, const void* W, int64_t ldw, 
   }
   CUtensorMap tmA;
   if (int rc = make_tmap(&tmA, A, M, K, lda, TC_BM, ab_dt)) return rc;
+  // MMA-bound shapes with a single TMA-storable output: the CTA-pair kernel (AUM_GEMM_PAIR=0 turns it off)
+  static int use_pair = -1;
+  if (use_pair < 0) { const char* e = getenv("AUM_GEMM_PAIR"); use_pair = (e && atoi(e) == 0) ? 0 : 1; }
+  // (with an activation epilogue - in_proj's SiLU(z) - the pair kernel measured no faster than the single-CTA one:
+  //  0.125 vs 0.126 ms, against 0.116 vs 0.124 ms for the bare GEMM; 16 epilogue warps did not change that)
+  if (use_pair && N >= 512 && K >= 256 && M >= 1024 && ep.C2 == nullptr && ep.vec_ok && ep.act == AUM_ACT_NONE)
+    return launch_pair<2>(tmA, W, ldw, ab_dt, ep, M, N, K, st);
   // Tile-N choice: the widest tile that does not waste more than ~12 % of the MMA on column padding.
   if (N <= 32)  return launch_bn<32>(tmA, W, ldw, ab_dt, ep, M, N, K, st);
   if (N <= 64)  return launch_bn<64>(tmA, W, ldw, ab_dt, ep, M, N, K, st);

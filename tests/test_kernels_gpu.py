@@ -104,6 +104,8 @@ def test_gemm_simt_fp32(M, N, K):
     torch.testing.assert_close(out.cpu(), _gemm_ref(a, w, bias, rs, True), rtol=1e-5, atol=1e-5)
 
 
+# shapes with N >= 512, K >= 256, M >= 1024 and no activation run the CTA-pair (cta_group::2) kernel, the others the
+# single-CTA one; AUM_GEMM_PAIR=0 forces the latter everywhere
 TC_SHAPES = [
     (300, 256, 128),      # M tail, BN=256
     (128, 64, 64),        # single tile, single k-block
@@ -114,6 +116,8 @@ TC_SHAPES = [
     (640, 80, 1536),      # x_proj: N=80 -> BN=96
     (100, 24, 200),       # small N -> BN=32, K tail
     (19000, 512, 256),    # more tiles than SMs (persistent loop, both TMEM buffers, phase flips)
+    (1100, 600, 320),     # CTA-pair kernel: M, N and K tails (600 = 2 x 256 + 88, 1100 = 4 x 256 + 76)
+    (32832, 768, 1536),   # out_proj at config-2 size: 387 pair tiles over 74 pairs
 ]
 
 
