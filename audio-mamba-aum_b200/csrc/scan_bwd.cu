@@ -295,7 +295,9 @@ dbc_reduce_kernel(const float* __restrict__ ws, float* __restrict__ dBC, int64_t
 }  // namespace aum
 
 extern "C" int64_t aum_selective_scan_bwd_dbc_ws_floats(int batch, int L, int D) {
-  return (int64_t)aum::ceil_div(D, aum::SB_CH) * aum::SB_WARPS * (int64_t)batch * L * 32;
+  // sized for the wider of the two kernels' warp counts (generic: 2 per 64 channels, TMA-streamed: 4 per 128)
+  const int parts_generic = aum::ceil_div(D, aum::SB_CH) * aum::SB_WARPS, parts_tma = aum::ceil_div(D, 128) * 4;
+  return (int64_t)(parts_generic > parts_tma ? parts_generic : parts_tma) * (int64_t)batch * L * 32;
 }
 
 extern "C" int64_t aum_selective_scan_bwd_workspace_floats(int batch, int L, int D) {
@@ -366,7 +368,8 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
     if (int rc = check_launch("aum_selective_scan_bwd")) return rc;
   }
   const int64_t rows = (int64_t)batch * L;
-  const int nparts = ceil_div(D, SB_CH) * SB_WARPS;
+  // one workspace slice per warp of the kernel that ran: 2 per 64-channel CTA (generic), 4 per 128-channel CTA (TMA)
+  const int nparts = fast < 0 ? ceil_div(D, SB_CH) * SB_WARPS : ceil_div(D, 128) * 4;
   for (int g = 0; g < p.ndirs; ++g)
     dbc_reduce_kernel<<<(unsigned)ceil_div64(rows * 32, 256), 256, 0, st>>>(p.dir[g].dbc_ws, p.dir[g].dBC, p.dir[g].ld_dbc, rows, nparts);
   return check_launch("aum_selective_scan_bwd(dbc reduce)");

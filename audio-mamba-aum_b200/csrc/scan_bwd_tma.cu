@@ -1,18 +1,20 @@
 // Selective scan backward — TMA-streamed kernel (the production path; math and reference citations: scan_bwd.cu).
 //
 // What changes against the generic kernel is how operands move and how the two directions are combined:
-//   * grid = (ceil(D/64), batch, directions): a CTA owns 64 channels of one sequence in ONE time direction (one
+//   * grid = (ceil(D/128), batch, directions): a CTA owns 128 channels of one sequence in ONE time direction (one
 //     thread per channel, the 16 states as 8 packed fp32x2 pairs).  The directions no longer meet inside a CTA:
 //     where du / ddelta are shared (Fo-Bi) both directions red.global.add into buffers the entry point zeroes
 //     first (two commutative fp32 additions per element: deterministic); dz / out_z are written by direction 0.
 //   * per 8-step checkpoint chunk one elected thread issues bulk tensor copies into a 2-stage ring: the
-//     checkpoint tile (16 x 64 fp32, state before the chunk, left by the forward kernel), delta, u, dout, z and
-//     (direction 0) y_pre tiles (8 x 64) and the packed [B|C] rows; all complete on the stage's mbarrier.  The
+//     checkpoint tile (16 x 128 fp32, state before the chunk, left by the forward kernel), delta, u, dout, z and
+//     (direction 0) y_pre tiles (8 x 128) and the packed [B|C] rows; all complete on the stage's mbarrier.  The
 //     loads of chunk c-1 are in flight while chunk c is processed, so no thread ever waits on a global load.
-//   * the chunk's state history lives in shared memory as [slot][n/4][ch][4]: one conflict-free 16-byte store
-//     per four states in the replay, one 16-byte load in the reverse-time walk.
-//   * shared memory (32 KB of history + 2 x 11 KB of stages at 16-bit activations) bounds residency at four CTAs
-//     = eight warps per SM, which is why nothing here may stall on memory.
+//   * the chunk's state history (8 slots x 16 states per channel) lives in TENSOR MEMORY, which this kernel has no
+//     other use for: thread = TMEM lane (the CTA's four warps are the four lane quarters), slot j = columns
+//     [16 j, 16 j + 16) of the CTA's 128-column allocation; one tcgen05.st (32x32b.x16) per replayed step, one
+//     tcgen05.ld per reverse-time step.  In shared memory the history cost 512 B per thread and bounded residency at
+//     8 warps per SM (the kernel is issue-bound: 446 instructions per warp-step at 48 % issue utilisation with 7
+//     resident warps); with only the 2 x 21 KB stages left the register file is the limit: 3 CTAs = 12 warps.
 // Eligibility (launch_scan_bwd_tma): d_state == 16, forward checkpoints present, packed fp32 [B|C] rows,
 // 16-byte aligned bases and row pitches.  Anything else runs scan_bwd.cu.
 #include <cuda.h>
@@ -22,9 +24,11 @@
 
 namespace aum {
 
-constexpr int BT_CH = 64;     // channels per CTA
+constexpr int BT_CH = 128;    // channels per CTA = TMEM lanes
+
 constexpr int BT_TT = 8;      // steps per checkpoint chunk (== SCAN_CK)
 static_assert(BT_TT == SCAN_CK, "chunk length must match the forward kernels' checkpoint interval");
+constexpr int BT_TMEM_COLS = BT_TT * SCAN_NS;   // 128 columns: 8 history slots x 16 states (power of two >= 32)
 
 template <typename T> struct BwdLayout {
   static constexpr int CK_BYTES = SCAN_NS * BT_CH * 4;             // checkpoint tile [n][ch]
@@ -34,9 +38,7 @@ template <typename T> struct BwdLayout {
   static constexpr int OFF_CK = 0, OFF_D = OFF_CK + CK_BYTES, OFF_BC = OFF_D + D_BYTES, OFF_U = OFF_BC + BC_BYTES;
   static constexpr int OFF_G = OFF_U + A_BYTES, OFF_Z = OFF_G + A_BYTES, OFF_Y = OFF_Z + A_BYTES;
   static constexpr int STAGE_BYTES = OFF_Y + A_BYTES;
-  static constexpr int SLOT_BYTES = SCAN_NS * BT_CH * 4;           // one history slot [n/4][ch][4]
-  static constexpr int HIST_BYTES = BT_TT * SLOT_BYTES;
-  static constexpr int SMEM_BYTES = HIST_BYTES + 2 * STAGE_BYTES + 128 /*align slack*/ + 64 /*mbarriers*/;
+  static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + 128 /*align slack*/ + 64 /*mbarriers, TMEM base slot*/;
 };
 
 struct ScanBwdMaps { CUtensorMap u[2], d[2], ck[2], g, z, y; };
@@ -50,11 +52,24 @@ __device__ __forceinline__ float ldsf(uint32_t a) { float v; asm volatile("ld.sh
 __device__ __forceinline__ float4 ldsf4(uint32_t a) {
   float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
 }
-__device__ __forceinline__ void lds_pair2(uint32_t a, f32x2& p0, f32x2& p1) {
-  asm volatile("ld.shared.v2.b64 {%0, %1}, [%2];" : "=l"(p0), "=l"(p1) : "r"(a));
+// state history in tensor memory: 16 consecutive columns of this thread's lane = the 16 states of one slot
+__device__ __forceinline__ void tmem_st16(uint32_t taddr, const f32x2 (&h)[SCAN_NS / 2]) {
+  uint32_t r[16];
+#pragma unroll
+  for (int k = 0; k < 8; ++k) { float lo, hi; upk2(h[k], lo, hi); r[2 * k] = __float_as_uint(lo); r[2 * k + 1] = __float_as_uint(hi); }
+  asm volatile("tcgen05.st.sync.aligned.32x32b.x16.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16};"
+               ::"r"(taddr), "r"(r[0]), "r"(r[1]), "r"(r[2]), "r"(r[3]), "r"(r[4]), "r"(r[5]), "r"(r[6]), "r"(r[7]),
+                 "r"(r[8]), "r"(r[9]), "r"(r[10]), "r"(r[11]), "r"(r[12]), "r"(r[13]), "r"(r[14]), "r"(r[15]) : "memory");
 }
-__device__ __forceinline__ void sts_pair2(uint32_t a, f32x2 p0, f32x2 p1) {
-  asm volatile("st.shared.v2.b64 [%0], {%1, %2};" ::"r"(a), "l"(p0), "l"(p1) : "memory");
+__device__ __forceinline__ void tmem_ld16(uint32_t taddr, f32x2 (&h)[SCAN_NS / 2]) {
+  uint32_t r[16];
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+               : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]),
+                 "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+               : "r"(taddr) : "memory");
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+  for (int k = 0; k < 8; ++k) h[k] = pk2(__uint_as_float(r[2 * k]), __uint_as_float(r[2 * k + 1]));
 }
 template <typename T> __device__ __forceinline__ float ldst(uint32_t a);
 template <> __device__ __forceinline__ float ldst<float>(uint32_t a) { return ldsf(a); }
@@ -68,8 +83,7 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-// Replay one forward step: h <- exp(dl A) h + dl u B; the new state goes to history slot `slot` (this thread's
-// 16-byte column inside each of the slot's four 1 KB planes).
+// Replay one forward step: h <- exp(dl A) h + dl u B; the new state goes to history slot `slot` (a TMEM address).
 __device__ __forceinline__ void replay_step(float u, float dl, uint32_t a_bc, uint32_t slot,
                                             f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2]) {
   const float du_ = dl * u;
@@ -81,19 +95,19 @@ __device__ __forceinline__ void replay_step(float u, float dl, uint32_t a_bc, ui
     upk2(mul2(dl2, a2[2 * q]), e0, e1); upk2(mul2(dl2, a2[2 * q + 1]), e2, e3);
     h[2 * q] = fma2(pk2(ex2_approx(e0), ex2_approx(e1)), h[2 * q], mul2(du2, pk2(Bv.x, Bv.y)));
     h[2 * q + 1] = fma2(pk2(ex2_approx(e2), ex2_approx(e3)), h[2 * q + 1], mul2(du2, pk2(Bv.z, Bv.w)));
-    sts_pair2(slot + (uint32_t)q * (BT_CH * 16), h[2 * q], h[2 * q + 1]);
   }
+  tmem_st16(slot, h);
 }
 
 template <typename T>
-__global__ void __launch_bounds__(BT_CH)
+__global__ void __launch_bounds__(BT_CH, 3)
 scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParams p) {
   using BL = BwdLayout<T>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (s_u32(smem_raw) + 127u) & ~127u;
-  const uint32_t hist = smem0;
-  const uint32_t stages = smem0 + BL::HIST_BYTES;
+  const uint32_t stages = smem0;
   const uint32_t bars = stages + 2 * BL::STAGE_BYTES;
+  const uint32_t tmem_slot = bars + 16;
 
   const int g = blockIdx.z;
   const ScanBwdDirDev& d = p.dir[g];
@@ -118,7 +132,15 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
   }
+  if (tig < 32) {      // warp 0 owns the TMEM allocation (128 columns: up to four CTAs per SM could hold one)
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(BT_TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
   __syncthreads();
+  asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
 
   // checkpoint chunking (identical to the forward kernels'): chunk 0 = [0, first), chunk c = [first + 8(c-1), +8)
   const int first = min(scan_ck_first(L, bidir, rev), L);
@@ -181,7 +203,7 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
   const int sbc = rev ? -(SCAN_ROW * 4) : (SCAN_ROW * 4);
   const int rstep = rev ? -1 : 1;
   const int part = blockIdx.x * (BT_CH / 32) + (tig >> 5);     // this warp's slice of the dB|dC partial workspace
-  const uint32_t hcol = hist + (uint32_t)tig * 16u;            // this thread's 16-byte column in plane 0 of slot 0
+  const uint32_t hcol = tmem_base + ((uint32_t)((tig >> 5) * 32) << 16);   // slot 0 of this warp's TMEM lane quarter
   const bool spg_on = p.softplus_grad != 0;
 
   for (int q = 0; q < nchunks; ++q) {
@@ -203,16 +225,15 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
       const uint32_t ck = st + BL::OFF_CK + (uint32_t)tig * 4u;
 #pragma unroll
       for (int k = 0; k < SCAN_NS / 2; ++k) h[k] = pk2(ldsf(ck + (uint32_t)(2 * k) * (BT_CH * 4)), ldsf(ck + (uint32_t)(2 * k + 1) * (BT_CH * 4)));
-#pragma unroll
-      for (int qq = 0; qq < 4; ++qq) sts_pair2(hcol + (uint32_t)qq * (BT_CH * 16), h[2 * qq], h[2 * qq + 1]);
-      uint32_t a_u = t_u, a_d = t_d, a_bc = t_bc, slot = hcol + BL::SLOT_BYTES;
+      tmem_st16(hcol, h);
+      uint32_t a_u = t_u, a_d = t_d, a_bc = t_bc, slot = hcol + SCAN_NS;
 #pragma unroll 1
       for (int j = 0; j < ns - 1; ++j) {
         replay_step(ldst<T>(a_u), ldsf(a_d), a_bc, slot, h, a2);
-        a_u += s16; a_d += s32; a_bc += sbc; slot += BL::SLOT_BYTES;
+        a_u += s16; a_d += s32; a_bc += sbc; slot += SCAN_NS;
       }
+      asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // the history is read back by the same thread below
     }
-    // (each thread only reads back its own column of the history: no barrier needed)
 
     // ---- reverse-time recurrence over the chunk, j = ns-1 .. 0
     {
@@ -221,7 +242,7 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
       uint32_t a_g = st + BL::OFF_G + e16 + (uint32_t)(jl * s16);
       uint32_t a_z = st + BL::OFF_Z + e16 + (uint32_t)(jl * s16);
       uint32_t a_y = st + BL::OFF_Y + e16 + (uint32_t)(jl * s16);
-      uint32_t slot = hcol + (uint32_t)jl * BL::SLOT_BYTES;
+      uint32_t slot = hcol + (uint32_t)jl * SCAN_NS;
       const int64_t r_last = (int64_t)row0 + (rev ? (L - 1 - (s0 + jl)) : (s0 + jl));      // global row of step s0+jl
       float* dup = d.du + r_last * d.ld_du + ch;
       float* ddp = d.ddelta + r_last * d.ld_dd + ch;
@@ -243,12 +264,13 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
         const float dlu = dl * u;
         const f32x2 dl2 = pk2(dl, dl), dy2 = pk2(dy, dy), dlu2 = pk2(dlu, dlu);
         f32x2 sB2 = pk2(0.f, 0.f), dd2 = pk2(0.f, 0.f);
+        f32x2 hprev[SCAN_NS / 2];
+        tmem_ld16(slot, hprev);                                                 // h_{s-1}, all 16 states
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
           const float4 Bv = ldsf4(a_bc + 16u * qq);
           const float4 Cv = ldsf4(a_bc + 16u * (4 + qq));
-          f32x2 hp[2];
-          lds_pair2(slot + (uint32_t)qq * (BT_CH * 16), hp[0], hp[1]);          // h_{s-1}, states 4qq .. 4qq+3
+          const f32x2 hp[2] = {hprev[2 * qq], hprev[2 * qq + 1]};
 #pragma unroll
           for (int hq = 0; hq < 2; ++hq) {
             const int k = 2 * qq + hq;                              // state pair (2k, 2k+1)
@@ -291,7 +313,7 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
             if (ozp) *ozp = from_f<T>(scale * yp * sz);
           }
         }
-        a_u -= s16; a_g -= s16; a_z -= s16; a_y -= s16; a_d -= s32; a_bc -= sbc; slot -= BL::SLOT_BYTES;
+        a_u -= s16; a_g -= s16; a_z -= s16; a_y -= s16; a_d -= s32; a_bc -= sbc; slot -= SCAN_NS;
         dup += gdu; ddp += gdd; wsp += gws;
         if (dzp) dzp += gdz;
         if (ozp) ozp += goz;
@@ -312,6 +334,9 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
     }
     if (d.dD) atomicAdd(d.dD + ch, dD_acc);
   }
+  asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+  __syncthreads();
+  if (tig < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BT_TMEM_COLS) : "memory");
 }
 
 template <typename T>
