@@ -293,3 +293,16 @@ def add_rmsnorm_bwd(dy: torch.Tensor, dres_out: Optional[torch.Tensor], r: torch
                                      L.ptr(dx), dim, L.ptr(dri), dim, L.ptr(dweight), rows, dim, L.stream())
     L.check(rc, "aum_add_rmsnorm_bwd")
     return dx, dri
+
+
+def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, *, lr: float, betas=(0.9, 0.999),
+              eps: float = 1e-8, weight_decay: float = 0.0, step: int = 1, grad_scale: float = 1.0) -> None:
+    """In-place torch.optim.Adam update of the flat fp32 buffer p from its flat gradient g and moments m, v
+    (aum_adam_step; reference: src/traintest.py:32-34,169)."""
+    L.require_cuda(p, g, m, v)
+    for t in (p, g, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != p.numel():
+            raise L.AumError("adam_step: p, g, m, v must be contiguous fp32 buffers of one size")
+    rc = L.lib().aum_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), float(betas[0]),
+                               float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale), L.stream())
+    L.check(rc, "aum_adam_step")

@@ -194,6 +194,18 @@ AUM_API int aum_add_rmsnorm_bwd(const void* dy, int64_t ld_dy, int dy_dtype,
                         float* dweight, int rows, int dim, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Fused Adam step over one flat fp32 buffer (the caller of the training path).
+ *   replaces torch.optim.Adam(trainables, lr, weight_decay=5e-7, betas=(0.95, 0.999)).step()
+ *   (src/traintest.py:32-34, :169) — same update rule (L2 weight decay folded into the gradient, bias-corrected
+ *   moments, eps added to sqrt(v_hat)), one pass over p, g, m, v (n floats each, 16-byte aligned) instead of the
+ *   multi-tensor implementation's ~10.  step counts from 1.  grad_scale multiplies g first (1/world_size after the
+ *   SUM all-reduce of the flat gradient buffer).  p, m, v are updated in place; g is not modified.
+ * ------------------------------------------------------------------------------------------- */
+AUM_API int aum_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
+                  float lr, float beta1, float beta2, float eps, float weight_decay,
+                  int step, float grad_scale, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Layout adapters for the reference's channel-major (batch, C, L) tensors:
  *   dst[b, j, i] = src[b, i, j]  for a (batch, R, C) -> (batch, C, R) transpose with explicit strides
  *   (elements): src element (b,i,j) at b*src_bs + i*src_ld + j; dst element (b,j,i) at b*dst_bs + j*dst_ld + i.

@@ -30,7 +30,12 @@ def _worker(rank, world, port, ret):
     red.reduce()
     gathered = [torch.zeros_like(torch.cat([g.flatten() for g in local])) for _ in range(world)]
     dist.all_gather(gathered, torch.cat([g.flatten() for g in local]))
-    torch.testing.assert_close(red.flat, torch.stack(gathered).mean(0))
+    # (every tensor starts on an aligned offset of the flat buffer; the padding in between stays zero)
+    mean = torch.stack(gathered).mean(0)
+    packed = torch.cat([red.flat[o:o + p.numel()] for p, o in zip(red.params, red.offsets)])
+    torch.testing.assert_close(packed, mean)
+    assert all(o % D.FlatGradReducer.ALIGN == 0 for o in red.offsets)
+    assert float(red.flat.abs().sum()) == float(packed.abs().sum())
     red.zero()
     assert all((p.grad == 0).all() for p in lin.parameters())
     dist.destroy_process_group()

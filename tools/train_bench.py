@@ -24,6 +24,7 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--depth", type=int, default=24)
     ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam instead of the fused flat-buffer step")
     args = ap.parse_args()
     rank, local = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -40,7 +41,10 @@ def main():
             blk.mixer.A_log.add_(0.1 * torch.randn(blk.mixer.A_log.shape, generator=g).to(dev))
             blk.mixer.A_b_log.add_(0.1 * torch.randn(blk.mixer.A_b_log.shape, generator=g).to(dev))
     red = D.FlatGradReducer(model.parameters())
-    opt = torch.optim.Adam(model.parameters(), lr=1e-5, betas=(0.95, 0.999), weight_decay=5e-7)
+    if args.torch_adam:
+        opt = torch.optim.Adam(model.parameters(), lr=1e-5, betas=(0.95, 0.999), weight_decay=5e-7)
+    else:
+        opt = D.FlatAdam(red, lr=1e-5, betas=(0.95, 0.999), weight_decay=5e-7)
     x = (0.5 * torch.randn(args.batch, 1024, 128, generator=g)).to(dev)
     y = (torch.rand(args.batch, 309, generator=g) > 0.97).float().to(dev)
     ar_ms = []
