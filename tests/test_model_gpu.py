@@ -54,3 +54,55 @@ def test_aum_base_logits_vs_oracle_full_depth():
     print(f"AuM-Base logits: max|ref|={scale:.4f} rel-to-scale err fp32={e32:.2e} fp16={e16:.2e} bf16={eb16:.2e}")
     assert e32 < 1e-4 and e16 < 1e-2 and eb16 < 8e-2
     assert (o16.argmax(-1) == ref.argmax(-1)).all()
+
+
+def test_aum_small_bibi_logits_vs_oracle_full_depth():
+    """BASELINE config 4 model (AuM-Small Bi-Bi: embed 384, depth 24, bimamba v2, if_devide_out) on 1 clip of
+    128x1024 mel, fp32 tier against the oracle (rtol 1e-3), 16-bit tiers against the logit scale."""
+    from aum_b200.audio_mamba import AudioMamba
+    sd = O.make_audio_mamba_state(384, 24, num_classes=527, bimamba_type="v2", seed=31, perturb_A=0.1)
+    x = O.make_spectrogram(1, (128, 1024), seed=32)
+    ref = O.audio_mamba_forward_oracle(sd, x, depth=24, bimamba_type="v2")
+    m = AudioMamba(embed_dim=384, depth=24, num_classes=527, bimamba_type="v2").to(DEV).eval()
+    m.load_state_dict(sd, strict=True)
+    with torch.no_grad():
+        out = m(x.to(DEV)).cpu()
+    scale = ref.abs().max().item()
+    torch.testing.assert_close(out, ref, rtol=1e-3, atol=1e-3 * scale)
+    m.act_dtype = torch.float16
+    with torch.no_grad():
+        o16 = m(x.to(DEV)).cpu()
+    assert (o16 - ref).abs().max().item() / scale < 1e-2
+    assert (o16.argmax(-1) == ref.argmax(-1)).all()
+
+
+@pytest.mark.parametrize("bt", ["v1", "v2"])
+def test_cuda_graph_and_sequence_groups_match_eager(bt):
+    """The path bench.py times — CUDA-graph replay with the batch split into two sequence groups on two streams,
+    input taken from a pinned HOST buffer — returns what the plain eager forward returns (same kernels, same sizes
+    per group: bit-identical), also with the groups serialised on one stream (bench.py's per-kernel timing pass)."""
+    from aum_b200.audio_mamba import AudioMamba
+    torch.manual_seed(5)
+    kw = dict(embed_dim=192, depth=3, num_classes=35, spectrogram_size=(128, 256), bimamba_type=bt, act_dtype=torch.float16)
+    plain = AudioMamba(**kw).to(DEV).eval()
+    fast = AudioMamba(**kw, use_cuda_graph=True, micro_batches=2).to(DEV).eval()
+    fast.load_state_dict(plain.state_dict(), strict=True)
+    x = 0.5 * torch.randn(6, 256, 128)
+    with torch.no_grad():
+        halves = torch.cat([plain(xc.to(DEV)) for xc in x.chunk(2, dim=0)], dim=0)     # eager, group by group
+        whole = plain(x.to(DEV))                                                     # eager, one group of 6
+        for _ in range(3):                                                           # capture, then two replays
+            g_out = fast(x.pin_memory())
+        fast.serialize_groups = True
+        fast.use_cuda_graph = False
+        s_out = fast(x.to(DEV))
+    assert torch.equal(g_out, halves)
+    assert torch.equal(s_out, halves)
+    torch.testing.assert_close(g_out, whole, rtol=2e-3, atol=2e-3)      # other batch grouping: same values up to fp16 tiling
+    # a weight update invalidates the captured graph (derived 16-bit weights are rebuilt)
+    with torch.no_grad():
+        fast.use_cuda_graph = True
+        fast.serialize_groups = False
+        fast.head.weight.mul_(2.0); fast.head.bias.mul_(2.0)
+        g2 = fast(x.pin_memory())
+    torch.testing.assert_close(g2, 2.0 * g_out, rtol=1e-5, atol=1e-5)
