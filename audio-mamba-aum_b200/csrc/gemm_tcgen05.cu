@@ -129,6 +129,15 @@ __device__ __forceinline__ void tc_ld_32x32b_x32(uint32_t taddr, uint32_t (&r)[3
         "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
       : "r"(taddr) : "memory");
 }
+// One lane of a CONVERGED warp.  The MMA issuer runs its loop with the whole warp converged and elects a lane only
+// around the tcgen05 instructions: inside an `if (lane == 0)` region the compiler wraps every uniform-datapath
+// instruction (UTCHMMA, UTCBAR) in its own ELECT / BRA.U.ANY loop - ~10 instructions per MMA on the one thread whose
+// issue rate bounds the tensor pipe.
+__device__ __forceinline__ bool elect_one() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
 __device__ __forceinline__ void tc_wait_ld() { asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory"); }
 
 // Shared-memory matrix descriptor: K-major operand, 128-byte swizzle, rows of 128 B, 8-row groups 1024 B apart
@@ -322,8 +331,8 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
-    if (lane == 0) {
+    // ================= MMA issuer (whole warp converged, one elected lane issues) =================
+    {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = blockIdx.x; tile < num_tiles; tile += gridDim.x) {
@@ -337,19 +346,21 @@ gemm_tcgen05_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_consta
           const uint32_t sb = sa + Cfg::A_BYTES;
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sb);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
-            // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
-            tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k) {
+              // advance 16 elements = 32 bytes along K inside the 128-byte swizzle row: +2 in 16-byte units
+              tc_mma_f16(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            }
+            tc_commit(empty_bar(stage));                    // smem stage reusable once these MMAs retire
+            if (kb == k_blocks - 1) tc_commit(tfull_bar(acc));   // accumulator complete
           }
-          tc_commit(empty_bar(stage));                    // smem stage reusable once these MMAs retire
-          if (kb == k_blocks - 1) tc_commit(tfull_bar(acc));   // accumulator complete
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
       }
     }
-    __syncwarp();
   } else {
     // ================= epilogue warps (2..): NSETS independent sets of 4 warps =================
     // Each set covers all 128 accumulator rows (one warp per TMEM lane quarter) and takes every other
@@ -496,8 +507,8 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer (leader CTA only) =================
-    if (leader && lane == 0) {
+    // ================= MMA issuer (leader CTA only; whole warp converged, one elected lane issues) =================
+    if (leader) {
       int stage = 0; uint32_t phase = 0;
       int acc = 0; uint32_t acc_phase = 0;
       for (int tile = pair; tile < num_tiles; tile += n_pairs) {
@@ -510,11 +521,14 @@ gemm_tcgen05_pair_kernel(const __grid_constant__ CUtensorMap tmA, const __grid_c
           const uint32_t sa = smem_base + stage * Cfg::STAGE_BYTES;
           const uint64_t da = make_smem_desc_sw128(sa);
           const uint64_t db = make_smem_desc_sw128(sa + Cfg::A_BYTES);
+          if (elect_one()) {
 #pragma unroll
-          for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
-            tc_mma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
-          tc_commit_pair(empty_bar(stage));
-          if (kb == k_blocks - 1) tc_commit_pair(tfull_bar(acc));
+            for (int k = 0; k < TC_BK / TC_UMMA_K; ++k)
+              tc_mma_f16_pair(d_tmem, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+            tc_commit_pair(empty_bar(stage));
+            if (kb == k_blocks - 1) tc_commit_pair(tfull_bar(acc));
+          }
+          __syncwarp();
           if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
         if (++acc == 2) { acc = 0; acc_phase ^= 1u; }
