@@ -100,23 +100,16 @@ class AudioMamba(nn.Module):
         """(B, T, F) spectrogram -> (B, N+1, Dm) fp32 token sequence with the cls token in the middle and
         the absolute position embedding added (mamba_models.py:510-541, tokenization.py:278-310,414-451)."""
         B, T_, F_ = x.shape
-        pf, pt = self.patch
         gf, gt = self.grid
-        # im2col of the stride-16 conv: token (f_blk, t_blk) <- pixels (kf, kt);  img[b,0,f,t] = x[b,t,f]
-        cols = x.view(B, gt, pt, gf, pf).permute(0, 3, 1, 4, 2).reshape(B * gf * gt, pf * pt)
-        cols = cols.to(act) if act != torch.float32 else cols.contiguous()
+        N = gf * gt
+        # im2col of the stride-16 conv (one kernel: gather + cast), the conv as one GEMM, cls / pos assembly (one kernel)
+        cols = ops.patchify(x.contiguous(), self.patch, act)
         w = mixer._cache.get(self.patch_embed.proj.weight, f"patchw:{act}",
                              lambda p: p.reshape(p.shape[0], -1).to(act).contiguous())
         tok = ops.gemm_tn(cols, w, bias=mixer._f32(self.patch_embed.proj.bias), out_dtype=torch.float32)
-        tok = tok.view(B, gf * gt, self.embed_dim)
-        N = gf * gt
-        tp = N // 2
-        pe = self.pos_embed.pos_embed          # slot 0 belongs to the cls token
-        hidden = torch.empty((B, N + 1, self.embed_dim), device=x.device, dtype=torch.float32)
-        torch.add(tok[:, :tp], pe[:, 1:tp + 1], out=hidden[:, :tp])
-        hidden[:, tp] = (self.cls_token[0, 0] + pe[0, 0])
-        torch.add(tok[:, tp:], pe[:, tp + 1:], out=hidden[:, tp + 1:])
-        return hidden
+        pos = mixer._cache.get(self.pos_embed.pos_embed, "pos:f32", lambda p: p.float().reshape(N + 1, -1).contiguous())
+        cls = mixer._cache.get(self.cls_token, "cls:f32", lambda p: p.float().reshape(-1).contiguous())
+        return ops.assemble_tokens(tok.view(B, N, self.embed_dim), pos, cls)
 
     def _forward_train(self, x: torch.Tensor, return_features: bool) -> torch.Tensor:
         """Autograd path (training): same data flow, differentiable glue.  The mixer and add+RMSNorm go through the

@@ -306,3 +306,35 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
     rc = L.lib().aum_adam_step(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), float(betas[0]),
                                float(betas[1]), float(eps), float(weight_decay), int(step), float(grad_scale), L.stream())
     L.check(rc, "aum_adam_step")
+
+
+def patchify(x: torch.Tensor, patch, out_dtype: torch.dtype) -> torch.Tensor:
+    """(B, T, F) fp32 spectrogram -> (B * gf * gt, pf * pt) im2col rows of the stride == kernel patch conv
+    (aum_patchify; reference: tokenization.py:278-310 via mamba_models.py:510-515)."""
+    L.require_cuda(x)
+    if x.dtype != torch.float32 or not x.is_contiguous() or x.dim() != 3:
+        raise L.AumError("patchify: x must be a contiguous fp32 (B, T, F) tensor")
+    B, T_, F_ = x.shape
+    pf, pt = patch
+    if F_ % pf or T_ % pt or pt % 4:
+        raise L.AumError("patchify: patch must tile the spectrogram and pt must be a multiple of 4")
+    cols = torch.empty((B * (F_ // pf) * (T_ // pt), pf * pt), device=x.device, dtype=out_dtype)
+    rc = L.lib().aum_patchify(L.ptr(x), L.ptr(cols), B, T_, F_, pf, pt, L.dt(out_dtype), L.stream())
+    L.check(rc, "aum_patchify")
+    return cols
+
+
+def assemble_tokens(tok: torch.Tensor, pos: torch.Tensor, cls: torch.Tensor) -> torch.Tensor:
+    """tok (B, N, Dm) fp32, pos (N + 1, Dm) fp32 (slot 0 = cls), cls (Dm) fp32 -> hidden (B, N + 1, Dm) fp32 with the
+    cls token in the middle (aum_assemble_tokens; reference: mamba_models.py:525-541)."""
+    L.require_cuda(tok, pos, cls)
+    B, N, Dm = tok.shape
+    for t in (tok, pos, cls):
+        if t.dtype != torch.float32 or not t.is_contiguous():
+            raise L.AumError("assemble_tokens: contiguous fp32 tensors required")
+    if pos.numel() != (N + 1) * Dm or cls.numel() != Dm:
+        raise L.AumError("assemble_tokens: pos must be (N + 1, Dm) and cls (Dm)")
+    hidden = torch.empty((B, N + 1, Dm), device=tok.device, dtype=torch.float32)
+    rc = L.lib().aum_assemble_tokens(L.ptr(tok), L.ptr(pos), L.ptr(cls), L.ptr(hidden), B, N, Dm, L.stream())
+    L.check(rc, "aum_assemble_tokens")
+    return hidden

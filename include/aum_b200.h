@@ -194,6 +194,20 @@ AUM_API int aum_add_rmsnorm_bwd(const void* dy, int64_t ld_dy, int dy_dtype,
                         float* dweight, int rows, int dim, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Front end of the block stack: data movement either side of the patch-embed GEMM.
+ *   aum_patchify: x (batch, T, F) fp32 spectrogram -> im2col rows (batch * (F/pf) * (T/pt), pf * pt) in `dtype`, so that
+ *     FlexiPatchEmbed's stride == kernel conv2d (src/utilities/tokenization.py:278-310; img[b,0,f,t] = x[b,t,f],
+ *     src/models/mamba_models.py:510-515) is ONE aum_gemm_tn with the conv weight flattened to (Dm, pf * pt).
+ *     Row order = x.flatten(2).transpose(1, 2) (frequency block major); column = kf * pt + kt.  pt % 4 == 0.
+ *   aum_assemble_tokens: patch tokens (batch, N, Dm) fp32 -> hidden (batch, N + 1, Dm) fp32: cls token inserted at
+ *     index N / 2, absolute position embedding added (mamba_models.py:525-541; tokenization.py:414-451: slot 0 of
+ *     pos (N + 1, Dm) belongs to the cls token).  cls: (Dm).  Dm % 4 == 0, 16-byte aligned buffers.
+ * ------------------------------------------------------------------------------------------- */
+AUM_API int aum_patchify(const float* x, void* cols, int batch, int T, int F, int pf, int pt, int dtype, void* stream);
+AUM_API int aum_assemble_tokens(const float* tok, const float* pos, const float* cls, float* hidden,
+                        int batch, int N, int Dm, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Fused Adam step over one flat fp32 buffer (the caller of the training path).
  *   replaces torch.optim.Adam(trainables, lr, weight_decay=5e-7, betas=(0.95, 0.999)).step()
  *   (src/traintest.py:32-34, :169) — same update rule (L2 weight decay folded into the gradient, bias-corrected

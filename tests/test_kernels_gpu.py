@@ -333,3 +333,30 @@ def test_scan_192_channel_build():
                         "-k", "selective_scan_all_modes or length_sweep or properties_at_full_size"],
                        env=env, capture_output=True, text=True, timeout=900)
     assert r.returncode == 0, r.stdout[-2000:] + r.stderr[-2000:]
+
+
+@pytest.mark.parametrize("dt", DTYPES)
+def test_patchify_and_token_assembly(dt):
+    """Front end either side of the patch-embed GEMM against the reference formulation: conv2d(img, W, stride=patch)
+    .flatten(2).transpose(1, 2) == patchify(x) @ W.flatten(1)^T, and cls insertion + position embedding
+    (tokenization.py:278-310,414-451; mamba_models.py:510-541)."""
+    from aum_b200 import ops
+    g = gen(12)
+    B, T_, F_, Dm, p = 3, 64, 32, 24, (16, 16)
+    x = rnd((B, T_, F_), g)
+    w = rnd((Dm, 1, p[0], p[1]), g, scale=1 / 16)
+    cols = ops.patchify(x.to(DEV), p, dt)
+    ref_cols = x.view(B, T_ // p[1], p[1], F_ // p[0], p[0]).permute(0, 3, 1, 4, 2).reshape(-1, p[0] * p[1])
+    torch.testing.assert_close(cols.float().cpu(), ref_cols.to(dt).float(), rtol=0, atol=0)
+    img = x.unsqueeze(1).transpose(2, 3)                                  # (B, 1, F, T)
+    ref_tok = torch.nn.functional.conv2d(img, w, None, stride=p).flatten(2).transpose(1, 2)
+    tok = ref_cols @ w.reshape(Dm, -1).t()
+    torch.testing.assert_close(tok.view(B, -1, Dm), ref_tok, rtol=1e-5, atol=1e-5)
+    if dt == torch.float32:
+        N = ref_tok.shape[1]
+        pos, cls = rnd((1, N + 1, Dm), g), rnd((1, 1, Dm), g)
+        tp = N // 2
+        ref = torch.cat((ref_tok[:, :tp], cls.expand(B, -1, -1), ref_tok[:, tp:]), dim=1) \
+            + torch.cat((pos[:, 1:tp + 1], pos[:, :1], pos[:, tp + 1:]), dim=1)
+        out = ops.assemble_tokens(ref_tok.contiguous().to(DEV), pos[0].contiguous().to(DEV), cls.reshape(-1).to(DEV))
+        torch.testing.assert_close(out.cpu(), ref, rtol=0, atol=0)
