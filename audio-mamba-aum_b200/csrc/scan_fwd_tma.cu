@@ -22,6 +22,7 @@
 // bias/softplus left to apply, 16-byte aligned bases and row pitches.  Anything else runs scan_fwd.cu.
 #include <cuda.h>
 #include <stdlib.h>
+#include <type_traits>
 
 #include "scan_common.cuh"
 #include "tma.cuh"
@@ -318,7 +319,10 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   const bool save_ypre = ypre_off != 0;
   int s0 = 0, stage = 0, m = 0;
   uint32_t fpar = 0, ppar = 0;                     // bit s: parity of the next wait on full / partial barrier of stage s
-  for (int k = 0; k < ntiles; ++k) {
+  // Tiles at the edges of the two phases (tile 0, the first finalising tile with the phase barrier in front of it, the
+  // last tile) go through this general step; everything in between - all of them full 8-step tiles - through the
+  // specialised loops below.
+  auto generic_step = [&](const int k) {
     const bool fin = k >= n1t;
     const int nt = min(k == 0 ? first8 : ST_TT, (fin ? L : S1) - s0);
     const uint32_t st = ring + (uint32_t)stage * SL::STAGE_BYTES;
@@ -394,6 +398,73 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     s0 += nt;
     stage = (stage + 1 == NSTG) ? 0 : stage + 1;
     m = (m + 1 == NW) ? 0 : m + 1;
+  };
+
+  // Steady-state loop over full tiles [k, kend) of ONE phase: walk direction, phase and gate are compile-time, so the
+  // per-tile code between two tile bodies is the barrier handshake and the owner's TMA duties and nothing else (the
+  // general step spends ~100 instructions there on re-deriving which case it is in: 16 % of the kernel's stall samples).
+  int k = 0;
+  auto fast_range = [&](auto fin_c, auto part_c, auto zm_c, auto rev_c, auto ypre_c, const int kend) {
+    constexpr bool FIN = decltype(fin_c)::value, PART = decltype(part_c)::value, REV = decltype(rev_c)::value;
+    constexpr bool YPRE = decltype(ypre_c)::value;
+    constexpr int ZM = decltype(zm_c)::value;
+    for (; k < kend; ++k) {
+      const uint32_t st = ring + (uint32_t)stage * SL::STAGE_BYTES;
+      if (ckp != nullptr && active) {        // training: state before this tile (tiles == checkpoint chunks)
+        float* c = ckp + (int64_t)k * SCAN_NS * p.Dch;
+#pragma unroll
+        for (int i = 0; i < SCAN_NS / 2; ++i) {
+          float lo, hi; upk2(h[i], lo, hi);
+          c[(int64_t)(2 * i) * p.Dch] = lo; c[(int64_t)(2 * i + 1) * p.Dch] = hi;
+        }
+      }
+      sbar_wait(full_bar(stage), (fpar >> stage) & 1u);
+      fpar ^= 1u << stage;
+      if (PART) { sbar_wait(pfull_bar(stage), (ppar >> stage) & 1u); ppar ^= 1u << stage; }
+      T* pyp = nullptr;
+      if (YPRE) pyp = ob + (int64_t)(row0 + (REV ? (L - 1 - s0) : s0)) * ldo + ypre_off;
+      scan_tile_full<T, CH, FIN, PART, ZM, REV, YPRE>(st + o_u, st + o_d, st + o_z, st + SL::OFF_BC, st + o_p, Dv, oscale,
+                                                      active, h, a2, pyp, ostep);
+      asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // y tile (generic proxy) -> bulk store (async proxy)
+      __syncwarp();
+      if (my_lane0) {
+        sbar_arrive(empty_bar(stage));
+        if (m == m_store) store_tile(k - 1);
+        if (m == m_refill && k >= 2) {
+          const int kk = k - 2 + NSTG;
+          if (kk < ntiles) {
+            bulk_wait_read<0>();
+            issue_tile(kk, FIN);
+          }
+        }
+      }
+      s0 += ST_TT;
+      stage = (stage + 1 == NSTG) ? 0 : stage + 1;
+      m = (m + 1 == NW) ? 0 : m + 1;
+    }
+  };
+  using std::integral_constant;
+  typedef integral_constant<bool, true> T_; typedef integral_constant<bool, false> F_;
+  auto fast_fin = [&](auto part_c, auto rev_c, const int kend) {       // finalising phase: pick the gate variant once
+    if (zmode == 0) fast_range(T_{}, part_c, integral_constant<int, 0>{}, rev_c, F_{}, kend);
+    else if (zmode == 2) fast_range(T_{}, part_c, integral_constant<int, 2>{}, rev_c, F_{}, kend);
+    else if (save_ypre) fast_range(T_{}, part_c, integral_constant<int, 1>{}, rev_c, T_{}, kend);
+    else fast_range(T_{}, part_c, integral_constant<int, 1>{}, rev_c, F_{}, kend);
+  };
+  // general step, then the run of full tiles of the same phase that follows it: tile 0 | tiles 1 .. n1t-1 | tile n1t
+  // (phase barrier in front) | tiles n1t+1 .. ntiles-2 | last tile.  (One call site per lambda: everything inlines and
+  // the recurrence state stays in registers.)
+  while (k < ntiles) {
+    generic_step(k);
+    ++k;
+    const int kend = (k <= n1t) ? n1t : ntiles - 1;
+    if (k < kend) {
+      if (k < n1t) {
+        if (rev) fast_range(F_{}, F_{}, integral_constant<int, 0>{}, T_{}, F_{}, kend);
+        else     fast_range(F_{}, F_{}, integral_constant<int, 0>{}, F_{}, F_{}, kend);
+      } else if (bidir) { if (rev) fast_fin(T_{}, T_{}, kend); else fast_fin(T_{}, F_{}, kend); }
+      else              { if (rev) fast_fin(F_{}, T_{}, kend); else fast_fin(F_{}, F_{}, kend); }
+    }
   }
   if (ntiles > 0 && owns(ntiles - 1)) store_tile(ntiles - 1);
   if (my_lane0) bulk_wait_all<0>();           // shared memory must outlive the bulk stores
