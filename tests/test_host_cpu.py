@@ -1,0 +1,74 @@
+"""CPU-only tests of the host-side logic around the engine: derived-weight cache invalidation, the flat-buffer
+layout of the training helpers, and the JSON line of bench.py's reference arm (no GPU, no compute through the C ABI)."""
+import json
+import os
+import subprocess
+import sys
+
+import torch
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def test_derived_weight_cache_follows_parameter_versions():
+    """16-bit / transposed / -exp(A_log) copies are cached per parameter and rebuilt after an in-place update
+    (optimizer.step, load_state_dict) or a raw-pointer update announced with torch._C._increment_version."""
+    from aum_b200 import mixer
+    p = torch.nn.Parameter(torch.arange(6.0).reshape(2, 3))
+    calls = []
+
+    def make(t):
+        calls.append(1)
+        return t.to(torch.float16)
+
+    a = mixer._cache.get(p, "w:test", make)
+    b = mixer._cache.get(p, "w:test", make)
+    assert a is b and len(calls) == 1
+    with torch.no_grad():
+        p.add_(1.0)                                   # what an optimizer does
+    c = mixer._cache.get(p, "w:test", make)
+    assert len(calls) == 2 and torch.equal(c.float(), p.detach())
+    torch._C._increment_version([p])                  # what FlatAdam does after its kernel wrote through a raw pointer
+    mixer._cache.get(p, "w:test", make)
+    assert len(calls) == 3
+    neg = mixer._neg_exp(torch.nn.Parameter(torch.zeros(4, 16)))
+    assert torch.equal(neg, -torch.ones(4, 16))
+
+
+def test_flat_gradient_buffer_layout():
+    """Every tensor of the flat gradient buffer starts on a 32-byte boundary, gradients alias it, zero() clears it."""
+    from aum_b200 import dist as D
+    ps = [torch.nn.Parameter(torch.randn(s)) for s in [(3, 5), (7,), (309,), (768, 2)]]
+    red = D.FlatGradReducer(ps)
+    assert all(o % D.FlatGradReducer.ALIGN == 0 for o in red.offsets)
+    assert red.numel >= sum(p.numel() for p in ps)
+    for p, o in zip(ps, red.offsets):
+        assert p.grad.data_ptr() == red.flat.data_ptr() + 4 * o
+    sum((p * p).sum() for p in ps).backward()
+    for p in ps:
+        torch.testing.assert_close(p.grad, 2 * p.detach())
+    red.zero()
+    assert float(red.flat.abs().sum()) == 0.0
+    assert D.shard_range(10, 0, 4) == (0, 3) and D.shard_range(10, 3, 4) == (8, 10)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the reference's CPU path through the oracle port): one JSON line with the same
+    metric / unit as the GPU arm, impl = reference, a cpu_baseline describing the run and an e2e object of its own."""
+    r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
+                       capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0, r.stderr[-2000:]
+    lines = [ln for ln in r.stdout.splitlines() if ln.startswith("{")]
+    assert len(lines) == 1
+    d = json.loads(lines[0])
+    assert d["impl"] == "reference" and d["unit"] == "clips/s" and d["higher_is_better"] is True
+    assert d["metric"].startswith("clips/sec AuM-Base")
+    assert d["value"] > 0 and d["steps"] == 1
+    cb = d["cpu_baseline"]
+    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    # a non-zero rank of a torchrun launch does no work and prints nothing
+    env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")
+    r2 = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--gpus", "2", "--steps", "1"],
+                        capture_output=True, text=True, timeout=120, env=env)
+    assert r2.returncode == 0 and r2.stdout.strip() == ""
