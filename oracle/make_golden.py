@@ -21,7 +21,7 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 sys.path.insert(0, HERE)
 import ref_loader  # noqa: E402
 
-OUT = os.path.join(os.path.dirname(HERE), "tests", "golden")
+OUT = os.environ.get("AUM_GOLDEN_OUT") or os.path.join(os.path.dirname(HERE), "tests", "golden")   # (override: regeneration check)
 SEED = 3949  # the reference's experiment seed (src/run.py:28-30)
 
 
