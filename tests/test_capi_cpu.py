@@ -75,3 +75,64 @@ def test_mamba_module_state_dict_keys_match_reference_golden():
     m = Mamba(64, bimamba_type="v1")
     assert m.A_log._no_weight_decay and m.D._no_weight_decay and m.dt_proj.bias._no_reinit
     assert torch.allclose(m.A_log[0], torch.log(torch.arange(1, 17.0)))
+
+
+PKG = os.path.join(ROOT, "audio-mamba-aum_b200")
+
+
+def _cuobjdump_sass():
+    import shutil
+    import subprocess
+    from aum_b200 import _lib
+    exe = shutil.which("cuobjdump") or "/usr/local/cuda/bin/cuobjdump"
+    if not os.path.exists(exe) or not os.path.isfile(_lib.LIB_PATH):
+        pytest.skip("cuobjdump or the built library not available")
+    return subprocess.run([exe, "-sass", _lib.LIB_PATH], capture_output=True, text=True, timeout=600).stdout
+
+
+def test_library_is_sm100a_and_uses_the_blackwell_instructions():
+    """The shared library carries sm_100a SASS only, and the hot kernels really are what DESIGN.md says they are:
+    tcgen05 MMAs (single-CTA and CTA-pair), TMA tensor loads / stores, TMEM loads / stores, packed fp32x2 math and
+    MUFU.EX2 in the scan (mnemonics of /opt/skills/guides/B200_PROFILING.md)."""
+    sass = _cuobjdump_sass()
+    archs = set(re.findall(r"arch = (sm_\w+)", sass))
+    assert archs == {"sm_100a"}, archs
+
+    def body(fragment):
+        parts = sass.split("Function : ")
+        hits = [p for p in parts if fragment in p.split("\n", 1)[0]]
+        assert hits, f"no kernel matching {fragment}"
+        return "\n".join(hits)
+
+    gemm = body("gemm_tcgen05_kernel")
+    assert "UTCHMMA" in gemm and "UTMALDG" in gemm and "UTMASTG" in gemm and "LDTM" in gemm
+    assert "UTCHMMA.2CTA" in body("gemm_tcgen05_pair_kernel") and "UTMALDG.2D.2CTA" in body("gemm_tcgen05_pair_kernel")
+    scan = body("scan_fwd_tma_kernel")
+    assert "UTMALDG" in scan and "UTMASTG" in scan and "MUFU.EX2" in scan and "FFMA2" in scan and "FMUL2" in scan
+    bwd = body("scan_bwd_tma_kernel")
+    assert "STTM" in bwd and "LDTM" in bwd and "UTMALDG" in bwd
+    assert "FFMA2" in body("conv1d_fwd_vec4_kernel")
+
+
+def test_hot_kernels_do_not_spill():
+    """ptxas logs of the in-tree build: the scan kernels keep their recurrence state in registers (a lambda that
+    failed to inline once put it on a 1.3 KB stack frame and made the kernel 3x slower), within the register budgets
+    the occupancy figures of DESIGN.md assume."""
+    logdir = os.path.join(PKG, "csrc", "build")
+    if not os.path.isdir(logdir):
+        pytest.skip("no build logs (library was not built in this tree)")
+
+    def entries(name):
+        txt = open(os.path.join(logdir, name)).read()
+        out = []
+        for m in re.finditer(r"Compiling entry function '(\S+)'[^\n]*\n[^\n]*\n\s*(\d+) bytes stack frame, (\d+) bytes spill stores, "
+                             r"(\d+) bytes spill loads\n[^\n]*Used (\d+) registers", txt):
+            out.append((m.group(1), int(m.group(2)), int(m.group(3)), int(m.group(4)), int(m.group(5))))
+        return out
+
+    fwd = [e for e in entries("scan_fwd_tma.ptxas.log") if "scan_fwd_tma_kernel" in e[0]]
+    assert fwd and all(st == 0 and ss == 0 and sl == 0 and regs <= 128 for _, st, ss, sl, regs in fwd), fwd
+    bwd = [e for e in entries("scan_bwd_tma.ptxas.log") if "scan_bwd_tma_kernel" in e[0]]
+    assert bwd and all(st == 0 and ss == 0 and regs <= 168 for _, st, ss, sl, regs in bwd), bwd
+    gemm = [e for e in entries("gemm_tcgen05.ptxas.log") if "gemm_tcgen05" in e[0]]
+    assert gemm and all(ss == 0 and sl == 0 for _, st, ss, sl, regs in gemm), gemm
