@@ -136,3 +136,20 @@ def test_hot_kernels_do_not_spill():
     assert bwd and all(st == 0 and ss == 0 and regs <= 168 for _, st, ss, sl, regs in bwd), bwd
     gemm = [e for e in entries("gemm_tcgen05.ptxas.log") if "gemm_tcgen05" in e[0]]
     assert gemm and all(ss == 0 and sl == 0 for _, st, ss, sl, regs in gemm), gemm
+
+
+def test_header_is_plain_c():
+    """include/aum_b200.h is the C ABI: it must compile as C99 (no C++ or torch types in the signatures)."""
+    import shutil
+    import subprocess
+    import tempfile
+    gcc = shutil.which("gcc")
+    if gcc is None:
+        pytest.skip("gcc not available")
+    with tempfile.TemporaryDirectory() as d:
+        src = os.path.join(d, "h.c")
+        with open(src, "w") as f:
+            f.write('#include "aum_b200.h"\nint main(void) { return aum_version() == 0; }\n')
+        r = subprocess.run([gcc, "-std=c99", "-Wall", "-Wextra", "-pedantic", "-Werror", "-fsyntax-only",
+                            "-I", os.path.join(ROOT, "include"), src], capture_output=True, text=True)
+    assert r.returncode == 0, r.stderr
