@@ -30,6 +30,28 @@
 namespace aum {
 
 constexpr int ST_TT = 8;      // tokens per tile
+
+// Which lane of a (converged) warp does the TMA bookkeeping.  Default (0): lane 0 under `if (lane == 0)` - the build that
+// is validated and measured.  -DAUM_SCAN_ELECT=1 is a round-2 experiment that has NOT been run on a GPU yet: elect.sync,
+// so that ptxas emits the UTMALDG / UTMASTG / UBLKCP of the owner's duties straight instead of wrapping each one in an
+// ELECT / BRA.U.ANY loop (the change that gave the tcgen05 GEMMs' MMA issuer 6 %, and which would shrink the 9-11 KB
+// steady-state loops that now cost 6 % of instruction-cache hit rate).  Every site runs with the warp converged and
+// the full mask, so the elected lane is the same one each time (it owns the bulk async-groups).
+#ifndef AUM_SCAN_ELECT
+#define AUM_SCAN_ELECT 0
+#endif
+#if AUM_SCAN_ELECT
+__device__ __forceinline__ bool scan_elect() {
+  uint32_t pred;
+  asm volatile("{\n\t.reg .pred p;\n\telect.sync _|p, 0xffffffff;\n\tselp.b32 %0, 1, 0, p;\n\t}" : "=r"(pred));
+  return pred != 0;
+}
+#define AUM_LEAD(lane0_expr) scan_elect()
+#define AUM_LEAD0(tig0_expr) (warp_in_group == 0 && scan_elect())
+#else
+#define AUM_LEAD(lane0_expr) (lane0_expr)
+#define AUM_LEAD0(tig0_expr) (tig0_expr)
+#endif
 // channels per CTA (= threads per direction) is a template parameter CH: 128 (default: two CTAs = 16 warps per SM, the
 // kernel owns the register file) or 192 (AUM_SCAN_TMA_CH=192: one 12-warp CTA per SM that leaves 16 K registers and
 // ~95 KB of shared memory free).  Measured at config 2 (fp16, pre-gated z): 0.541 ms vs 0.582 ms - the XU pipe needs
@@ -277,8 +299,12 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     }
   };
   const bool my_lane0 = lane == 0;
+#if AUM_SCAN_ELECT
+  auto owns = [&](int j) { return (j % NW) == warp_in_group && scan_elect(); };     // (warp-uniform test first)
+#else
   auto owns = [&](int j) { return my_lane0 && (j % NW) == warp_in_group; };
-  if (tig == 0) {
+#endif
+  if (AUM_LEAD0(tig == 0)) {
     for (int k = 0; k < NSTG && k < ntiles; ++k) issue_tile(k, !bidir);
   }
   // highest tile issued before iteration k ends its producer step (see the loop tail): NSTG - 1 up front, then k - 2 + NSTG
@@ -332,10 +358,10 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
       // stores (full tiles), the generic-proxy stores of short tiles are made visible to the async proxy, then the
       // CTA meets and the producer catches up on the partial tiles of the stages already in flight
       if (n1t >= 1 && owns(n1t - 1)) store_tile(n1t - 1);
-      if (my_lane0) bulk_wait_all<0>();
+      if (AUM_LEAD(my_lane0)) bulk_wait_all<0>();
       asm volatile("fence.proxy.async.global;" ::: "memory");
       __syncthreads();
-      if (tig == 0) {
+      if (AUM_LEAD0(tig == 0)) {
         const int upto = issued_before(n1t);
         for (int kk = n1t; kk <= upto; ++kk) issue_partial(kk);
       }
@@ -384,7 +410,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     // hand the stage back.  The elected thread then (a) bulk-stores the tile finished one iteration ago, once all
     // four warps have released it, and (b) refills the stage of the tile before that, once its store has drained.
     __syncwarp();
-    if (my_lane0) {
+    if (AUM_LEAD(my_lane0)) {
       sbar_arrive(empty_bar(stage));
       if (m == m_store && k >= 1 && !(bidir && k == n1t)) store_tile(k - 1);     // (tile n1t-1 left at the phase barrier)
       if (m == m_refill && k >= 2) {
@@ -427,7 +453,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
                                                       active, h, a2, pyp, ostep);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // y tile (generic proxy) -> bulk store (async proxy)
       __syncwarp();
-      if (my_lane0) {
+      if (AUM_LEAD(my_lane0)) {
         sbar_arrive(empty_bar(stage));
         if (m == m_store) store_tile(k - 1);
         if (m == m_refill && k >= 2) {
@@ -467,7 +493,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     }
   }
   if (ntiles > 0 && owns(ntiles - 1)) store_tile(ntiles - 1);
-  if (my_lane0) bulk_wait_all<0>();           // shared memory must outlive the bulk stores
+  if (AUM_LEAD(my_lane0)) bulk_wait_all<0>();  // shared memory must outlive the bulk stores
   if (bidir && n2t == 0) {                  // (degenerate) keep the CTA barrier count equal across directions
     asm volatile("fence.proxy.async.global;" ::: "memory");
     __syncthreads();
