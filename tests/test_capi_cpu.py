@@ -43,6 +43,19 @@ def test_argument_errors_are_reported_not_crashed():
     assert rc != 0 and b"null" in lib.aum_last_error()
     rc = lib.aum_selective_scan_fwd(None, None, None, 0, None, 0, 1, 1, 1, 16, 0, 1.0, None, 0, 0, None)
     assert rc != 0 and b"direction" in lib.aum_last_error()
+    # the entry points added for the callers either side of the path validate before they launch, too
+    rc = lib.aum_adam_step(None, None, None, None, 8, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None)
+    assert rc != 0 and b"aum_adam_step" in lib.aum_last_error()
+    buf = ctypes.create_string_buffer(64)
+    p = ctypes.cast(buf, ctypes.c_void_p)
+    rc = lib.aum_adam_step(p, p, p, p, 8, 1e-3, 0.9, 0.999, 1e-8, 0.0, 0, 1.0, None)        # steps count from 1
+    assert rc != 0 and b"step" in lib.aum_last_error()
+    rc = lib.aum_patchify(p, p, 1, 30, 128, 16, 16, 0, None)                                  # T % pt != 0
+    assert rc != 0 and b"aum_patchify" in lib.aum_last_error()
+    rc = lib.aum_assemble_tokens(p, p, p, p, 1, 4, 6, None)                                   # Dm % 4 != 0
+    assert rc != 0 and b"multiple of 4" in lib.aum_last_error()
+    assert lib.aum_adam_step(None, None, None, None, 0, 1e-3, 0.9, 0.999, 1e-8, 0.0, 1, 1.0, None) == 0   # empty: no-op
+    assert lib.aum_patchify(None, None, 0, 1024, 128, 16, 16, 1, None) == 0
 
 
 def test_product_path_has_no_cpu_fallback():
