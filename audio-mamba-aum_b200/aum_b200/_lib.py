@@ -11,7 +11,8 @@ import os
 import torch
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(_HERE, "lib", "libaum_b200.so")
+# AUM_B200_LIB: an experiment build of the same library (csrc/Makefile VARIANT=...); never a different implementation
+LIB_PATH = os.environ.get("AUM_B200_LIB") or os.path.join(_HERE, "lib", "libaum_b200.so")
 
 F32, F16, BF16 = 0, 1, 2
 ACT_NONE, ACT_SOFTPLUS, ACT_SILU = 0, 1, 2

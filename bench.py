@@ -60,14 +60,25 @@ class _StdoutToStderr:
         os.close(self._saved)
 
 
+SCAN_TRAFFIC_FILE = os.path.join("profiles", "r2_scan_traffic.json")
+
+
 def scan_traffic(sequences_per_launch: int):
-    """dram__bytes_read.sum + dram__bytes_write.sum of one scan launch, from the committed ncu --set full capture
-    (taken on a 64-sequence launch; traffic is linear in the number of sequences)."""
+    """dram__bytes_read.sum + dram__bytes_write.sum of ONE scan launch of exactly this size, from the committed
+    `ncu --set full` capture of the kernel (tools/ncu_scan_traffic.sh writes the file).  Only used when the capture
+    was taken on the same launch size and on the kernel source that is in the tree now (sha256 of scan_fwd_tma.cu
+    recorded next to the numbers); otherwise null - a DRAM byte count cannot be read outside a profiler."""
     try:
-        t = json.load(open(os.path.join(ROOT, "profiles", "r1_scan_traffic.json")))
-        return int((t["dram__bytes_read.sum"] + t["dram__bytes_write.sum"]) * sequences_per_launch / 64)
+        import hashlib
+        t = json.load(open(os.path.join(ROOT, SCAN_TRAFFIC_FILE)))
+        src = os.path.join(ROOT, "audio-mamba-aum_b200", "csrc", "scan_fwd_tma.cu")
+        if t.get("kernel_source_sha256") != hashlib.sha256(open(src, "rb").read()).hexdigest():
+            return None, "null: committed ncu capture predates the current scan_fwd_tma.cu"
+        if int(t.get("sequences_per_launch", -1)) != sequences_per_launch:
+            return None, "null: committed ncu capture is of another launch size"
+        return int(t["dram__bytes_read.sum"] + t["dram__bytes_write.sum"]), SCAN_TRAFFIC_FILE
     except Exception:
-        return None
+        return None, "null: no ncu capture committed"
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -120,9 +131,62 @@ class ClockSampler:
 
 
 # ------------------------------------------------------------------------------------------------------
-def cpu_reference_sample(blocks: int = 2, repeats: int = 1):
-    """The reference's CPU implementation of the path (oracle port of selective_scan_ref / bimamba_inner_ref /
-    AudioMamba.forward), fp32, all host threads.  Bounded sample: ONE clip through the front end and `blocks` of
+_REF_MODEL = {}
+
+
+def reference_clip_forward():
+    """ONE whole clip through the reference's OWN code on the host CPU: the unmodified ``AudioMamba`` of
+    src/models/mamba_models.py (config 2: AuM-Base Fo-Bi, depth 24) whose mixer runs the reference's own
+    ``bimamba_inner_ref`` / ``selective_scan_ref`` (selective_scan_interface.py:673-709, 86-152), imported from the
+    staged copy ``oracle/_ref`` (oracle/build_ref.py; the CUDA wheels it would otherwise call cannot run on sm_100).
+    fp32, all the host threads torch will use.  Returns (seconds, threads)."""
+    import contextlib
+    import io
+    import warnings
+    import ref_loader
+    if "m" not in _REF_MODEL:
+        # the reference's per-token ops are small: beyond a few tens of threads intra-op oversubscription makes it SLOWER
+        # (measured on the 128-core GPU box, profiles/r2_reference_threads.txt); AUM_REF_THREADS overrides
+        torch.set_num_threads(int(os.environ.get("AUM_REF_THREADS", 0)) or max(1, min(os.cpu_count() or 1, 32)))
+        with warnings.catch_warnings():
+            warnings.simplefilter("ignore")
+            ns = ref_loader.load_reference_model()
+            torch.manual_seed(SEED)
+            with contextlib.redirect_stdout(io.StringIO()):
+                m = ns.AudioMamba(spectrogram_size=CFG["spectrogram_size"], patch_size=(16, 16), strides=(16, 16),
+                                  depth=CFG["depth"], embed_dim=CFG["embed_dim"], num_classes=CFG["num_classes"],
+                                  bimamba_type=CFG["bimamba_type"]).eval()
+        g = torch.Generator().manual_seed(SEED)
+        _REF_MODEL["m"] = m
+        _REF_MODEL["x"] = 0.5 * torch.randn(1, CFG["spectrogram_size"][1], CFG["spectrogram_size"][0], generator=g)
+        _REF_MODEL["src"] = ref_loader.REF_KIND
+    with torch.no_grad():
+        t0 = time.perf_counter()
+        out = _REF_MODEL["m"](_REF_MODEL["x"])
+        dt_ = time.perf_counter() - t0
+    assert tuple(out.shape) == (1, CFG["num_classes"]) and bool(torch.isfinite(out).all())
+    return dt_, torch.get_num_threads()
+
+
+def cpu_reference_sample(clips: int = 2):
+    """cpu_baseline of the main arm: `clips` whole clips (one at a time) through reference_clip_forward()."""
+    try:
+        reference_clip_forward()                      # builds the model, first-touch
+        ts = [reference_clip_forward() for _ in range(clips)]
+    except Exception as e:                            # staged reference missing: fall back to the oracle port
+        r = cpu_port_sample(blocks=2)
+        r["note"] = f"oracle/_ref unavailable ({type(e).__name__}: {e}); oracle port timed instead"
+        return r
+    sec = statistics.median([t for t, _ in ts])
+    return {"value": 1.0 / sec, "unit": UNIT, "cores": ts[0][1], "kind": "reference",
+            "sample": f"{clips} whole clips (batch 1 each, median) through the reference's own AudioMamba + bimamba_inner_ref "
+                      f"(+1 untimed warm-up clip), all 24 blocks, fp32, {_REF_MODEL['src']}",
+            "seconds_per_clip": sec}
+
+
+def cpu_port_sample(blocks: int = 2, repeats: int = 1):
+    """Fallback only (no staged reference): the oracle port of selective_scan_ref / bimamba_inner_ref /
+    AudioMamba.forward, fp32.  Bounded sample: ONE clip through the front end and `blocks` of
     the 24 blocks; whole-model time extrapolated linearly in the block count (every block is identical work)."""
     import aum_oracle as O
     # the oracle's per-token ops are small: beyond ~16 threads intra-op oversubscription makes it SLOWER
@@ -151,25 +215,49 @@ def cpu_reference_sample(blocks: int = 2, repeats: int = 1):
             "seconds_per_block_per_clip": per_block}
 
 
+REFERENCE_ARM_BUDGET_S = 330.0
+
+
 def run_reference(args, rank):
-    """--impl reference: the reference's own CPU path (oracle port; the Python reference cannot travel to the
-    GPU box).  Rank 0 only; one step = one bounded sample."""
+    """--impl reference: the reference's own CPU implementation of the path, timed on the box's host cores.
+    One step = ONE WHOLE CLIP through the unmodified reference model (reference_clip_forward: all 24 blocks, nothing
+    extrapolated): the bounded sample of the batch-64 workload is its batch size, 1 of 64 clips - every clip is the
+    same work and the CPU path has no cross-clip reuse, so clips/s is what is reported.  W warm-up + K timed steps are
+    run as asked, bounded by a wall-clock budget (REFERENCE_ARM_BUDGET_S): at ~5-10 s per clip the driver's 5 + 20
+    steps fit; if the budget runs out first, `steps` reports the number actually timed.  Rank 0 only."""
     if rank != 0:
         return
-    vals = []
-    for i in range(args.warmup + args.steps):
-        r = cpu_reference_sample(blocks=1)
-        if i >= args.warmup:
-            vals.append(r)
-    v = statistics.median([r["value"] for r in vals]) if vals else float("nan")
-    last = vals[-1] if vals else {"cores": os.cpu_count(), "kind": "port", "sample": "none"}
-    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-           "warmup": args.warmup, "ms_per_step": (1000.0 / v) if v == v and v > 0 else None,
+    t_start = time.perf_counter()
+    secs, threads, w_done = [], 1, 0
+    try:
+        for i in range(args.warmup + args.steps):
+            if i >= 1 and time.perf_counter() - t_start > REFERENCE_ARM_BUDGET_S and (i < args.warmup or len(secs) >= 3):
+                if i < args.warmup:
+                    continue                  # out of budget during warm-up: go straight to the timed steps
+                break
+            t, threads = reference_clip_forward()
+            if i >= args.warmup:
+                secs.append(t)
+            else:
+                w_done += 1
+        kind, src, note = "reference", _REF_MODEL.get("src", "?"), None
+    except Exception as e:
+        r = cpu_port_sample(blocks=1)
+        secs, threads, kind, src = [1.0 / r["value"]], r["cores"], "port", "oracle port"
+        note = f"oracle/_ref unavailable ({type(e).__name__}: {e}): oracle port, 1 clip x 1 of 24 blocks extrapolated"
+    sec = statistics.median(secs)
+    v = 1.0 / sec
+    sample = (f"1 whole clip per step (1 of the 64 clips of a batch; all 24 blocks, nothing extrapolated) through the "
+              f"reference's own AudioMamba + bimamba_inner_ref / selective_scan_ref, fp32, {src}")
+    out = {"impl": "reference", "metric": METRIC, "value": v, "unit": UNIT, "n_gpus": args.gpus, "steps": len(secs),
+           "steps_requested": args.steps, "warmup": w_done, "ms_per_step": 1000.0 * sec,
            "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
-           "config": {"workload": "AuM-Base Fo-Bi forward, 128x1024 mel -> 513 tokens (CPU sample: 1 clip, 1 of 24 blocks, extrapolated)"},
-           "cpu_baseline": {"value": v, "unit": UNIT, "cores": last["cores"], "kind": last["kind"], "sample": last["sample"]},
+           "config": {"workload": "AuM-Base Fo-Bi forward (BASELINE configs[1]): 128x1024 mel -> 513 tokens, depth 24, "
+                                  "d_model 768, d_state 16; CPU sample: batch 1 per step",
+                      "clips_per_step": 1},
+           "cpu_baseline": {"value": v, "unit": UNIT, "cores": threads, "kind": kind, "sample": note or sample},
            "e2e": {"value": v, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-           "gpu_launches": 0}
+           "gpu_launches": 0, "wall_s": time.perf_counter() - t_start}
     print(json.dumps(out), flush=True)
 
 
@@ -326,7 +414,7 @@ def main():
     if rank == 0:
         cpu = None
         if world == 1 and not args.no_cpu_baseline:
-            cpu = cpu_reference_sample(blocks=2)
+            cpu = cpu_reference_sample(clips=2)
         out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps,
                "warmup": args.warmup, "ms_per_step": ms_step, "higher_is_better": True, "scaling": "weak",
                "vs_baseline": None, "dtype": args.dtype, "data": "synthetic",

@@ -42,6 +42,17 @@ def silu_oracle(x: torch.Tensor) -> torch.Tensor:
     return x * torch.sigmoid(x)
 
 
+def _rnd(t: Optional[torch.Tensor], io_dtype: Optional[torch.dtype]) -> Optional[torch.Tensor]:
+    """Round-trip through the autocast dtype: the reference's half-precision rounding points.
+    Under ``--mixed_precision=fp16`` (exps/*/*.sh) the reference materialises xz, conv1d_out, x_dbl (hence the raw
+    delta, B and C), both directional out_z tensors, their sum and the out_proj output in the autocast dtype and
+    casts the three projection weights to it (selective_scan_interface.py:452-457,463-468,499-507,517); scan
+    state, A, D and delta_bias stay fp32.  ``io_dtype=None`` (default) leaves everything in fp32 (the oracle)."""
+    if t is None or io_dtype is None:
+        return t
+    return t.to(io_dtype).to(t.dtype)
+
+
 def causal_conv1d_oracle(x: torch.Tensor, weight: torch.Tensor, bias: Optional[torch.Tensor],
                          silu: bool = True) -> torch.Tensor:
     """Depthwise causal conv along the last axis + optional SiLU.
@@ -121,17 +132,19 @@ def selective_scan_oracle(u, delta, A, B, C, D=None, z=None, delta_bias=None,
 # fused inner ops
 # --------------------------------------------------------------------------------------
 
-def _proj_stage(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, d_state):
+def _proj_stage(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, d_state, io_dtype=None):
     """conv -> x_proj -> dt_proj, shared by the three inner ops
-    (selective_scan_interface.py:642-668 / :679-705)."""
+    (selective_scan_interface.py:642-668 / :679-705).  io_dtype: see _rnd (emulated-reference rounding points
+    of the fused forward, :452-468)."""
     L = xz.shape[-1]
     R = delta_proj_weight.shape[1]
+    xz = _rnd(xz, io_dtype)
     x, z = xz.chunk(2, dim=1)
     w = conv1d_weight.reshape(conv1d_weight.shape[0], conv1d_weight.shape[-1])   # "d 1 w -> d w"
-    x = causal_conv1d_oracle(x, w, conv1d_bias, silu=True)                       # (:646 / :683)
+    x = _rnd(causal_conv1d_oracle(x, w, conv1d_bias, silu=True), io_dtype)       # (:646 / :683; :463)
     Bsz, Di, _ = x.shape
-    x_dbl = F.linear(x.permute(0, 2, 1).reshape(Bsz * L, Di), x_proj_weight)     # (:650) (B*L, R+2N)
-    delta = (delta_proj_weight @ x_dbl[:, :R].t()).reshape(Di, Bsz, L).permute(1, 0, 2)   # (:651-652)
+    x_dbl = _rnd(F.linear(x.permute(0, 2, 1).reshape(Bsz * L, Di), _rnd(x_proj_weight, io_dtype)), io_dtype)  # (:650; :467)
+    delta = _rnd((_rnd(delta_proj_weight, io_dtype) @ x_dbl[:, :R].t()), io_dtype).reshape(Di, Bsz, L).permute(1, 0, 2)   # (:651-652; :468)
     Bm = x_dbl[:, R:R + d_state].reshape(Bsz, L, d_state).permute(0, 2, 1).contiguous()   # (:654-658)
     Cm = x_dbl[:, -d_state:].reshape(Bsz, L, d_state).permute(0, 2, 1).contiguous()       # (:662-666)
     return x, z, delta, Bm, Cm
@@ -139,43 +152,43 @@ def _proj_stage(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight
 
 def mamba_inner_oracle(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
                        out_proj_weight, out_proj_bias, A, D=None, delta_bias=None,
-                       compute_dtype=torch.float32):
+                       compute_dtype=torch.float32, io_dtype=None):
     """Fo-Fo inner op; restates mamba_inner_ref (selective_scan_interface.py:636-670)."""
     x, z, delta, Bm, Cm = _proj_stage(xz, conv1d_weight, conv1d_bias, x_proj_weight,
-                                      delta_proj_weight, A.shape[-1])
-    y = selective_scan_oracle(x, delta, A, Bm, Cm, D, z=z, delta_bias=delta_bias,
-                              delta_softplus=True, compute_dtype=compute_dtype)    # (:669)
-    return F.linear(y.permute(0, 2, 1), out_proj_weight, out_proj_bias)            # (:670)
+                                      delta_proj_weight, A.shape[-1], io_dtype)
+    y = _rnd(selective_scan_oracle(x, delta, A, Bm, Cm, D, z=z, delta_bias=delta_bias,
+                                   delta_softplus=True, compute_dtype=compute_dtype), io_dtype)    # (:669)
+    return _rnd(F.linear(y.permute(0, 2, 1), _rnd(out_proj_weight, io_dtype), _rnd(out_proj_bias, io_dtype)), io_dtype)   # (:670)
 
 
 def mamba_inner_no_out_proj_oracle(xz, conv1d_weight, conv1d_bias, x_proj_weight,
                                    delta_proj_weight, A, D=None, delta_bias=None,
-                                   compute_dtype=torch.float32):
+                                   compute_dtype=torch.float32, io_dtype=None):
     """One Bi-Bi pipeline: MambaInnerFnNoOutProj.forward semantics
     (selective_scan_interface.py:155-224) = mamba_inner_ref without :670; returns (B, Di, L)."""
     x, z, delta, Bm, Cm = _proj_stage(xz, conv1d_weight, conv1d_bias, x_proj_weight,
-                                      delta_proj_weight, A.shape[-1])
-    return selective_scan_oracle(x, delta, A, Bm, Cm, D, z=z, delta_bias=delta_bias,
-                                 delta_softplus=True, compute_dtype=compute_dtype)
+                                      delta_proj_weight, A.shape[-1], io_dtype)
+    return _rnd(selective_scan_oracle(x, delta, A, Bm, Cm, D, z=z, delta_bias=delta_bias,
+                                      delta_softplus=True, compute_dtype=compute_dtype), io_dtype)
 
 
 def bimamba_inner_oracle(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
                          out_proj_weight, out_proj_bias, A, A_b, D=None, delta_bias=None,
-                         compute_dtype=torch.float32):
+                         compute_dtype=torch.float32, io_dtype=None):
     """Fo-Bi inner op; restates bimamba_inner_ref (selective_scan_interface.py:673-709).
 
     Both directions share conv / x_proj / dt_proj / D / delta_bias; only A vs A_b
     differ; the reverse scan runs on flipped tensors and is flipped back (:706-708).
     D*u therefore enters twice."""
     x, z, delta, Bm, Cm = _proj_stage(xz, conv1d_weight, conv1d_bias, x_proj_weight,
-                                      delta_proj_weight, A.shape[-1])
-    y = selective_scan_oracle(x, delta, A, Bm, Cm, D, z=z, delta_bias=delta_bias,
-                              delta_softplus=True, compute_dtype=compute_dtype)         # (:706)
-    y_b = selective_scan_oracle(x.flip([-1]), delta.flip([-1]), A_b, Bm.flip([-1]),
-                                Cm.flip([-1]), D, z.flip([-1]), delta_bias,
-                                delta_softplus=True, compute_dtype=compute_dtype)       # (:707)
-    y = y + y_b.flip([-1])                                                              # (:708)
-    return F.linear(y.permute(0, 2, 1), out_proj_weight, out_proj_bias)                 # (:709)
+                                      delta_proj_weight, A.shape[-1], io_dtype)
+    y = _rnd(selective_scan_oracle(x, delta, A, Bm, Cm, D, z=z, delta_bias=delta_bias,
+                                   delta_softplus=True, compute_dtype=compute_dtype), io_dtype)         # (:706; out_z_f :499)
+    y_b = _rnd(selective_scan_oracle(x.flip([-1]), delta.flip([-1]), A_b, Bm.flip([-1]),
+                                     Cm.flip([-1]), D, z.flip([-1]), delta_bias,
+                                     delta_softplus=True, compute_dtype=compute_dtype), io_dtype)       # (:707; out_z_b :503)
+    y = _rnd(y + y_b.flip([-1]), io_dtype)                                              # (:708; :507)
+    return _rnd(F.linear(y.permute(0, 2, 1), _rnd(out_proj_weight, io_dtype), _rnd(out_proj_bias, io_dtype)), io_dtype)   # (:709; :517)
 
 
 # --------------------------------------------------------------------------------------
@@ -183,13 +196,15 @@ def bimamba_inner_oracle(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_pr
 # --------------------------------------------------------------------------------------
 
 def mamba_forward_oracle(p: Dict[str, torch.Tensor], hidden: torch.Tensor, bimamba_type: str = "v1",
-                         if_devide_out: bool = False, compute_dtype=torch.float32) -> torch.Tensor:
+                         if_devide_out: bool = False, compute_dtype=torch.float32, io_dtype=None) -> torch.Tensor:
     """Mamba.forward fast path (vim-mamba_ssm/mamba_ssm/modules/mamba_simple.py:169-311).
 
     ``p`` uses the module's state-dict key names (in_proj.weight, conv1d.weight, ...).
-    hidden: (B, L, Dm) -> (B, L, Dm)."""
+    hidden: (B, L, Dm) -> (B, L, Dm).  io_dtype: emulate the reference's autocast rounding points (see _rnd);
+    the in_proj matmul (:185-189) runs in the autocast dtype, so its operands and result are rounded too."""
     Bsz, L, Dm = hidden.shape
-    W_in = p["in_proj.weight"]
+    W_in = _rnd(p["in_proj.weight"], io_dtype)
+    hidden = _rnd(hidden, io_dtype)
     xz = (W_in @ hidden.reshape(Bsz * L, Dm).t()).reshape(-1, Bsz, L).permute(1, 0, 2)   # (:185-189)
     if "in_proj.bias" in p and p["in_proj.bias"] is not None:
         xz = xz + p["in_proj.bias"].to(xz.dtype)[None, :, None]                          # (:190-191)
@@ -199,27 +214,27 @@ def mamba_forward_oracle(p: Dict[str, torch.Tensor], hidden: torch.Tensor, bimam
         A_b = -torch.exp(p["A_b_log"].float())                                           # (:197)
         out = bimamba_inner_oracle(xz, p["conv1d.weight"], p["conv1d.bias"], p["x_proj.weight"],
                                    p["dt_proj.weight"], p["out_proj.weight"], ob, A, A_b,
-                                   p["D"].float(), p["dt_proj.bias"].float(), compute_dtype)   # (:198-213)
+                                   p["D"].float(), p["dt_proj.bias"].float(), compute_dtype, io_dtype)   # (:198-213)
     elif bimamba_type == "v2":
         A_b = -torch.exp(p["A_b_log"].float())                                           # (:215)
         o = mamba_inner_no_out_proj_oracle(xz, p["conv1d.weight"], p["conv1d.bias"],
                                            p["x_proj.weight"], p["dt_proj.weight"], A,
-                                           p["D"].float(), p["dt_proj.bias"].float(), compute_dtype)  # (:216-228)
+                                           p["D"].float(), p["dt_proj.bias"].float(), compute_dtype, io_dtype)  # (:216-228)
         o_b = mamba_inner_no_out_proj_oracle(xz.flip([-1]), p["conv1d_b.weight"], p["conv1d_b.bias"],
                                              p["x_proj_b.weight"], p["dt_proj_b.weight"], A_b,
-                                             p["D_b"].float(), p["dt_proj_b.bias"].float(), compute_dtype)  # (:229-241)
-        y = (o + o_b.flip([-1])).permute(0, 2, 1)
+                                             p["D_b"].float(), p["dt_proj_b.bias"].float(), compute_dtype, io_dtype)  # (:229-241)
+        y = _rnd((o + o_b.flip([-1])).permute(0, 2, 1), io_dtype)
         if if_devide_out:
-            y = y / 2                                                                    # (:246)
-        out = F.linear(y, p["out_proj.weight"], ob)                                      # (:244/:246)
+            y = y / 2                                                                    # (:246)  (exact in fp16/bf16)
+        out = _rnd(F.linear(y, _rnd(p["out_proj.weight"], io_dtype), _rnd(ob, io_dtype)), io_dtype)   # (:244/:246)
     elif bimamba_type == "none":
         out = mamba_inner_oracle(xz, p["conv1d.weight"], p["conv1d.bias"], p["x_proj.weight"],
                                  p["dt_proj.weight"], p["out_proj.weight"], ob, A,
-                                 p["D"].float(), p["dt_proj.bias"].float(), compute_dtype)     # (:249-263)
+                                 p["D"].float(), p["dt_proj.bias"].float(), compute_dtype, io_dtype)     # (:249-263)
     else:
         raise ValueError(bimamba_type)
     if "gamma" in p and p["gamma"] is not None:
-        out = out * p["gamma"]                                                           # (:309-310)
+        out = _rnd(out * p["gamma"], io_dtype)                                           # (:309-310)
     return out
 
 
@@ -252,18 +267,23 @@ def audio_mamba_forward_oracle(sd: Dict[str, torch.Tensor], x: torch.Tensor, *, 
                                bimamba_type: str = "v1", if_devide_out: bool = True,
                                patch: Tuple[int, int] = (16, 16), eps: float = 1e-5,
                                compute_dtype=torch.float32, n_blocks: Optional[int] = None,
-                               return_features: bool = False) -> torch.Tensor:
+                               return_features: bool = False, io_dtype=None) -> torch.Tensor:
     """AudioMamba.forward, default configuration (src/models/mamba_models.py:509-685):
     rms_norm=True, fused_add_norm=True, residual_in_fp32=True, abs pos-embed, middle cls token,
     no rope, no flips, drop_path 0.  ``sd`` is the model's state dict.  x: (B, T, F).
 
     n_blocks (< depth) runs only the first n_blocks layers — used ONLY by bench.py's bounded CPU
-    sample, never by parity tests."""
+    sample, never by parity tests.
+
+    io_dtype (torch.float16 / torch.bfloat16): the *emulated reference* — the same forward with every tensor
+    the reference materialises in the autocast dtype under ``accelerate --mixed_precision`` rounded to it
+    (patch-embed conv, the normed activations, everything listed at _rnd, the head); the residual stream stays
+    fp32 (residual_in_fp32, mamba_models.py:209).  Used by the 16-bit parity tier: SURVEY.md section 8(c)."""
     Bsz = x.shape[0]
-    img = x.unsqueeze(1).transpose(2, 3)                                    # (:510-511) B,1,F,T
-    w = sd["patch_embed.proj.weight"]
-    b = sd["patch_embed.proj.bias"]
-    t = F.conv2d(img, w, b, stride=patch)                                   # tokenization.py:306
+    img = _rnd(x.unsqueeze(1).transpose(2, 3), io_dtype)                    # (:510-511) B,1,F,T
+    w = _rnd(sd["patch_embed.proj.weight"], io_dtype)
+    b = _rnd(sd["patch_embed.proj.bias"], io_dtype)
+    t = _rnd(F.conv2d(img, w, b, stride=patch), io_dtype)                   # tokenization.py:306
     t = t.flatten(2).transpose(1, 2)                                        # (:308) B, N, Dm
     N = t.shape[1]
     tp = N // 2                                                             # (:528-529)
@@ -279,13 +299,13 @@ def audio_mamba_forward_oracle(sd: Dict[str, torch.Tensor], x: torch.Tensor, *, 
     for i in range(nb):                                                     # (:602-622)
         nw = sd[f"layers.{i}.norm.weight"]
         hidden, residual = rms_norm_oracle(hidden, nw, None, residual, eps, prenorm=True)   # (:77-97)
-        hidden = mamba_forward_oracle(block_params(sd, i), hidden, bimamba_type,
-                                      if_devide_out, compute_dtype)                          # (:98)
-    hidden = rms_norm_oracle(hidden, sd["norm_f.weight"], None, residual, eps, prenorm=False)  # (:646-657)
+        hidden = mamba_forward_oracle(block_params(sd, i), _rnd(hidden, io_dtype), bimamba_type,
+                                      if_devide_out, compute_dtype, io_dtype)                # (:98)
+    hidden = _rnd(rms_norm_oracle(hidden, sd["norm_f.weight"], None, residual, eps, prenorm=False), io_dtype)  # (:646-657)
     feat = hidden[:, tp, :]                                                 # (:660-664)
     if return_features:
         return feat
-    return F.linear(feat, sd["head.weight"], sd["head.bias"])               # (:682)
+    return _rnd(F.linear(feat, _rnd(sd["head.weight"], io_dtype), _rnd(sd["head.bias"], io_dtype)), io_dtype)   # (:682)
 
 
 # --------------------------------------------------------------------------------------

@@ -1,9 +1,10 @@
-"""Import the REAL reference (kaistmm/Audio-Mamba-AuM) on CPU, unmodified, from /root/reference.
+"""Import the REAL reference (kaistmm/Audio-Mamba-AuM) on CPU, unmodified.
 
-TEST INFRASTRUCTURE ONLY, and build-container only: /root/reference does not exist on the
-GPU box, so nothing in ``-m gpu`` tests, ``smoke()`` or ``bench.py`` may import this module.
-It is used by ``oracle/make_golden.py`` (fixture generation) and by the optional
-``tests/test_oracle_vs_reference.py`` (skipped when /root/reference is absent).
+TEST / BENCH INFRASTRUCTURE ONLY (never imported by the product).  Source tree, first that exists:
+``$AUM_REFERENCE_ROOT``, ``/root/reference`` (build container), ``oracle/_ref`` (the byte-for-byte staged copy
+of the needed files made by ``oracle/build_ref.py``; git-ignored, travels to the GPU box).  Nothing here reads
+/root/reference on the GPU box.  Used by ``oracle/make_golden.py`` (fixture generation), the CPU oracle tests,
+``bench.py --impl reference`` / ``cpu_baseline`` (the reference's own CPU path, timed) and the drop-in tests.
 
 Recipe: the reference's hot path imports three native pip modules
 unconditionally (selective_scan_interface.py:9-11).  We register empty stand-ins so the *Python*
@@ -25,12 +26,24 @@ import types
 import torch
 import torch.nn.functional as F
 
-REF_ROOT = os.environ.get("AUM_REFERENCE_ROOT", "/root/reference")
+_PROBE = "vim-mamba_ssm/mamba_ssm/ops/selective_scan_interface.py"
+
+
+def _find_root() -> str:
+    cands = [os.environ.get("AUM_REFERENCE_ROOT"), "/root/reference",
+             os.path.join(os.path.dirname(os.path.abspath(__file__)), "_ref")]
+    for c in cands:
+        if c and os.path.isfile(os.path.join(c, _PROBE)):
+            return c
+    return cands[1]
+
+
+REF_ROOT = _find_root()
+REF_KIND = "staged copy (oracle/_ref)" if REF_ROOT.endswith("_ref") else "reference tree"
 
 
 def reference_available() -> bool:
-    return os.path.isfile(os.path.join(
-        REF_ROOT, "vim-mamba_ssm/mamba_ssm/ops/selective_scan_interface.py"))
+    return os.path.isfile(os.path.join(REF_ROOT, _PROBE))
 
 
 def _stub(name: str, **attrs) -> types.ModuleType:
@@ -112,11 +125,8 @@ def load_reference():
     return ns
 
 
-def load_reference_model():
-    """Also import src/models/mamba_models.py (AudioMamba) with a 4-symbol timm shim."""
-    ns = load_reference()
-    if hasattr(ns, "AudioMamba"):
-        return ns
+def _timm_shim():
+    """The four timm symbols src/models/mamba_models.py and src/utilities/*.py import (timm is not installed)."""
     import math
 
     def to_2tuple(x):
@@ -144,6 +154,14 @@ def load_reference_model():
     _stub("timm.layers", to_2tuple=to_2tuple, trunc_normal_=trunc_normal_,
           lecun_normal_=lecun_normal_, DropPath=DropPath)
     _stub("wget")
+
+
+def load_reference_model():
+    """Also import src/models/mamba_models.py (AudioMamba) with a 4-symbol timm shim."""
+    ns = load_reference()
+    if hasattr(ns, "AudioMamba"):
+        return ns
+    _timm_shim()
     if REF_ROOT not in sys.path:
         sys.path.insert(0, REF_ROOT)
     mm = importlib.import_module("src.models.mamba_models")
@@ -151,3 +169,26 @@ def load_reference_model():
     ns.mm = mm
     ns.AudioMamba = mm.AudioMamba
     return ns
+
+
+def load_reference_model_over_shim():
+    """Drop-in check: the reference's OWN ``src/models/mamba_models.py`` (AudioMamba, Block, create_block), unmodified,
+    importing ``mamba_ssm.modules.mamba_simple.Mamba`` and ``mamba_ssm.ops.triton.layernorm.{RMSNorm, rms_norm_fn}``
+    (mamba_models.py:18,26) from THIS repo's ``audio-mamba-aum_b200/mamba_ssm`` package instead of the pip wheel.
+    Must run in a process that has not called load_reference() (both register a package named ``mamba_ssm``)."""
+    if not reference_available():
+        raise RuntimeError("reference tree not present at " + REF_ROOT)
+    if "ns" in _loaded:
+        raise RuntimeError("load_reference() already registered the reference's mamba_ssm in this process")
+    import importlib.machinery  # noqa: F401
+    pkg = os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "audio-mamba-aum_b200")
+    if pkg not in sys.path:
+        sys.path.insert(0, pkg)
+    import mamba_ssm.modules.mamba_simple as shim_ms     # this repo's shim
+    assert os.path.abspath(shim_ms.__file__).startswith(pkg), shim_ms.__file__
+    _timm_shim()
+    if REF_ROOT not in sys.path:
+        sys.path.insert(0, REF_ROOT)
+    mm = importlib.import_module("src.models.mamba_models")
+    assert mm.Mamba is shim_ms.Mamba
+    return types.SimpleNamespace(mm=mm, AudioMamba=mm.AudioMamba, Mamba=shim_ms.Mamba)
