@@ -77,6 +77,8 @@ SIGNATURES = {
                               C.c_void_p, C.c_int64, C.c_int, C.c_int,
                               C.c_int, C.c_int, C.c_int,
                               C.c_void_p, C.c_void_p, C.c_int, C.c_int, C.c_void_p]),
+    "aum_gemm_wgrad": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int,
+                                 C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "aum_causal_conv1d_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "aum_selective_scan_fwd": (C.c_int, [C.POINTER(ScanDir), C.POINTER(ScanDir), C.c_void_p, C.c_int64,
@@ -180,11 +182,28 @@ def ptr(t):
     return None if t is None else C.c_void_p(t.data_ptr())
 
 
+import threading
+
+_tls = threading.local()
+
+
 def stream():
-    return C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    """The CURRENT stream of the device the op's tensors live on (require_cuda noted it), not of whatever device is
+    current: the library switches to the tensors' device for the call (csrc/common.cuh DeviceGuard), as the
+    reference's kernels do with a CUDAGuard."""
+    return C.c_void_p(torch.cuda.current_stream(getattr(_tls, "device", None)).cuda_stream)
 
 
 def require_cuda(*tensors):
+    """All tensors of one op must be CUDA tensors on ONE device; remembers that device for stream()."""
+    dev = None
     for t in tensors:
-        if t is not None and not t.is_cuda:
+        if t is None:
+            continue
+        if not t.is_cuda:
             raise AumError("aum_b200 ops need CUDA tensors (there is no CPU fallback)")
+        if dev is None:
+            dev = t.device
+        elif t.device != dev:
+            raise AumError(f"aum_b200 op got tensors on different devices ({dev} and {t.device})")
+    _tls.device = dev

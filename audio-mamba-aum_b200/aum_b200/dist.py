@@ -42,14 +42,22 @@ def shard_range(n_items: int, rank: int, world: int):
 
 
 class FlatGradReducer:
-    """One all-reduce per step over a single flat gradient buffer.
+    """The one collective of the training path: an all-reduce (mean) of ONE flat fp32 gradient buffer.
 
-    Gradients are views into the flat buffer (set once), so backward writes land in it directly and the
-    collective needs no packing copies.  `reduce()` averages over ranks."""
+    Gradients are views into the flat buffer (set once) and the parameters are marked ``_aum_direct_grad``: the engine's
+    backward kernels accumulate straight into the views (aum_b200.autograd), so the collective needs no packing copy
+    and the backward no AccumulateGrad pass.
+
+    Overlap with backward (what DDP's buckets do for the reference, /root/reference/src/traintest.py:39,168): pass the
+    parameters in the order their gradients become final (`AudioMamba.grad_ready_order()`: head first, layer 0 and the
+    embeddings last) together with `chunk_ends`, the element offsets at which a chunk of that order is complete;
+    `hook(k)` returns a tensor hook that launches chunk k's all-reduce on NCCL's stream the moment backward reaches
+    that point, and `reduce()` launches whatever is left and joins.  Without chunk information `reduce()` is a single
+    all-reduce after backward."""
 
     ALIGN = 8      # elements
 
-    def __init__(self, params: Iterable[torch.nn.Parameter]):
+    def __init__(self, params: Iterable[torch.nn.Parameter], chunk_after: Optional[List[int]] = None):
         self.params: List[torch.nn.Parameter] = [p for p in params if p.requires_grad]
         if not self.params:
             raise ValueError("no trainable parameters")
@@ -66,14 +74,61 @@ class FlatGradReducer:
         self.flat = torch.zeros(self.numel, device=dev, dtype=dt)
         for p, o in zip(self.params, self.offsets):
             p.grad = self.flat[o:o + p.numel()].view_as(p)
+            p._aum_direct_grad = True
+        # chunk k = flat[bounds[k] : bounds[k+1]]; chunk_after lists, per chunk but the last, the number of leading
+        # parameters (of the given order) it ends after
+        ends = [self.offsets[i] if i < len(self.offsets) else self.numel for i in (chunk_after or [])]
+        self.bounds = [0] + [e for e in ends if 0 < e < self.numel] + [self.numel]
+        self._launched = 0
+        self._works = []
+        self.async_launches = 0
+
+    @property
+    def n_chunks(self) -> int:
+        return len(self.bounds) - 1
 
     def zero(self):
         self.flat.zero_()
+        self._launched = 0
+        self._works = []
+
+    def _active(self) -> bool:
+        return dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1
+
+    def _launch_upto(self, k_end: int):
+        """All-reduce chunks [launched, k_end) as ONE contiguous slice, asynchronously (NCCL orders it after the
+        kernels already enqueued on the current stream)."""
+        if k_end <= self._launched:
+            return
+        lo, hi = self.bounds[self._launched], self.bounds[k_end]
+        self._launched = k_end
+        if not self._active() or hi <= lo:
+            return
+        sl = self.flat[lo:hi]
+        if dist.get_backend() == "nccl":
+            self._works.append((dist.all_reduce(sl, op=dist.ReduceOp.AVG, async_op=True), None))
+        else:       # gloo (CPU tests) has no AVG
+            self._works.append((dist.all_reduce(sl, op=dist.ReduceOp.SUM, async_op=True), sl))
+        self.async_launches += 1
+
+    def hook(self, k: int):
+        """Tensor hook for the activation whose gradient is computed right after every parameter gradient of chunks
+        0..k is final: launches those chunks' all-reduce while backward continues."""
+        def fire(grad):
+            self._launch_upto(k + 1)
+            return grad
+        return fire
 
     def reduce(self):
-        if dist.is_available() and dist.is_initialized() and dist.get_world_size() > 1:
-            dist.all_reduce(self.flat, op=dist.ReduceOp.SUM)
-            self.flat.div_(dist.get_world_size())
+        """Launch what has not been launched yet, wait for every piece (the current stream waits; the host does not
+        block on NCCL), and return the averaged flat gradient."""
+        self._launch_upto(self.n_chunks)
+        world = dist.get_world_size() if self._active() else 1
+        for w, sl in self._works:
+            w.wait()
+            if sl is not None:
+                sl.div_(world)
+        self._works = []
         return self.flat
 
 
@@ -83,12 +138,18 @@ class FlatAdam:
     Parameters become views into a flat fp32 buffer (same order as the FlatGradReducer's gradient buffer), the two
     moments are flat as well, and `step()` is a single aum_adam_step launch instead of the multi-tensor
     implementation's ~10 passes.  Same update rule and defaults as the reference's recipe
-    (/root/reference/src/traintest.py:32-34).  CUDA only (the product path has no CPU fallback)."""
+    (/root/reference/src/traintest.py:32-34).  CUDA only (the product path has no CPU fallback).
+
+    Mixed precision: bf16 and fp32 activations need no loss scaling.  With fp16 activations pass `grad_scale` = 1 / loss
+    scale and `skip_nonfinite=True`: like accelerate's GradScaler (which the reference's fp16 recipe relies on) the step
+    is skipped - p, m and v untouched - when the flat gradient holds an inf or NaN, and `step()` returns False so the
+    caller can lower its scale."""
 
     def __init__(self, reducer: FlatGradReducer, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
                  weight_decay: float = 0.0):
         self.reducer, self.lr, self.betas, self.eps, self.weight_decay = reducer, lr, tuple(betas), eps, weight_decay
         self.t = 0
+        self.generation = 0          # bumped by every applied step: derived-weight caches / CUDA graphs key on versions
         flat = torch.zeros_like(reducer.flat)
         with torch.no_grad():
             for p, off in zip(reducer.params, reducer.offsets):
@@ -99,22 +160,31 @@ class FlatAdam:
         self.m = torch.zeros_like(flat)
         self.v = torch.zeros_like(flat)
 
-    def step(self, grad_scale: float = 1.0):
-        from . import mixer, ops
+    def step(self, grad_scale: float = 1.0, skip_nonfinite: bool = False) -> bool:
+        from . import ops
+        if skip_nonfinite and not bool(torch.isfinite(self.reducer.flat).all()):     # (one host sync, fp16 recipe only)
+            return False
         self.t += 1
         ops.adam_step(self.flat_p, self.reducer.flat, self.m, self.v, lr=self.lr, betas=self.betas, eps=self.eps,
                       weight_decay=self.weight_decay, step=self.t, grad_scale=grad_scale)
-        # the kernel wrote through a raw pointer: tell autograd's version counters (the derived 16-bit weight copies of
-        # the mixer are revalidated against them)
+        # the kernel wrote through a raw pointer, which autograd's version counters do not see: bump the engine's weight
+        # generation, which every derived-weight cache entry (16-bit copies, -exp(A_log), ...) and every captured CUDA
+        # graph is keyed on, so both are rebuilt before the next forward.  (Version counters are bumped too where torch
+        # exposes that, for third-party observers; nothing here depends on it.)
+        from . import mixer
+        mixer.bump_generation()
         bump = getattr(torch._C, "_increment_version", None)
         if bump is not None:
             try:
                 bump(self.reducer.params)
-            except TypeError:
-                for p in self.reducer.params:
-                    bump(p)
-        else:
-            mixer._cache.clear()
+            except (TypeError, RuntimeError):
+                try:
+                    for p in self.reducer.params:
+                        bump(p)
+                except (TypeError, RuntimeError):
+                    pass
+        self.generation += 1
+        return True
 
     def zero_grad(self):
         self.reducer.zero()

@@ -6,7 +6,9 @@ mamba_inner_fn_no_out_proj (:627-633) and causal_conv1d_fn (pip causal_conv1d, u
 The engine is token-major.  A (B, C, L) argument that is really a transposed view of a token-major buffer
 (stride(1) == 1 — what this package's own Mamba module passes) is used in place; a genuinely channel-major
 tensor (stride(-1) == 1, the reference's layout, :458-459) goes through one aum_transpose launch.
-Forward only for now: these raise under autograd (see aum_b200.autograd).
+Like the reference's autograd.Functions (:14-74, 155-289, 292-434, 437-603) every op here is differentiable: when a
+gradient is required the call is routed through the Functions of aum_b200.autograd (native backward kernels), with
+the layout adapters done by differentiable torch views / copies.
 """
 from __future__ import annotations
 
@@ -18,9 +20,18 @@ from . import _lib as L
 from . import mixer, ops
 
 
-def _no_grad_check(*ts):
-    if torch.is_grad_enabled() and any(t is not None and isinstance(t, torch.Tensor) and t.requires_grad for t in ts):
-        raise NotImplementedError("aum_b200 functional ops are forward-only for now; use torch.no_grad()")
+def _needs_grad(*ts) -> bool:
+    return torch.is_grad_enabled() and any(isinstance(t, torch.Tensor) and t.requires_grad for t in ts)
+
+
+def _tm_grad(t: torch.Tensor, dtype=None) -> torch.Tensor:
+    """(B, C, L) -> token-major (B, L, C) with differentiable torch ops (autograd path)."""
+    tm = t.transpose(1, 2)
+    if dtype is not None and tm.dtype != dtype:
+        tm = tm.to(dtype)
+    if tm.stride(-1) != 1 or (tm.shape[0] > 1 and tm.stride(0) != tm.shape[1] * tm.stride(1)):
+        tm = tm.contiguous()
+    return tm
 
 
 def _to_token_major(t: torch.Tensor, dtype: Optional[torch.dtype] = None) -> torch.Tensor:
@@ -45,9 +56,11 @@ def _is_tm_view(t: torch.Tensor) -> bool:
 
 def causal_conv1d_fn(x, weight, bias=None, activation=None):
     """x: (B, D, L); weight: (D, W); bias: (D,); activation in (None, 'silu', 'swish').  Returns (B, D, L)."""
-    _no_grad_check(x, weight, bias)
     if activation not in (None, "silu", "swish"):
         raise NotImplementedError("activation must be None, silu or swish")
+    if _needs_grad(x, weight, bias):
+        from .autograd import ConvFn
+        return ConvFn.apply(_tm_grad(x), weight, bias, activation is not None).transpose(1, 2)
     view = _is_tm_view(x)
     x_tm = _to_token_major(x)
     y = ops.causal_conv1d(x_tm, mixer._conv_w(weight), mixer._f32(bias) if bias is not None else None,
@@ -59,7 +72,6 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
                       return_last_state=False):
     """u, delta, z: (B, D, L); A: (D, N) real; B, C: (B, N, L) or (B, 1, N, L); D, delta_bias: (D,).
     Returns out (B, D, L) [and last_state (B, D, N)]  (reference :77-83, semantics :86-152)."""
-    _no_grad_check(u, delta, A, B, C, D, z, delta_bias)
     if A.is_complex():
         raise NotImplementedError("complex A is never used by AuM (mamba_simple.py:193)")
     if B.dim() == 4:
@@ -72,6 +84,8 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
         C = C[:, 0]
     if B.dim() != 3 or C.dim() != 3:
         raise NotImplementedError("only input-dependent B/C of shape (B, N, L) are supported (the AuM mode)")
+    if _needs_grad(u, delta, A, B, C, D, z, delta_bias):
+        return _selective_scan_grad(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state)
     view = _is_tm_view(u)
     dt_ = u.dtype
     u_tm = _to_token_major(u)
@@ -91,6 +105,31 @@ def selective_scan_fn(u, delta, A, B, C, D=None, z=None, delta_bias=None, delta_
     return (out, last) if return_last_state else out
 
 
+def _selective_scan_grad(u, delta, A, B, C, D, z, delta_bias, delta_softplus, return_last_state):
+    """selective_scan_fn under autograd (SelectiveScanFn, :14-74): bias + softplus and the layout adapters as
+    differentiable torch ops, the recurrence and its backward on the engine (autograd.ScanFn).  d_state == 16."""
+    from .autograd import ScanFn
+    if A.shape[1] != 16:
+        raise NotImplementedError("the differentiable scan supports d_state == 16 (the AuM configuration)")
+    dt_ = u.dtype
+    d32 = delta.float()
+    if delta_bias is not None:
+        d32 = d32 + delta_bias.float()[None, :, None]
+    if delta_softplus:
+        d32 = torch.nn.functional.softplus(d32)
+    bc = torch.cat([B.float().transpose(1, 2), C.float().transpose(1, 2)], dim=-1).contiguous()      # (B, L, 2N)
+    out_tm = ScanFn.apply(_tm_grad(u), _tm_grad(d32), A.float().contiguous(), bc,
+                          D.float().contiguous() if D is not None else None, _tm_grad(z, dt_) if z is not None else None)
+    out = out_tm.transpose(1, 2)
+    if not return_last_state:
+        return out
+    with torch.no_grad():        # the reference returns last_state without a gradient path as well (:40-42)
+        _, last = selective_scan_fn(u.detach(), delta.detach(), A.detach(), B.detach(), C.detach(),
+                                    D.detach() if D is not None else None, z.detach() if z is not None else None,
+                                    delta_bias.detach() if delta_bias is not None else None, delta_softplus, True)
+    return out, last
+
+
 def _autocast_dtype(x: torch.Tensor) -> torch.dtype:
     return torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else x.dtype
 
@@ -108,7 +147,6 @@ def _inner(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, 
         raise NotImplementedError("delta_softplus=False is never used by the inner ops (mamba_simple.py:212)")
     if A.is_complex():
         raise NotImplementedError("complex A is never used by AuM")
-    _no_grad_check(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, A_b, D, delta_bias)
     act = _autocast_dtype(xz)
     xz_tm = _to_token_major(xz, act)            # (B, L, 2Di)
     Di = xz_tm.shape[-1] // 2
@@ -122,10 +160,31 @@ def _inner(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, 
     return ops.selective_scan(fwd, bwd, xz_tm[..., Di:]), _is_tm_view(xz)
 
 
+def _inner_grad(mode, has_out, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
+                out_proj_bias, A, A_b, D, delta_bias, B, C, B_proj_bias, C_proj_bias, delta_softplus):
+    """The fused inner ops under autograd (BiMambaInnerFn / MambaInnerFn / MambaInnerFnNoOutProj): autograd.InnerFn on a
+    token-major xz; gradients w.r.t. xz come back through the transpose as the reference's dxz (:599)."""
+    from .autograd import InnerCfg, InnerFn
+    if B is not None or C is not None or B_proj_bias is not None or C_proj_bias is not None:
+        raise NotImplementedError("only input-dependent B/C without projection biases (the AuM mode, mamba_simple.py:208-209)")
+    if not delta_softplus:
+        raise NotImplementedError("delta_softplus=False is never used by the inner ops (mamba_simple.py:212)")
+    if A.is_complex():
+        raise NotImplementedError("complex A is never used by AuM")
+    act = _autocast_dtype(xz)
+    xz_tm = _tm_grad(xz, act)
+    cfg = InnerCfg(mode, has_out, 1.0, False)
+    return InnerFn.apply(cfg, xz_tm, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, delta_bias, A, D,
+                         None, None, None, None, None, A_b, None, out_proj_weight, out_proj_bias)
+
+
 def mamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight,
                    out_proj_weight, out_proj_bias, A, B=None, C=None, D=None, delta_bias=None,
                    B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
     """Fo-Fo fused inner op (reference :606-614 / MambaInnerFn.forward :296-365).  xz: (B, 2Di, L) -> (B, L, Dm)."""
+    if _needs_grad(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias, A, D, delta_bias):
+        return _inner_grad("none", True, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
+                           out_proj_bias, A, None, D, delta_bias, B, C, B_proj_bias, C_proj_bias, delta_softplus)
     out_z, _ = _inner(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, None, D, delta_bias,
                       B, C, B_proj_bias, C_proj_bias, delta_softplus, two_dirs=False)
     Bsz, Lq, Di = out_z.shape
@@ -137,6 +196,9 @@ def bimamba_inner_fn(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_w
                      out_proj_weight, out_proj_bias, A, A_b, B=None, C=None, D=None, delta_bias=None,
                      B_proj_bias=None, C_proj_bias=None, delta_softplus=True):
     """Fo-Bi fused inner op (reference :616-624 / BiMambaInnerFn.forward :441-517).  xz: (B, 2Di, L) -> (B, L, Dm)."""
+    if _needs_grad(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight, out_proj_bias, A, A_b, D, delta_bias):
+        return _inner_grad("v1", True, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, out_proj_weight,
+                           out_proj_bias, A, A_b, D, delta_bias, B, C, B_proj_bias, C_proj_bias, delta_softplus)
     out_z, _ = _inner(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, A_b, D, delta_bias,
                       B, C, B_proj_bias, C_proj_bias, delta_softplus, two_dirs=True)
     Bsz, Lq, Di = out_z.shape
@@ -148,6 +210,9 @@ def mamba_inner_fn_no_out_proj(xz, conv1d_weight, conv1d_bias, x_proj_weight, de
                                A, B=None, C=None, D=None, delta_bias=None, B_proj_bias=None, C_proj_bias=None,
                                delta_softplus=True):
     """One Bi-Bi pipeline (reference :627-633 / MambaInnerFnNoOutProj.forward :159-224).  Returns (B, Di, L)."""
+    if _needs_grad(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, D, delta_bias):
+        return _inner_grad("none", False, xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, None, None,
+                           A, None, D, delta_bias, B, C, B_proj_bias, C_proj_bias, delta_softplus).transpose(1, 2)
     out_z, view = _inner(xz, conv1d_weight, conv1d_bias, x_proj_weight, delta_proj_weight, A, None, D, delta_bias,
                          B, C, B_proj_bias, C_proj_bias, delta_softplus, two_dirs=False)
     return _to_channel_major(out_z, view)

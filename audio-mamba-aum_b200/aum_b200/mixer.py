@@ -33,6 +33,21 @@ def _round_up(x: int, m: int) -> int:
     return (x + m - 1) // m * m
 
 
+# Weight generation: bumped by anything that changes parameter VALUES behind autograd's back (the fused Adam kernel
+# writes through raw pointers).  Cache entries and CUDA graphs are keyed on it in addition to the version counters.
+_GENERATION = 0
+
+
+def bump_generation() -> int:
+    global _GENERATION
+    _GENERATION += 1
+    return _GENERATION
+
+
+def generation() -> int:
+    return _GENERATION
+
+
 class _DerivedCache:
     """Derived, read-only views of parameters (16-bit copies, zero-padded copies, A = -exp(A_log)).
     Entries are revalidated against the parameter's version counter and storage pointer, so in-place
@@ -43,7 +58,7 @@ class _DerivedCache:
 
     def get(self, param: torch.Tensor, tag: str, fn):
         key = (id(param), tag)
-        ver = (param._version, param.data_ptr(), param.device, param.dtype)
+        ver = (param._version, param.data_ptr(), param.device, param.dtype, _GENERATION)
         hit = self._d.get(key)
         if hit is not None and hit[0] == ver and hit[2]() is param:
             return hit[1]

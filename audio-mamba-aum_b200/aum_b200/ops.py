@@ -73,6 +73,34 @@ def gemm_tn(a: torch.Tensor, w: torch.Tensor, *, out: Optional[torch.Tensor] = N
     return out
 
 
+def gemm_wgrad(dy: torch.Tensor, x: torch.Tensor, dw: torch.Tensor) -> torch.Tensor:
+    """dw[No, Ki] += dy[T, No]^T @ x[T, Ki]: the weight-gradient reduction over the token axis (aum_gemm_wgrad).
+    dy, x: token-major 2-D (views into wider buffers are fine); dw: fp32, accumulated into (row pitch >= Ki).
+    16-bit operands run the tcgen05 MN-major kernel; fp32 operands (strict-parity tier) are transposed once each and
+    go through the fp32 CUDA-core GEMM, whose result is added to dw."""
+    L.require_cuda(dy, x, dw)
+    T, No, ld_dy = _as_rows(dy)
+    T2, Ki, ld_x = _as_rows(x)
+    if T2 != T or dy.dtype != x.dtype or dw.dtype != torch.float32 or dw.dim() != 2 or tuple(dw.shape) != (No, Ki):
+        raise L.AumError(f"gemm_wgrad: incompatible operands dy{tuple(dy.shape)} x{tuple(x.shape)} dw{tuple(dw.shape)} {dw.dtype}")
+    if dw.stride(1) != 1 and Ki != 1:
+        raise L.AumError("gemm_wgrad: dw rows must be contiguous")
+    if T == 0:
+        return dw
+    ok16 = lambda t, ld: t.data_ptr() % 16 == 0 and (ld * 2) % 16 == 0
+    if dy.dtype in (torch.float16, torch.bfloat16) and ok16(dy, ld_dy) and ok16(x, ld_x):
+        rc = L.lib().aum_gemm_wgrad(L.ptr(dy), ld_dy, L.ptr(x), ld_x, L.dt(dy.dtype), L.ptr(dw),
+                                    dw.stride(0) if No > 1 else max(dw.stride(0), Ki), T, No, Ki, L.stream())
+        L.check(rc, "aum_gemm_wgrad")
+        return dw
+    # fp32 tier / unaligned views: dW = (dy^T)[No, T] @ (x^T)[Ki, T]^T through the K-contiguous GEMM
+    dyT = transpose(dy.reshape(1, T, No) if dy.is_contiguous() else dy.contiguous().view(1, T, No)).view(No, T)
+    xT = transpose(x.reshape(1, T, Ki) if x.is_contiguous() else x.contiguous().view(1, T, Ki)).view(Ki, T)
+    part = gemm_tn(dyT, xT, out_dtype=torch.float32)
+    dw.add_(part)
+    return dw
+
+
 def causal_conv1d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], *, silu: bool = True,
                   reverse: bool = False, out: Optional[torch.Tensor] = None) -> torch.Tensor:
     """x: (B, L, D) token-major (may be a channel slice of a wider buffer); w: (D, W) fp32; bias (D) fp32."""
@@ -145,6 +173,7 @@ def selective_scan(fwd: Optional[ScanDirection], bwd: Optional[ScanDirection], z
     import ctypes as C
     sf = fwd._struct(B, Lq, Dch, N) if fwd is not None else None
     sb = bwd._struct(B, Lq, Dch, N) if bwd is not None else None
+    L.require_cuda(ref.u, out, z, y_pre, fwd.u if fwd is not None else None, bwd.u if bwd is not None else None)
     ldz = _as_rows(z)[2] if z is not None else 0
     if PROFILE is not None:
         ev0 = torch.cuda.Event(enable_timing=True)
@@ -269,6 +298,7 @@ def selective_scan_bwd(fwd: Optional[ScanBwdDirection], bwd: Optional[ScanBwdDir
     ref = fwd if fwd is not None else bwd
     u = ref.t[0]
     B, Lq, Dch = u.shape
+    L.require_cuda(u, z, y_pre, dout, dz, out_z, *(t_ for d_ in (fwd, bwd) if d_ is not None for t_ in d_.t))
     sf = fwd._struct() if fwd is not None else None
     sb = bwd._struct() if bwd is not None else None
     ld = lambda t: _as_rows(t)[2] if t is not None else 0

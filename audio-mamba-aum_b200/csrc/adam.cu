@@ -37,6 +37,7 @@ extern "C" int aum_adam_step(float* p, const float* g, float* m, float* v, int64
                              float lr, float beta1, float beta2, float eps, float weight_decay,
                              int step, float grad_scale, void* stream) {
   using namespace aum;
+  DeviceGuard device_guard(p);
   if (n == 0) return 0;
   AUM_REQUIRE(p && g && m && v, "aum_adam_step: null pointer");
   AUM_REQUIRE(n > 0 && step >= 1, "aum_adam_step: bad size / step (steps count from 1)");

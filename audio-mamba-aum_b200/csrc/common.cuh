@@ -124,4 +124,31 @@ __host__ __device__ inline int ceil_div(int a, int b) { return (a + b - 1) / b; 
 
 inline bool aligned16(const void* p) { return (reinterpret_cast<uintptr_t>(p) & 15) == 0; }
 
+// ---- device handling ----------------------------------------------------------------------------
+// Every entry point runs on the device that owns its output pointer (what at::cuda::CUDAGuard on u.get_device() does
+// in the reference's pybind kernels): if that is not the calling thread's current device, switch for the duration of
+// the call.  Per-device state (cudaFuncSetAttribute done, SM count) is keyed by device ordinal.
+struct DeviceGuard {
+  int prev = -1;
+  explicit DeviceGuard(const void* p) {
+    cudaPointerAttributes a;
+    if (p != nullptr && cudaPointerGetAttributes(&a, p) == cudaSuccess && a.type == cudaMemoryTypeDevice) {
+      int cur = 0;
+      cudaGetDevice(&cur);
+      if (cur != a.device) { prev = cur; cudaSetDevice(a.device); }
+    } else {
+      (void)cudaGetLastError();     // host / unregistered pointer: leave the error state clean, argument checks report it
+    }
+  }
+  ~DeviceGuard() { if (prev >= 0) cudaSetDevice(prev); }
+  DeviceGuard(const DeviceGuard&) = delete;
+  DeviceGuard& operator=(const DeviceGuard&) = delete;
+};
+constexpr int AUM_MAX_DEVICES = 64;
+inline int current_device() { int d = 0; cudaGetDevice(&d); return (d >= 0 && d < AUM_MAX_DEVICES) ? d : 0; }
+template <typename V> struct PerDevice {
+  V v[AUM_MAX_DEVICES] = {};
+  V& cur() { return v[current_device()]; }
+};
+
 }  // namespace aum

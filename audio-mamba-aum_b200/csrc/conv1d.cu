@@ -250,6 +250,7 @@ extern "C" int aum_causal_conv1d_fwd(const void* x, int64_t ldx, const float* w,
                                      void* out, int64_t ldo, int batch, int L, int D, int W,
                                      int dtype, int silu, int reverse, void* stream) {
   using namespace aum;
+  DeviceGuard device_guard(out);
   if (batch == 0 || L == 0 || D == 0) return 0;      // empty input: nothing to do (pointers may be null)
   AUM_REQUIRE(x && w && out, "aum_causal_conv1d_fwd: null pointer");
   AUM_REQUIRE(W >= 2 && W <= CONV_MAXW, "aum_causal_conv1d_fwd: width %d unsupported (2..4)", W);
@@ -413,6 +414,7 @@ extern "C" int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w,
                                      float* dw, float* dbias, int batch, int L, int D, int W,
                                      int dtype, int silu, int reverse, void* stream) {
   using namespace aum;
+  DeviceGuard device_guard(dx);
   AUM_REQUIRE(x && w && dout && dx && dw, "aum_causal_conv1d_bwd: null pointer");
   AUM_REQUIRE(W >= 2 && W <= CONV_MAXW, "aum_causal_conv1d_bwd: width %d unsupported (2..4)", W);
   AUM_REQUIRE(batch >= 0 && L >= 0 && D >= 0, "aum_causal_conv1d_bwd: negative size");

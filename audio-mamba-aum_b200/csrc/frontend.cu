@@ -61,6 +61,7 @@ assemble_tokens_kernel(const float4* __restrict__ tok, const float4* __restrict_
 
 extern "C" int aum_patchify(const float* x, void* cols, int batch, int T_, int F_, int pf, int pt, int dtype, void* stream) {
   using namespace aum;
+  DeviceGuard device_guard(cols);
   if (batch == 0) return 0;
   AUM_REQUIRE(x && cols, "aum_patchify: null pointer");
   AUM_REQUIRE(batch > 0 && pf > 0 && pt > 0 && pt % 4 == 0 && F_ % pf == 0 && T_ % pt == 0,
@@ -81,6 +82,7 @@ extern "C" int aum_patchify(const float* x, void* cols, int batch, int T_, int F
 extern "C" int aum_assemble_tokens(const float* tok, const float* pos, const float* cls, float* hidden,
                                    int batch, int N, int Dm, void* stream) {
   using namespace aum;
+  DeviceGuard device_guard(hidden);
   if (batch == 0) return 0;
   AUM_REQUIRE(tok && pos && cls && hidden, "aum_assemble_tokens: null pointer");
   AUM_REQUIRE(batch > 0 && N > 0 && Dm > 0 && Dm % 4 == 0, "aum_assemble_tokens: Dm must be a multiple of 4");

@@ -8,6 +8,7 @@ extern "C" int aum_gemm_tn(const void* A, int64_t lda, const void* W, int64_t ld
                            const float* bias, const float* row_scale, int act,
                            int backend, void* stream) {
   using namespace aum;
+  DeviceGuard device_guard(C);
   if (M == 0 || N == 0) return 0;                     // empty output: nothing to do (pointers may be null)
   AUM_REQUIRE(A && W && C, "aum_gemm_tn: null pointer");
   AUM_REQUIRE(M >= 0 && N >= 0 && K >= 0, "aum_gemm_tn: negative size");

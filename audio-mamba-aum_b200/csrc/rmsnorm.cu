@@ -126,6 +126,7 @@ extern "C" int aum_add_rmsnorm_fwd(const void* x, int64_t ldx, int x_dtype,
                                    void* residual_out, int64_t ldro, int ro_dtype,
                                    float* rstd_out, int rows, int dim, float eps, void* stream) {
   using namespace aum;
+  DeviceGuard device_guard(y);
   if (rows == 0) return 0;                            // empty input: nothing to do (pointers may be null)
   AUM_REQUIRE(x && weight && y, "aum_add_rmsnorm_fwd: null pointer");
   AUM_REQUIRE(rows >= 0 && dim > 0, "aum_add_rmsnorm_fwd: bad shape rows=%d dim=%d", rows, dim);
@@ -258,6 +259,7 @@ extern "C" int aum_add_rmsnorm_bwd(const void* dy, int64_t ld_dy, int dy_dtype,
                                    void* dx, int64_t ld_dx, float* dresidual_in, int64_t ld_dri,
                                    float* dweight, int rows, int dim, void* stream) {
   using namespace aum;
+  DeviceGuard device_guard(dx);
   AUM_REQUIRE(dy && r && rstd && weight && dx && dweight, "aum_add_rmsnorm_bwd: null pointer");
   AUM_REQUIRE(rows >= 0 && dim > 0, "aum_add_rmsnorm_bwd: bad shape");
   AUM_REQUIRE(dim % 8 == 0 && dim <= 8 * 32 * RN_MAXC, "aum_add_rmsnorm_bwd: dim must be a multiple of 8 and <= %d", 8 * 32 * RN_MAXC);

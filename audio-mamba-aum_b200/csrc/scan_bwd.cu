@@ -311,6 +311,7 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
                                       int batch, int L, int D, int N, int dtype, float out_scale,
                                       int softplus_grad, void* stream) {
   using namespace aum;
+  DeviceGuard device_guard(dout);
   AUM_REQUIRE(fwd || bwd, "aum_selective_scan_bwd: at least one direction is required");
   AUM_REQUIRE(dout, "aum_selective_scan_bwd: null dout");
   AUM_REQUIRE(N == SCAN_NS, "aum_selective_scan_bwd: d_state must be %d", SCAN_NS);
@@ -349,7 +350,8 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
   dim3 grid(ceil_div(D, SB_CH), batch);
   cudaStream_t st = (cudaStream_t)stream;
   const int smem = 2 * (SB_TT + 1) * SCAN_NS * SB_CH * (int)sizeof(float);     // 73 728 B
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_dev;
+  bool& attr_set = attr_set_dev.cur();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(scan_bwd_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);
     if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_bwd_kernel<__half>, cudaFuncAttributeMaxDynamicSharedMemorySize, smem);

@@ -368,7 +368,8 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
 template <typename T>
 static int launch_bt(const ScanBwdMaps& maps, const ScanBwdParams& p, cudaStream_t st) {
   using BL = BwdLayout<T>;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_dev;
+  bool& attr_set = attr_set_dev.cur();
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("aum_selective_scan_bwd: cudaFuncSetAttribute(smem=%d): %s", BL::SMEM_BYTES, cudaGetErrorString(e)); return 2; }

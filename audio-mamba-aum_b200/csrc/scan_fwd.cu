@@ -304,6 +304,7 @@ extern "C" int aum_selective_scan_fwd(const aum_scan_dir_t* fwd, const aum_scan_
                                       int batch, int L, int D, int N, int dtype,
                                       float out_scale, void* y_pre, int64_t ld_ypre, int flags, void* stream) {
   using namespace aum;
+  DeviceGuard device_guard(out);
   AUM_REQUIRE(fwd || bwd, "aum_selective_scan_fwd: at least one direction is required");
   AUM_REQUIRE(out, "aum_selective_scan_fwd: null output");
   AUM_REQUIRE(N >= 1 && N <= SCAN_NS, "aum_selective_scan_fwd: d_state %d unsupported (1..%d)", N, SCAN_NS);

@@ -31,14 +31,14 @@ namespace aum {
 
 constexpr int ST_TT = 8;      // tokens per tile
 
-// Which lane of a (converged) warp does the TMA bookkeeping.  Default (0): lane 0 under `if (lane == 0)` - the build that
-// is validated and measured.  -DAUM_SCAN_ELECT=1 is a round-2 experiment that has NOT been run on a GPU yet: elect.sync,
-// so that ptxas emits the UTMALDG / UTMASTG / UBLKCP of the owner's duties straight instead of wrapping each one in an
-// ELECT / BRA.U.ANY loop (the change that gave the tcgen05 GEMMs' MMA issuer 6 %, and which would shrink the 9-11 KB
-// steady-state loops that now cost 6 % of instruction-cache hit rate).  Every site runs with the warp converged and
-// the full mask, so the elected lane is the same one each time (it owns the bulk async-groups).
+// Which lane of a (converged) warp does the TMA bookkeeping: the one elect.sync picks (default), so that ptxas emits the
+// UTMALDG / UTMASTG / UBLKCP of the owner's duties straight instead of wrapping each one in an ELECT / BRA.U.ANY loop, as it
+// does inside an `if (lane == 0)` region (the same change gave the tcgen05 GEMMs' MMA issuer 6 %).  Measured on B200
+// (profiles/r2_scan_elect_ab.txt): 0.524 -> 0.510 ms per 64-sequence launch, 0.280 -> 0.272 ms per 32-sequence launch,
+// every scan parity test green.  Every site runs with the warp converged and the full mask, so the elected lane is the
+// same one each time (it owns the bulk async-groups).  -DAUM_SCAN_ELECT=0 restores the lane-0 build.
 #ifndef AUM_SCAN_ELECT
-#define AUM_SCAN_ELECT 0
+#define AUM_SCAN_ELECT 1
 #endif
 #if AUM_SCAN_ELECT
 __device__ __forceinline__ bool scan_elect() {
@@ -513,7 +513,8 @@ template <typename T, int NSTG, int CH>
 static int launch_n(const ScanTmaMaps& maps, const ScanParams& p, cudaStream_t st) {
   using SL = StageLayout<T, NSTG, CH>;
   constexpr int MINB = CH <= 128 ? 2 : 1;
-  static bool attr_set = false;
+  static PerDevice<bool> attr_set_dev;
+  bool& attr_set = attr_set_dev.cur();
   // CH = 128: two resident CTAs per SM (128 registers, 90-110 KB of stages each); a 3-CTA / 80-register build measured slower
   if (!attr_set) {
     cudaError_t e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, MINB, NSTG, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);

@@ -53,6 +53,7 @@ extern "C" int aum_transpose(const void* src, int64_t src_bs, int64_t src_ld,
                              void* dst, int64_t dst_bs, int64_t dst_ld,
                              int batch, int R, int C, int src_dtype, int dst_dtype, void* stream) {
   using namespace aum;
+  DeviceGuard device_guard(dst);
   if (batch == 0 || R == 0 || C == 0) return 0;
   AUM_REQUIRE(src && dst, "aum_transpose: null pointer");
   AUM_REQUIRE(batch >= 0 && R >= 0 && C >= 0, "aum_transpose: negative size");

@@ -147,7 +147,7 @@ def reference_clip_forward():
     if "m" not in _REF_MODEL:
         # the reference's per-token ops are small: beyond a few tens of threads intra-op oversubscription makes it SLOWER
         # (measured on the 128-core GPU box, profiles/r2_reference_threads.txt); AUM_REF_THREADS overrides
-        torch.set_num_threads(int(os.environ.get("AUM_REF_THREADS", 0)) or max(1, min(os.cpu_count() or 1, 32)))
+        torch.set_num_threads(int(os.environ.get("AUM_REF_THREADS", 0)) or max(1, min(os.cpu_count() or 1, 16)))
         with warnings.catch_warnings():
             warnings.simplefilter("ignore")
             ns = ref_loader.load_reference_model()
@@ -262,6 +262,112 @@ def run_reference(args, rank):
 
 
 # ------------------------------------------------------------------------------------------------------
+def train_leg(dev, world, dist, rank, steps=6, warmup=3, batch=32):
+    """BASELINE configs[2]: AuM-Base Fo-Bi TRAINING step, bf16 activations, VGGSound-shape inputs (128x1024 mel, 309
+    classes), batch 32 per GPU (256 at 8 GPUs), one process per GPU: forward + backward + the ONE gradient all-reduce
+    (flat fp32 buffer, launched in 3 reverse-layer-order chunks from autograd hooks while backward runs) + fused Adam.
+    Every rank runs it (the all-reduce is the path's only collective); device-timed, max over ranks."""
+    from aum_b200 import _lib
+    from aum_b200.audio_mamba import AudioMamba
+    from aum_b200.trainer import TrainStep
+    torch.manual_seed(SEED)
+    model = AudioMamba(embed_dim=768, depth=24, num_classes=309, bimamba_type="v1", act_dtype=torch.bfloat16).to(dev)
+    g = torch.Generator().manual_seed(SEED + 100 + rank)
+    with torch.no_grad():
+        for blk in model.layers:
+            blk.mixer.A_log.add_(0.1 * torch.randn(blk.mixer.A_log.shape, generator=g).to(dev))
+            blk.mixer.A_b_log.add_(0.1 * torch.randn(blk.mixer.A_b_log.shape, generator=g).to(dev))
+    ts = TrainStep(model, lr=1e-5, n_chunks=3)
+    x = (0.5 * torch.randn(batch, 1024, 128, generator=g)).to(dev)
+    y = (torch.rand(batch, 309, generator=g) > 0.97).float().to(dev)
+
+    def barrier():
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(warmup):
+        ts(x, y)
+    barrier()
+    ts.timing = []
+    l0, a0 = _lib.launch_count(), ts.reducer.async_launches
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for _ in range(steps):
+        loss = ts(x, y)
+    e1.record()
+    barrier()
+    t = torch.tensor([e0.elapsed_time(e1) / steps, sum(a.elapsed_time(b) for a, b in ts.timing) / steps], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms, exposed = t[0].item(), t[1].item()
+    launches = (_lib.launch_count() - l0) // steps
+    pieces = (ts.reducer.async_launches - a0) // steps
+    # what the same all-reduce costs when nothing overlaps it (one piece, after backward)
+    alone = None
+    if dist is not None:
+        barrier()
+        s0, s1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        s0.record()
+        for _ in range(3):
+            dist.all_reduce(ts.reducer.flat, op=dist.ReduceOp.AVG)
+        s1.record()
+        barrier()
+        alone = s0.elapsed_time(s1) / 3
+    out = {"metric": "clips/sec AuM-Base training step (fwd+bwd+grad all-reduce+Adam)", "value": world * batch / (ms / 1e3),
+           "unit": "clips/s", "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "dtype": "bf16",
+           "config": {"workload": f"BASELINE configs[2]: AuM-Base Fo-Bi, depth 24, 309 classes, 128x1024 mel, batch {batch}/GPU "
+                                  f"(global {world * batch}), BCE-with-logits, Adam betas (0.95, 0.999) wd 5e-7, fp32 master weights"},
+           "allreduce": {"bytes": ts.reducer.numel * 4, "pieces_per_step": pieces, "launched_from_backward_hooks": max(pieces - 1, 0),
+                         "exposed_ms": exposed, "alone_ms": alone,
+                         "note": "exposed = device time between the end of backward and the gradient buffer being final"},
+           "gpu_launches": launches, "loss": float(loss), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
+    del ts, model
+    torch.cuda.empty_cache()
+    return out
+
+
+def small_bibi_leg(dev, world, dist, steps=10, warmup=3, batch=32):
+    """BASELINE configs[3]: AuM-Small Bi-Bi (embed 384, depth 24, bimamba v2, if_devide_out) forward, 128x1024 mel,
+    batch 32 per GPU (128 at 4 GPUs), fp16, CUDA-graph replay with two sequence groups - replicas, no collective."""
+    from aum_b200.audio_mamba import AudioMamba
+    torch.manual_seed(SEED)
+    model = AudioMamba(embed_dim=384, depth=24, num_classes=527, bimamba_type="v2", act_dtype=torch.float16,
+                       use_cuda_graph=True, micro_batches=2).to(dev).eval()
+    g = torch.Generator().manual_seed(SEED + 200)
+    with torch.no_grad():
+        for blk in model.layers:
+            blk.mixer.A_log.add_(0.1 * torch.randn(blk.mixer.A_log.shape, generator=g).to(dev))
+            blk.mixer.A_b_log.add_(0.1 * torch.randn(blk.mixer.A_b_log.shape, generator=g).to(dev))
+    x = (0.5 * torch.randn(batch, 1024, 128, generator=g)).to(dev)
+    with torch.no_grad():
+        for _ in range(warmup):
+            model(x)
+        if dist is not None:
+            dist.barrier()
+        torch.cuda.synchronize()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        for _ in range(steps):
+            model(x)
+        e1.record()
+    if dist is not None:
+        dist.barrier()
+    torch.cuda.synchronize()
+    t = torch.tensor([e0.elapsed_time(e1) / steps], device=dev)
+    if dist is not None:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = t.item()
+    n_params = sum(p.numel() for p in model.parameters())
+    del model
+    torch.cuda.empty_cache()
+    return {"metric": "clips/sec AuM-Small Bi-Bi 128x1024 mel fwd", "value": world * batch / (ms / 1e3), "unit": "clips/s",
+            "n_gpus": world, "steps": steps, "warmup": warmup, "ms_per_step": ms, "dtype": "fp16",
+            "config": {"workload": f"BASELINE configs[3]: AuM-Small Bi-Bi forward, depth 24, d_model 384, {n_params} params, "
+                                   f"batch {batch}/GPU (global {world * batch})"}}
+
+
+# ------------------------------------------------------------------------------------------------------
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -273,6 +379,7 @@ def main():
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--micro-batches", type=int, default=2, help="independent sequence groups on separate CUDA streams")
     ap.add_argument("--no-graph", action="store_true", help="launch every kernel from Python instead of replaying a CUDA graph")
+    ap.add_argument("--no-extra", action="store_true", help="skip the training-step (configs[2]) and AuM-Small Bi-Bi (configs[3]) legs")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     rank = int(os.environ.get("RANK", "0"))
@@ -395,21 +502,53 @@ def main():
     mb = args.micro_batches if (args.micro_batches > 1 and B % args.micro_batches == 0 and B >= 2 * args.micro_batches) else 1
     M = (B // mb) * Lq            # rows one scan launch processes (one micro-batch)
     s_act = 2
-    alg_bytes = M * Di * (3 * s_act + 4) + M * 2 * Nst * 4 + 4 * (2 * Di * Nst + Di)
+    # ALGORITHMIC bytes of one fused bidirectional scan launch, SURVEY.md section 8(d):
+    #   s*(4*B*D*L + 2*B*N*L) + 4*(2*D*N + 2*D)   (u, delta, z in, out written, B and C rows; A, A_b, D, delta_bias)
+    # with every activation counted at the activation size s = 2.  This build keeps delta and the packed B|C rows in
+    # fp32 in HBM; the bytes it would need with those counted at 4 bytes are reported next to it, not used for `frac`.
+    alg_bytes = s_act * (4 * M * Di + 2 * M * Nst) + 4 * (2 * Di * Nst + 2 * Di)
+    alg_bytes_fp32_delta = M * Di * (3 * s_act + 4) + M * 2 * Nst * 4 + 4 * (2 * Di * Nst + 2 * Di)
     roof = None
     if scan_ms:
         avg = sum(scan_ms) / len(scan_ms)
         ach = alg_bytes / (avg * 1e-3) / 1e9
-        roof = {"kernel": "scan_fwd_kernel (fused forward+reverse selective scan)", "bound": "hbm", "achieved": ach,
-                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": scan_traffic(B // mb), "peak_source": peak_src,
-                "avg_launch_ms": avg, "launches_timed": len(scan_ms), "algorithmic_bytes_per_launch": alg_bytes,
+        traffic, traffic_src = scan_traffic(B // mb)
+        n_exp = M * Di * Nst * 2
+        roof = {"kernel": "scan_fwd_tma_kernel (fused forward+reverse selective scan)", "bound": "hbm", "achieved": ach,
+                "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
+                "peak_source": peak_src, "avg_launch_ms": avg, "launches_timed": len(scan_ms),
+                "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_formula": "SURVEY 8(d): s*(4BDL+2BNL)+4*(2DN+2D), s=2",
+                "achieved_with_fp32_delta_bytes": alg_bytes_fp32_delta / (avg * 1e-3) / 1e9,
                 "share_of_step": (scan_all_ms / all_ms) if all_ms > 0 else None, "sequences_per_launch": B // mb,
                 # the ceiling that actually binds this kernel: one MUFU.EX2 per (token, channel, state, direction);
                 # peak = 15.8 results/clk/SM measured (profiles/r1_microbench_pipe_rates.txt) x 148 SMs x max SM clock
-                "xu_pipe": {"achieved_Texp_per_s": M * Di * Nst * 2 / (avg * 1e-3) / 1e12,
+                "xu_pipe": {"achieved_Texp_per_s": n_exp / (avg * 1e-3) / 1e12,
                             "peak_Texp_per_s": 15.8 * 148 * 1.965e9 / 1e12,
-                            "frac": (M * Di * Nst * 2 / (avg * 1e-3) / 1e12) / (15.8 * 148 * 1.965e9 / 1e12)},
+                            "frac": (n_exp / (avg * 1e-3) / 1e12) / (15.8 * 148 * 1.965e9 / 1e12)},
                 "note": "16 ex2 per (token,channel,direction): MUFU-bound before HBM-bound (xu_pipe), see DESIGN.md section 5"}
+    # whole-model roofline, SURVEY.md section 8(d): per block s*B*L*(2Dm + 7Di + 2(R+2N)) + s*P_block on the hot path and
+    # B*L*Dm*(4+4+s+s) for the add+RMSNorm either side of it; once per forward the fp32 spectrogram, the patch-embed /
+    # position / head parameters and the logits
+    Dm, depth, R_ = CFG["embed_dim"], CFG["depth"], (CFG["embed_dim"] + 15) // 16
+    p_block = 2 * Di * Dm + Di * 4 + Di + (R_ + 2 * Nst) * Di + Di * R_ + Di + 2 * Di * Nst + Di + Dm * Di + Dm
+    rows = B * Lq
+    bytes_block = s_act * rows * (2 * Dm + 7 * Di + 2 * (R_ + 2 * Nst)) + s_act * p_block
+    bytes_norm = rows * Dm * (4 + 4 + s_act + s_act)
+    bytes_once = B * F_ * T_ * 4 + s_act * (256 * Dm + CFG["num_classes"] * Dm) + 4 * Lq * Dm + B * CFG["num_classes"] * 4
+    model_bytes = depth * (bytes_block + bytes_norm) + bytes_once
+    model_flops = 2.0 * rows * depth * (Dm * 2 * Di + Di * (R_ + 2 * Nst) + R_ * Di + Di * Dm)
+    roof_model = {"bound": "hbm", "algorithmic_bytes_per_step": model_bytes, "achieved": model_bytes / (ms_step * 1e-3) / 1e9,
+                  "peak": peak, "unit": "GB/s", "frac": model_bytes / (ms_step * 1e-3) / 1e9 / peak,
+                  "formula": "SURVEY 8(d): depth*(s*B*L*(2Dm+7Di+2(R+2N)) + s*P_block + B*L*Dm*(8+2s)) + input/embed/head",
+                  "gemm_tflops": model_flops / (ms_step * 1e-3) / 1e12,
+                  "note": "the path's floors are additive unless kernels overlap: HBM ~4.1 ms + tensor ~4.1 ms + MUFU (scan) ~8.9 ms per 64 clips"}
+
+    # ---- the other GPU configurations of BASELINE.json, after the headline measurement (every rank: the training step
+    # holds the path's one collective)
+    train = extra = None
+    if not args.no_extra:
+        train = train_leg(dev, world, dist, rank)
+        extra = [small_bibi_leg(dev, world, dist)]
 
     if rank == 0:
         cpu = None
@@ -426,7 +565,8 @@ def main():
                "e2e": {"value": e2e_value, "unit": UNIT, "h2d_bytes_per_step": x_host.numel() * 4,
                        "d2h_bytes_per_step": logits_host.numel() * 4},
                "gpu_launches": launches, "launch_mode": "eager" if args.no_graph else "cuda-graph replay of the same launches",
-               "roofline": roof, "cpu_baseline": cpu, "clocks": clocks}
+               "roofline": roof, "roofline_model": roof_model, "cpu_baseline": cpu, "clocks": clocks,
+               "train": train, "extra": extra}
         print(json.dumps(out), flush=True)
     if dist is not None:
         dist.destroy_process_group()

@@ -73,6 +73,21 @@ AUM_API int aum_gemm_tn(const void* A, int64_t lda, const void* W, int64_t ldw, 
                 int backend, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
+ * Weight-gradient products of the projections:  dW[No, Ki] += dY[T, No]^T @ X[T, Ki]   (ACCUMULATES: zero dW first,
+ * or point it into the trainer's flat gradient buffer).
+ *   replaces the reductions over the token axis in BiMambaInnerFn / MambaInnerFn / MambaInnerFnNoOutProj .backward:
+ *   d(out_proj.weight) = einsum("eB,dB->ed", dout, out_z)  (selective_scan_interface.py:563, :395, :254-256 caller),
+ *   d(dt_proj.weight)  = einsum("dB,Br->dr", ddelta, x_dbl[:, :R])  (:586, :417, :273),
+ *   d(x_proj.weight)   = einsum("Br,Bd->rd", dx_dbl, conv1d_out)    (:589, :420, :276),
+ *   and autograd's d(in_proj.weight) of the matmul at mamba_simple.py:185-189.
+ *   dY, X: fp16 / bf16 token-major rows (16-byte aligned bases and row pitches); dW fp32 with ld_dw >= Ki.
+ *   tcgen05 with MN-major operand descriptors (no transposed copies), split-K over tokens with fp32 atomic adds:
+ *   the summation ORDER of the partial sums is not deterministic (every addend is).
+ * ------------------------------------------------------------------------------------------- */
+AUM_API int aum_gemm_wgrad(const void* dY, int64_t ld_dy, const void* X, int64_t ld_x, int ab_dtype,
+                   float* dW, int64_t ld_dw, int T, int No, int Ki, void* stream);
+
+/* ---------------------------------------------------------------------------------------------
  * Depthwise causal conv1d (+bias, +SiLU) along the token axis.
  *   replaces causal_conv1d_cuda.causal_conv1d_fwd(x, w, bias, None, silu)
  *   (selective_scan_interface.py:177,239,318,380,463,532) and causal_conv1d_fn (:646,:683).

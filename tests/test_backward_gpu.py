@@ -284,3 +284,118 @@ def test_audio_mamba_training_step_matches_oracle_autograd():
         ref = ref_p[n].grad
         err = (p.grad.cpu() - ref).abs().max().item()
         assert err <= 2e-3 * max(ref.abs().max().item(), 1e-6) + 1e-7, (n, err, ref.abs().max().item())
+
+
+# ----------------------------------------------------------------------------------------------------
+# The reference's functional ops are autograd.Functions (selective_scan_interface.py:14-74, 155-289, 292-434, 437-603):
+# the shim's are differentiable too, with the reference's (batch, channel, length) layouts.
+def _fn_params(Dm, g, bt="v1"):
+    p = O.make_mamba_params(Dm, bimamba_type=bt, seed=77, perturb_A=0.1)
+    return {k: v.clone() for k, v in p.items()}
+
+
+@pytest.mark.parametrize("which", ["bimamba_inner_fn", "mamba_inner_fn", "mamba_inner_fn_no_out_proj"])
+@pytest.mark.parametrize("channel_major", [True, False])
+def test_functional_inner_ops_backward_vs_oracle_autograd(which, channel_major):
+    import mamba_ssm.ops.selective_scan_interface as F_
+    Dm, Lq, B = 64, 37, 2
+    Di = 2 * Dm
+    g = gen(21)
+    p = _fn_params(Dm, g)
+    xz0 = rnd((B, 2 * Di, Lq), g)
+    G = rnd((B, Lq, Dm), g) if which != "mamba_inner_fn_no_out_proj" else rnd((B, Di, Lq), g)
+    names = ["conv1d.weight", "conv1d.bias", "x_proj.weight", "dt_proj.weight", "out_proj.weight", "A_log", "A_b_log", "D",
+             "dt_proj.bias"]
+
+    def run(dev, fns):
+        q = {k: p[k].clone().to(dev).requires_grad_() for k in names}
+        if channel_major or dev == "cpu":
+            xz = xz0.clone().to(dev).requires_grad_()
+            xz_arg = xz
+        else:       # a transposed view of a token-major buffer (what this package's own module passes)
+            xz = xz0.transpose(1, 2).contiguous().to(dev).requires_grad_()
+            xz_arg = xz.transpose(1, 2)
+        A, A_b = -torch.exp(q["A_log"]), -torch.exp(q["A_b_log"])
+        if which == "bimamba_inner_fn":
+            out = fns[0](xz_arg, q["conv1d.weight"], q["conv1d.bias"], q["x_proj.weight"], q["dt_proj.weight"],
+                         q["out_proj.weight"], None, A, A_b, None, None, q["D"], q["dt_proj.bias"])
+        elif which == "mamba_inner_fn":
+            out = fns[1](xz_arg, q["conv1d.weight"], q["conv1d.bias"], q["x_proj.weight"], q["dt_proj.weight"],
+                         q["out_proj.weight"], None, A, None, None, q["D"], q["dt_proj.bias"])
+        else:
+            out = fns[2](xz_arg, q["conv1d.weight"], q["conv1d.bias"], q["x_proj.weight"], q["dt_proj.weight"],
+                         A, None, None, q["D"], q["dt_proj.bias"])
+        (out * G.to(dev)).sum().backward()
+        gx = xz.grad if (channel_major or dev == "cpu") else xz.grad.transpose(1, 2)
+        return out.detach().cpu(), gx.cpu(), {k: (v.grad.cpu() if v.grad is not None else None) for k, v in q.items()}
+
+    oracle = (lambda *a: O.bimamba_inner_oracle(*a[:7], a[7], a[8], a[11], a[12]),
+              lambda *a: O.mamba_inner_oracle(*a[:7], a[7], a[10], a[11]),
+              lambda *a: O.mamba_inner_no_out_proj_oracle(*a[:5], a[5], a[8], a[9]))
+    out_r, gx_r, gr = run("cpu", oracle)
+    out_d, gx_d, gd = run(DEV, (F_.bimamba_inner_fn, F_.mamba_inner_fn, F_.mamba_inner_fn_no_out_proj))
+    torch.testing.assert_close(out_d, out_r, rtol=1e-4, atol=1e-5)
+    _close(gx_d, gx_r, 5e-4, 5e-5, "dxz")
+    for k in names:
+        if gr[k] is None:
+            assert gd[k] is None or gd[k].abs().max() == 0, k
+            continue
+        _close(gd[k], gr[k], 1e-3, 1e-4, k)
+
+
+def test_functional_selective_scan_fn_and_conv_backward_vs_oracle_autograd():
+    import mamba_ssm.ops.selective_scan_interface as F_
+    from causal_conv1d import causal_conv1d_fn
+    g = gen(22)
+    B, D, Lq, N = 2, 48, 29, 16
+    base = dict(u=rnd((B, D, Lq), g), delta=0.5 * rnd((B, D, Lq), g),
+                A=-torch.exp(torch.log(torch.arange(1, N + 1.0)).repeat(D, 1) + 0.1 * rnd((D, N), g)),
+                Bm=rnd((B, N, Lq), g), Cm=rnd((B, N, Lq), g), Dv=1 + 0.1 * rnd((D,), g), z=rnd((B, D, Lq), g),
+                bias=0.5 * rnd((D,), g) - 1.0)
+    G = rnd((B, D, Lq), g)
+
+    def run(dev, fn, use_z):
+        q = {k: v.clone().to(dev).requires_grad_() for k, v in base.items()}
+        out = fn(q["u"], q["delta"], q["A"], q["Bm"], q["Cm"], q["Dv"], q["z"] if use_z else None, q["bias"], True)
+        (out * G.to(dev)).sum().backward()
+        return out.detach().cpu(), {k: (v.grad.cpu() if v.grad is not None else None) for k, v in q.items()}
+
+    for use_z in (True, False):
+        out_r, gr = run("cpu", lambda u, d, A, Bm, Cm, Dv, z, b, sp: O.selective_scan_oracle(u, d, A, Bm, Cm, Dv, z, b, sp), use_z)
+        out_d, gd = run(DEV, F_.selective_scan_fn, use_z)
+        torch.testing.assert_close(out_d, out_r, rtol=1e-4, atol=2e-5)
+        for k in base:
+            if k == "z" and not use_z:
+                continue
+            _close(gd[k], gr[k], 5e-4, 5e-5, f"scan d{k} (z={use_z})")
+    # causal_conv1d_fn
+    x, w, b = rnd((B, D, Lq), g), rnd((D, 4), g, 0.5), rnd((D,), g, 0.5)
+    xr, wr, br = (t.clone().requires_grad_() for t in (x, w, b))
+    (O.causal_conv1d_oracle(xr, wr, br, True) * G).sum().backward()
+    xd, wd, bd = (t.clone().to(DEV).requires_grad_() for t in (x, w, b))
+    (causal_conv1d_fn(xd, wd, bd, "silu") * G.to(DEV)).sum().backward()
+    _close(xd.grad, xr.grad, 1e-4, 1e-5, "conv dx")
+    _close(wd.grad, wr.grad, 1e-4, 1e-5, "conv dw")
+    _close(bd.grad, br.grad, 1e-4, 1e-5, "conv db")
+
+
+def test_direct_gradient_accumulation_into_a_flat_buffer():
+    """FlatGradReducer marks parameters for in-place gradient accumulation: the kernels write straight into the flat
+    buffer (no temporaries, no AccumulateGrad) and the result equals the autograd-delivered gradients."""
+    from aum_b200.audio_mamba import AudioMamba
+    from aum_b200.dist import FlatGradReducer
+    torch.manual_seed(11)
+    kw = dict(embed_dim=192, depth=2, num_classes=35, spectrogram_size=(128, 128), bimamba_type="v1", act_dtype=torch.bfloat16)
+    a = AudioMamba(**kw).to(DEV)
+    b = AudioMamba(**kw).to(DEV)
+    b.load_state_dict(a.state_dict())
+    x = 0.5 * torch.randn(3, 128, 128, device=DEV)
+    tgt = (torch.rand(3, 35, device=DEV) > 0.7).float()
+    torch.nn.functional.binary_cross_entropy_with_logits(a(x), tgt).backward()
+    red = FlatGradReducer(b.parameters())
+    red.zero()
+    torch.nn.functional.binary_cross_entropy_with_logits(b(x), tgt).backward()
+    for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
+        assert pb.grad.data_ptr() >= red.flat.data_ptr() and pb.grad.data_ptr() < red.flat.data_ptr() + red.flat.numel() * 4, n
+        scale = max(pa.grad.abs().max().item(), 1e-9)
+        assert (pa.grad - pb.grad).abs().max().item() <= 2e-2 * scale, (n, scale)

@@ -41,6 +41,24 @@ def _worker(rank, world, port, ret):
     assert (red.flat[pad] == 0).all()
     red.zero()
     assert all((p.grad == 0).all() for p in lin.parameters())
+    # chunked, overlapped form: parameters in gradient-ready order (last layer first), the first chunk's all-reduce
+    # launched from a tensor hook in the middle of backward, the rest by reduce(); same averaged gradients
+    torch.manual_seed(0)
+    l1, l2 = torch.nn.Linear(5, 7), torch.nn.Linear(7, 3)
+    order = list(l2.parameters()) + list(l1.parameters())
+    red2 = D.FlatGradReducer(order, chunk_after=[2])
+    assert red2.n_chunks == 2 and red2.bounds[1] == red2.offsets[2]
+    h = l1(x)
+    h.register_hook(red2.hook(0))          # backward passes here once l2's gradients are final
+    l2(h).sum().backward()
+    assert red2.async_launches == 1        # chunk 0 went out during backward
+    red2.reduce()
+    assert red2.async_launches == 2
+    packed2 = torch.cat([red2.flat[o:o + p.numel()] for p, o in zip(red2.params, red2.offsets)])
+    ref_order = torch.cat([mean_part for mean_part in (
+        torch.cat([packed[sum(q.numel() for q in list(lin.parameters())[:i]):][:p_.numel()]
+                   for i, p_ in enumerate(lin.parameters()) if i in idx]) for idx in ((2, 3), (0, 1)))])
+    torch.testing.assert_close(packed2, ref_order)
     dist.destroy_process_group()
     ret[rank] = 1
 
