@@ -81,6 +81,9 @@ SIGNATURES = {
                                  C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "aum_causal_conv1d_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
+    "aum_conv_xproj_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                     C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
+                                     C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "aum_selective_scan_fwd": (C.c_int, [C.POINTER(ScanDir), C.POINTER(ScanDir), C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_void_p, C.c_int64, C.c_int, C.c_void_p]),

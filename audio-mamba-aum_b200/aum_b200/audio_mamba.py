@@ -267,6 +267,49 @@ class AudioMamba(nn.Module):
             v += p_._version + (p_.data_ptr() & 0xffff)
         return v
 
+    @torch.no_grad()
+    def infer_stream(self, batches, return_features: bool = False):
+        """Streaming inference over an iterable of HOST batches (pinned (B, T, F) fp32 tensors of one shape): yields the
+        logits of each batch as a device tensor.  The host->device copy of batch i+1 runs on a copy stream while batch
+        i's forward (CUDA-graph replay when use_cuda_graph) runs on the current stream, through two device staging
+        buffers - so the transfer is off the critical path, which a plain ``model(x_host)`` call per batch cannot do."""
+        it = iter(batches)
+        try:
+            nxt = next(it)
+        except StopIteration:
+            return
+        dev = self.cls_token.device
+        cur = torch.cuda.current_stream(dev)
+        copy_stream = torch.cuda.Stream(device=dev)
+        stg = [torch.empty(nxt.shape, device=dev, dtype=nxt.dtype) for _ in range(2)]
+        copied = [torch.cuda.Event() for _ in range(2)]
+        consumed = [torch.cuda.Event() for _ in range(2)]
+
+        def issue(i, xh):
+            copy_stream.wait_event(consumed[i])          # the forward that read this staging buffer has been enqueued and done
+            with torch.cuda.stream(copy_stream):
+                stg[i].copy_(xh, non_blocking=True)
+                copied[i].record(copy_stream)
+
+        for e in consumed:
+            e.record(cur)
+        issue(0, nxt)
+        i = 0
+        while nxt is not None:
+            try:
+                after = next(it)
+            except StopIteration:
+                after = None
+            if after is not None:
+                if after.shape != nxt.shape or after.dtype != nxt.dtype:
+                    raise ValueError("infer_stream: every batch must have the same shape and dtype")
+                issue(i ^ 1, after)
+            cur.wait_event(copied[i])
+            out = self.forward(stg[i], return_features)   # (graph path: one device-to-device copy into the captured input)
+            consumed[i].record(cur)
+            yield out
+            nxt, i = after, i ^ 1
+
     def forward(self, x: torch.Tensor, return_features: bool = False) -> torch.Tensor:
         if torch.is_grad_enabled() and any(p.requires_grad for p in self.parameters()):
             return self._forward_train(x, return_features)

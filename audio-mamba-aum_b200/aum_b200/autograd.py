@@ -115,11 +115,14 @@ def _branch_fwd(xz, Di, N, cw, cb, xw, dtw, dtb, reverse, act):
     M = B * Lq
     R = dtw.shape[1]
     Rpad = mixer._round_up(R, 8)
-    u = ops.causal_conv1d(xz[..., :Di], mixer._conv_w(cw), mixer._f32(cb) if cb is not None else None,
-                          silu=True, reverse=reverse)
     dt = torch.empty((M, Rpad), device=xz.device, dtype=act)
     bc = torch.empty((M, 2 * N), device=xz.device, dtype=F32)
-    ops.gemm_tn(u.view(M, Di), mixer._w(xw, act), out=dt, out2=bc, split=R)
+    cw_, cb_, wx = mixer._conv_w(cw), (mixer._f32(cb) if cb is not None else None), mixer._w(xw, act)
+    if mixer._FUSE_CONV_XPROJ and ops.conv_xproj_eligible(xz[..., :Di], cw_, wx, R, 2 * N):
+        u = ops.conv_xproj(xz[..., :Di], cw_, cb_, wx, R, dt, bc, reverse=reverse)
+    else:
+        u = ops.causal_conv1d(xz[..., :Di], cw_, cb_, silu=True, reverse=reverse)
+        ops.gemm_tn(u.view(M, Di), wx, out=dt, out2=bc, split=R)
     delta = ops.gemm_tn(dt, mixer._w(dtw, act, pad_cols=Rpad), k=R,
                         bias=mixer._f32(dtb) if dtb is not None else None, act=L.ACT_SOFTPLUS, out_dtype=F32)
     return u, delta.view(B, Lq, Di), dt, bc.view(B, Lq, 2 * N)

@@ -27,6 +27,7 @@ from . import ops
 
 
 _PREGATE_Z = os.environ.get("AUM_PREGATE_Z", "1") == "1"
+_FUSE_CONV_XPROJ = os.environ.get("AUM_FUSE_CONV_XPROJ", "1") == "1"
 
 
 def _round_up(x: int, m: int) -> int:
@@ -113,11 +114,16 @@ def _pipeline(xz: torch.Tensor, Di: int, N: int, conv_w, conv_b, x_proj_w, dt_pr
     act = xz.dtype
     R = dt_proj_w.shape[1]
     x = xz[..., :Di]
-    u = ops.causal_conv1d(x, _conv_w(conv_w), _f32(conv_b) if conv_b is not None else None, silu=True, reverse=reverse)
     Rpad = _round_up(R, 8)
     dt = torch.empty((M, Rpad), device=xz.device, dtype=act)
     bc = torch.empty((M, 2 * N), device=xz.device, dtype=torch.float32)
-    ops.gemm_tn(u.view(M, Di), _w(x_proj_w, act), out=dt, out2=bc, split=R, backend=backend)
+    cw, cb, wx = _conv_w(conv_w), (_f32(conv_b) if conv_b is not None else None), _w(x_proj_w, act)
+    if _FUSE_CONV_XPROJ and backend != L.GEMM_SIMT and ops.conv_xproj_eligible(x, cw, wx, R, 2 * N):
+        # conv + SiLU as the producer of x_proj's tensor-core operand: one launch, x read once (:463 + :467)
+        u = ops.conv_xproj(x, cw, cb, wx, R, dt, bc, reverse=reverse)
+    else:
+        u = ops.causal_conv1d(x, cw, cb, silu=True, reverse=reverse)
+        ops.gemm_tn(u.view(M, Di), wx, out=dt, out2=bc, split=R, backend=backend)
     delta = ops.gemm_tn(dt, _w(dt_proj_w, act, pad_cols=Rpad), k=R, bias=_f32(dt_bias), act=L.ACT_SOFTPLUS,
                         out_dtype=delta_dtype, backend=backend)
     bc3 = bc.view(B, Lq, 2 * N)

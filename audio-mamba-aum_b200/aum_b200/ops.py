@@ -120,6 +120,37 @@ def causal_conv1d(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor]
     return out
 
 
+def conv_xproj_eligible(x: torch.Tensor, conv_w: torch.Tensor, wx: torch.Tensor, R: int, N2: int) -> bool:
+    """Shapes / dtypes / alignments the fused conv + x_proj kernel takes (everything AuM-Small and AuM-Base produce)."""
+    if x.dtype not in (torch.float16, torch.bfloat16) or wx.dtype != x.dtype or conv_w.shape[-1] != 4:
+        return False
+    Di = x.shape[-1]
+    ldx = _as_rows(x)[2]
+    return (R % 8 == 0 and R + N2 <= 128 and Di % 8 == 0 and x.data_ptr() % 16 == 0 and (ldx * 2) % 16 == 0
+            and wx.is_contiguous() and wx.data_ptr() % 16 == 0)
+
+
+def conv_xproj(x: torch.Tensor, conv_w: torch.Tensor, conv_b: Optional[torch.Tensor], wx: torch.Tensor, R: int,
+               dt: torch.Tensor, bc: torch.Tensor, *, reverse: bool = False, u: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """u = silu(causal_conv1d(x) + b) and u @ wx^T -> dt[:, :R] (16-bit) | bc (fp32) in ONE launch (aum_conv_xproj_fwd).
+    x: (B, L, Di) token-major view; conv_w (Di, 4) fp32; wx (R + N2, Di) in x's dtype; returns u (B, L, Di)."""
+    L.require_cuda(x, conv_w, wx, dt, bc)
+    B, Lq, Di = x.shape
+    ldx = _as_rows(x)[2]
+    N2 = wx.shape[0] - R
+    if u is None:
+        u = torch.empty((B, Lq, Di), device=x.device, dtype=x.dtype)
+    if conv_w.dtype != torch.float32 or not conv_w.is_contiguous() or tuple(conv_w.shape) != (Di, 4):
+        raise L.AumError("conv_xproj: conv weight must be contiguous fp32 (Di, 4)")
+    if bc.dtype != torch.float32 or dt.dtype != x.dtype or bc.shape[-1] < N2 or dt.shape[-1] < R:
+        raise L.AumError("conv_xproj: dt must have x's dtype and >= R columns, bc fp32 with >= N2 columns")
+    rc = L.lib().aum_conv_xproj_fwd(L.ptr(x), ldx, L.ptr(conv_w), L.ptr(conv_b), L.ptr(wx), wx.stride(0),
+                                    L.ptr(u), _as_rows(u)[2], L.ptr(dt), _as_rows(dt)[2], L.ptr(bc), _as_rows(bc)[2],
+                                    B, Lq, Di, R, N2, L.dt(x.dtype), int(reverse), L.stream())
+    L.check(rc, "aum_conv_xproj_fwd")
+    return u
+
+
 class ScanDirection:
     """One time direction of the scan (struct aum_scan_dir).  All tensors token-major:
     u, delta: (B, L, D); A: (D, N) fp32; Bm, Cm: (B, L, N); D, delta_bias: (D,) fp32 or None."""

@@ -1,0 +1,342 @@
+// Fused  x --causal conv1d + bias + SiLU--> u --x_proj--> (dt | B | C)   for sm_100a (16-bit activations).
+//
+// Reference ops replaced, one launch instead of two and one pass over x instead of a write + re-read of u:
+//   conv1d_out = causal_conv1d_cuda.causal_conv1d_fwd(x, w, b, None, True)      selective_scan_interface.py:463 (:177,:318)
+//   x_dbl      = F.linear(rearrange(conv1d_out, 'b d l -> (b l) d'), x_proj_weight)                          :467 (:181,:322)
+// (BASELINE.json's north star asks for the depthwise conv + SiLU to be fused into the kernel that consumes it; the
+// consumer that needs a full cross-channel reduction of u is x_proj, so the conv is the PRODUCER of x_proj's A operand.
+// u is still written once, because the scan reads it.)
+//
+// One persistent CTA per SM walks 128-token tiles; per tile it loops over the Di channels in blocks of 64:
+//   warp 0      TMA producer: the raw x rows of the block (128 tokens + 3 halo rows x 64 channels, un-swizzled) and the
+//               x_proj weight block W_x[:, 64 channels] (K-major, 128-byte swizzle) into a 4-stage ring.
+//   warps 2..9  conv: each thread takes 8 channels x 4 tokens: 7 LDS.128 of raw rows, 4 taps as fp32 FMAs, bias, SiLU
+//               (ftz MUFU), and writes the 16-bit results into the stage's A tile in the 128-byte-swizzled K-major layout
+//               the tensor core reads.  One elected thread then (a) publishes the tile to the MMA warp and (b) sends the
+//               SAME tile to HBM as u with one bulk tensor store.
+//   warp 1      tcgen05.mma 128 x NB x 16 (NB = 96 for AuM-Base's 80 outputs), accumulating over all channel blocks in
+//               TMEM; tcgen05.commit frees the stage.
+//   epilogue    (conv warps 2..5, lane = token row): TMEM -> registers -> dt (16-bit, first R columns) | [B|C] (fp32).
+// Sequence boundaries: the halo rows of a token near the start (causal) or end (anti-causal, Bi-Bi's second branch) of
+// its sequence belong to the neighbouring sequence or lie outside the tensor: those taps are masked.
+#include <cuda.h>
+#include <stdlib.h>
+
+#include "gemm_common.cuh"
+#include "tcgen05_ptx.cuh"
+#include "tma.cuh"
+
+namespace aum {
+
+constexpr int CX_BM = 128;                 // tokens per tile
+constexpr int CX_BK = 64;                  // channels per block (128 B of 16-bit)
+constexpr int CX_HALO = 3;                 // d_conv - 1
+constexpr int CX_RAW_ROWS = CX_BM + CX_HALO;
+constexpr int CX_RAW_BYTES = 17 * 1024;    // 131 rows x 128 B = 16768, padded to keep 1024-byte alignment of what follows
+constexpr int CX_A_BYTES = CX_BM * 128;    // 16 KB, 128-byte swizzled
+constexpr int CX_STAGES = 4;
+constexpr int CX_CONV_WARPS = 8;
+constexpr int CX_THREADS = 64 + 32 * CX_CONV_WARPS;
+constexpr int CX_BAR_ID = 3;               // named barrier of the conv warps
+
+template <int NB> struct CxCfg {
+  static constexpr int W_BYTES = NB * 128;
+  static constexpr int STAGE_BYTES = CX_RAW_BYTES + W_BYTES + CX_A_BYTES;
+  static constexpr int SMEM_BYTES = CX_STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int TMEM_COLS = NB <= 32 ? 32 : NB <= 64 ? 64 : 128;
+  static_assert(NB % 16 == 0 && NB >= 16 && NB <= 128, "UMMA N");
+  static_assert(W_BYTES % 1024 == 0 || NB % 8 == 0, "");
+};
+
+struct CxParams {
+  const float* cw; const float* cb;        // conv weight (Di, 4) fp32, bias (Di) fp32 or null
+  void* dt; int64_t ld_dt; int dt_dt;      // (M, >= R) activation dtype
+  float* bc; int64_t ld_bc;                // (M, 2N) fp32
+  int M, L, Di, R, Nout;                   // Nout = R + 2N
+  int reverse;
+};
+
+__device__ __forceinline__ void conv_bar() { asm volatile("bar.sync %0, %1;" ::"n"(CX_BAR_ID), "n"(32 * CX_CONV_WARPS) : "memory"); }
+__device__ __forceinline__ uint4 lds_u4(uint32_t a) {
+  uint4 v; asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
+}
+template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t v);
+template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
+template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
+template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b);
+template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
+
+template <typename T, int NB>
+__global__ void __launch_bounds__(CX_THREADS, 1)
+conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
+                  const __grid_constant__ CUtensorMap tmU, const CxParams p, uint32_t idesc) {
+  using Cfg = CxCfg<NB>;
+  extern __shared__ uint8_t smem_raw[];
+  const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
+  const uint32_t bar_base = smem_base + CX_STAGES * Cfg::STAGE_BYTES;
+  auto raw_full = [&](int s) { return bar_base + 8u * s; };                     // TMA: raw x rows + W block landed
+  auto a_full = [&](int s) { return bar_base + 8u * (CX_STAGES + s); };         // conv: A tile written
+  auto st_free = [&](int s) { return bar_base + 8u * (2 * CX_STAGES + s); };    // MMA: stage consumed
+  const uint32_t tfull = bar_base + 8u * (3 * CX_STAGES);
+  const uint32_t tempty = bar_base + 8u * (3 * CX_STAGES + 1);
+  const uint32_t tmem_slot = bar_base + 8u * (3 * CX_STAGES + 2);
+  auto s_raw = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
+  auto s_w = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + CX_RAW_BYTES; };
+  auto s_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + CX_RAW_BYTES + Cfg::W_BYTES; };
+
+  const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+  const int n_tiles = (p.M + CX_BM - 1) / CX_BM;
+  const int k_blocks = (p.Di + CX_BK - 1) / CX_BK;
+
+  if (warp == 0 && lane == 0) {
+    for (int s = 0; s < CX_STAGES; ++s) { mbar_init(raw_full(s), 1); mbar_init(a_full(s), 1); mbar_init(st_free(s), 1); }
+    mbar_init(tfull, 1); mbar_init(tempty, 128);
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+    asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+  }
+  if (warp == 1) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(tmem_slot), "n"(Cfg::TMEM_COLS) : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+  }
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  uint32_t tmem_base;
+  asm volatile("ld.shared.b32 %0, [%1];" : "=r"(tmem_base) : "r"(tmem_slot));
+
+  if (warp == 0) {
+    // ================= TMA producer =================
+    if (lane == 0) {
+      int stage = 0; uint32_t phase = 0;
+      for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+        const int m0 = tile * CX_BM;
+        // causal: rows [m0 - 3, m0 + 128); anti-causal: rows [m0, m0 + 131).  Out-of-range rows are zero-filled.
+        const int row0 = p.reverse ? m0 : m0 - CX_HALO;
+        for (int kb = 0; kb < k_blocks; ++kb) {
+          mbar_wait(st_free(stage), phase ^ 1u);
+          mbar_arrive_expect_tx(raw_full(stage), CX_RAW_ROWS * 128 + Cfg::W_BYTES);
+          tma_load_2d(s_raw(stage), &tmX, kb * CX_BK, row0, raw_full(stage));
+          tma_load_2d(s_w(stage), &tmW, kb * CX_BK, 0, raw_full(stage));
+          if (++stage == CX_STAGES) { stage = 0; phase ^= 1u; }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ================= MMA issuer =================
+    int stage = 0; uint32_t phase = 0, tphase = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      mbar_wait(tempty, tphase ^ 1u);                 // epilogue of the previous tile has drained the accumulator
+      tc_fence_after();
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        mbar_wait(a_full(stage), phase);
+        tc_fence_after();
+        const uint64_t da = make_smem_desc_sw128(s_a(stage));
+        const uint64_t db = make_smem_desc_sw128(s_w(stage));
+        if (elect_one()) {
+#pragma unroll
+          for (int k = 0; k < CX_BK / 16; ++k)
+            tc_mma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
+          tc_commit(st_free(stage));
+          if (kb == k_blocks - 1) tc_commit(tfull);
+        }
+        __syncwarp();
+        if (++stage == CX_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      tphase ^= 1u;
+    }
+  } else {
+    // ================= conv warps (2..9) + epilogue (2..5) =================
+    const int ct = threadIdx.x - 64;                  // 0..255
+    const int cg = ct & 7;                            // 8-channel group inside the 64-channel block (16 B)
+    const int tr = ct >> 3;                           // 0..31: tokens 4 tr .. 4 tr + 3 of the tile
+    const bool leader = ct == 0;
+    int stage = 0; uint32_t phase = 0, tphase = 0;
+    int pending_stores = 0;
+    for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = tile * CX_BM;
+      // position of this thread's first token in its sequence, and the per-token edge masks (bit j of mask[i]: tap row
+      // j of token i is valid).  Causal: tap row j of a token at position l holds x[l - 3 + j]; anti-causal: x[l + j].
+      int l0 = (m0 + 4 * tr) % p.L;
+      uint32_t mask[4];
+      bool edge = false;
+#pragma unroll
+      for (int i = 0; i < 4; ++i) {
+        int l = l0 + i; if (l >= p.L) l -= p.L;
+        uint32_t mk = 0;
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {
+          const bool ok = p.reverse ? (l + j < p.L) : (l - CX_HALO + j >= 0);
+          mk |= ok ? (1u << j) : 0u;
+        }
+        mask[i] = mk; edge |= (mk != 0xfu);
+      }
+      for (int kb = 0; kb < k_blocks; ++kb) {
+        const int c0 = kb * CX_BK + cg * 8;           // first of this thread's 8 channels
+        // taps and bias of the 8 channels (L1-resident after the first tile)
+        float wv[4][8], bv[8];
+#pragma unroll
+        for (int c = 0; c < 8; ++c) {
+          const bool okc = c0 + c < p.Di;
+          const float4 w4 = okc ? __ldg(reinterpret_cast<const float4*>(p.cw) + (c0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
+          // tap row j multiplies weight index j (causal) or 3 - j (anti-causal)
+          wv[0][c] = p.reverse ? w4.w : w4.x; wv[1][c] = p.reverse ? w4.z : w4.y;
+          wv[2][c] = p.reverse ? w4.y : w4.z; wv[3][c] = p.reverse ? w4.x : w4.w;
+          bv[c] = (okc && p.cb != nullptr) ? __ldg(p.cb + c0 + c) : 0.f;
+        }
+        mbar_wait(raw_full(stage), phase);
+        // raw rows 4 tr .. 4 tr + 6 of the block, this thread's 16-byte channel group
+        const uint32_t rbase = s_raw(stage) + (uint32_t)(4 * tr) * 128u + (uint32_t)cg * 16u;
+        float xr[7][8];
+#pragma unroll
+        for (int r = 0; r < 7; ++r) {
+          const uint4 q = lds_u4(rbase + (uint32_t)r * 128u);
+          const float2 f0 = unpack2<T>(q.x), f1 = unpack2<T>(q.y), f2 = unpack2<T>(q.z), f3 = unpack2<T>(q.w);
+          xr[r][0] = f0.x; xr[r][1] = f0.y; xr[r][2] = f1.x; xr[r][3] = f1.y;
+          xr[r][4] = f2.x; xr[r][5] = f2.y; xr[r][6] = f3.x; xr[r][7] = f3.y;
+        }
+        uint32_t outp[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          float acc[8];
+#pragma unroll
+          for (int c = 0; c < 8; ++c) acc[c] = bv[c];
+          if (!edge) {
+#pragma unroll
+            for (int j = 0; j < 4; ++j)
+#pragma unroll
+              for (int c = 0; c < 8; ++c) acc[c] = fmaf(wv[j][c], xr[i + j][c], acc[c]);
+          } else {
+#pragma unroll
+            for (int j = 0; j < 4; ++j) {
+              const float mj = ((mask[i] >> j) & 1u) ? 1.f : 0.f;
+#pragma unroll
+              for (int c = 0; c < 8; ++c) acc[c] = fmaf(wv[j][c] * mj, xr[i + j][c], acc[c]);
+            }
+          }
+#pragma unroll
+          for (int c = 0; c < 8; c += 2) outp[i][c >> 1] = pack2<T>(silu_ftz(acc[c]), silu_ftz(acc[c + 1]));
+        }
+        // the bulk store that read this A buffer CX_STAGES blocks ago must have drained before it is overwritten
+        if (leader && pending_stores >= CX_STAGES) { tma_store_wait_read<CX_STAGES - 1>(); }
+        conv_bar();
+        // A tile: row = token (128 B = 64 channels), 16-byte chunk index XOR (row & 7)  (128-byte swizzle)
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          const uint32_t row = (uint32_t)(4 * tr + i);
+          st_shared_v4(s_a(stage) + row * 128u + ((((uint32_t)cg) ^ (row & 7u)) << 4), outp[i][0], outp[i][1], outp[i][2], outp[i][3]);
+        }
+        asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
+        conv_bar();
+        if (leader) {
+          mbar_arrive(a_full(stage));                                   // -> MMA warp
+          tma_store_2d(&tmU, s_a(stage), kb * CX_BK, m0);               // u[m0 .. m0+127, 64 channels] (clipped at M / Di)
+          tma_store_commit();
+          ++pending_stores;
+        }
+        if (++stage == CX_STAGES) { stage = 0; phase ^= 1u; }
+      }
+      // ---- epilogue of the tile: the first four conv warps, lane = token row (warp & 3 = TMEM lane quarter)
+      if (warp < 6) {
+        mbar_wait(tfull, tphase);
+        tc_fence_after();
+        const int q = warp & 3;
+        const int row = m0 + q * 32 + lane;
+        const uint32_t t_row = tmem_base + ((uint32_t)(q * 32) << 16);
+        EpiParams ep;
+        ep.C = p.dt; ep.ldc = p.ld_dt; ep.c_dt = p.dt_dt;
+        ep.C2 = p.bc; ep.ldc2 = p.ld_bc; ep.c2_dt = AUM_F32; ep.split = p.R;
+        ep.bias = nullptr; ep.row_scale = nullptr; ep.act = AUM_ACT_NONE; ep.act_col0 = 0;
+        ep.M = p.M; ep.N = p.Nout; ep.vec_ok = 1;
+#pragma unroll 1
+        for (int c0 = 0; c0 < NB; c0 += 32) {
+          if (c0 >= p.Nout) break;
+          uint32_t r[32];
+          tc_ld_32x32b_x32(t_row + (uint32_t)c0, r);
+          tc_wait_ld();
+#pragma unroll
+          for (int g = 0; g < 4; ++g) {
+            float v[8];
+#pragma unroll
+            for (int i = 0; i < 8; ++i) v[i] = __uint_as_float(r[g * 8 + i]);
+            epi_store8(ep, row, c0 + g * 8, v, 1.f);
+          }
+        }
+        tc_fence_before();
+        mbar_arrive(tempty);
+      }
+      tphase ^= 1u;
+    }
+    if (leader) tma_store_wait_read<0>();             // shared memory must outlive the last bulk stores
+  }
+
+  tc_fence_before();
+  __syncthreads();
+  tc_fence_after();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(Cfg::TMEM_COLS) : "memory");
+  }
+}
+
+template <typename T, int NB>
+static int launch_cx(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmU, const CxParams& p, int dt, cudaStream_t st) {
+  using Cfg = CxCfg<NB>;
+  static PerDevice<bool> attr_set_dev;
+  bool& attr_set = attr_set_dev.cur();
+  if (!attr_set) {
+    cudaError_t e = cudaFuncSetAttribute(conv_xproj_kernel<T, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    if (e != cudaSuccess) { set_error("aum_conv_xproj_fwd: cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
+    attr_set = true;
+  }
+  static PerDevice<int> sms_dev;
+  int& sms = sms_dev.cur();
+  if (sms == 0) { cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, current_device()); if (sms <= 0) sms = 148; }
+  const int n_tiles = ceil_div(p.M, CX_BM);
+  const int grid = n_tiles < sms ? n_tiles : sms;
+  const int fmt = (dt == AUM_F16) ? 0 : 1;
+  const uint32_t idesc = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10)
+                       | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(CX_BM >> 4) << 24);
+  conv_xproj_kernel<T, NB><<<grid, CX_THREADS, Cfg::SMEM_BYTES, st>>>(tmX, tmW, tmU, p, idesc);
+  return check_launch("aum_conv_xproj_fwd");
+}
+
+}  // namespace aum
+
+extern "C" int aum_conv_xproj_fwd(const void* x, int64_t ldx, const float* conv_w, const float* conv_b,
+                                  const void* Wx, int64_t ldw, void* u, int64_t ldu,
+                                  void* dt, int64_t ld_dt, float* bc, int64_t ld_bc,
+                                  int batch, int L, int Di, int R, int N2, int dtype, int reverse, void* stream) {
+  using namespace aum;
+  DeviceGuard device_guard(u);
+  if (batch == 0 || L == 0 || Di == 0) return 0;
+  AUM_REQUIRE(x && conv_w && Wx && u && dt && bc, "aum_conv_xproj_fwd: null pointer");
+  AUM_REQUIRE(batch > 0 && L > 0 && Di > 0 && R >= 0 && N2 > 0, "aum_conv_xproj_fwd: bad sizes");
+  AUM_REQUIRE(dtype == AUM_F16 || dtype == AUM_BF16, "aum_conv_xproj_fwd: activations must be fp16 or bf16 (got dtype %d)", dtype);
+  const int Nout = R + N2;
+  AUM_REQUIRE(Nout <= 128, "aum_conv_xproj_fwd: R + 2N = %d exceeds 128", Nout);
+  AUM_REQUIRE(R % 8 == 0, "aum_conv_xproj_fwd: dt_rank must be a multiple of 8 (16-byte stores of the split output)");
+  AUM_REQUIRE(ldx >= Di && ldu >= Di && ldw >= Di && ld_dt >= R && ld_bc >= N2, "aum_conv_xproj_fwd: leading dimension too small");
+  auto ok16 = [](const void* p_, int64_t ld, int sz) { return aligned16(p_) && (ld * sz) % 16 == 0; };
+  AUM_REQUIRE(ok16(x, ldx, 2) && ok16(u, ldu, 2) && ok16(Wx, ldw, 2) && ok16(dt, ld_dt, 2) && ok16(bc, ld_bc, 4) && aligned16(conv_w),
+              "aum_conv_xproj_fwd: 16-byte aligned bases and row pitches required");
+  AUM_REQUIRE(Di % 8 == 0, "aum_conv_xproj_fwd: d_inner must be a multiple of 8");
+  AUM_REQUIRE(tma_available(), "aum_conv_xproj_fwd: cuTensorMapEncodeTiled unavailable");
+  const int64_t M = (int64_t)batch * L;
+  AUM_REQUIRE(M < (1ll << 31) - 256, "aum_conv_xproj_fwd: too many tokens");
+  const int NB = Nout <= 32 ? 32 : Nout <= 64 ? 64 : Nout <= 96 ? 96 : 128;
+  CUtensorMap tmX, tmW, tmU;
+  if (int rc = tma_encode_2d(&tmX, x, dtype, M, Di, ldx, CX_RAW_ROWS, CX_BK, false, "aum_conv_xproj_fwd(x)")) return rc;
+  if (int rc = tma_encode_2d(&tmW, Wx, dtype, Nout, Di, ldw, NB, CX_BK, true, "aum_conv_xproj_fwd(W_x)")) return rc;
+  if (int rc = tma_encode_2d(&tmU, u, dtype, M, Di, ldu, CX_BM, CX_BK, true, "aum_conv_xproj_fwd(u)")) return rc;
+  CxParams p;
+  p.cw = conv_w; p.cb = conv_b; p.dt = dt; p.ld_dt = ld_dt; p.dt_dt = dtype; p.bc = bc; p.ld_bc = ld_bc;
+  p.M = (int)M; p.L = L; p.Di = Di; p.R = R; p.Nout = Nout; p.reverse = reverse ? 1 : 0;
+  cudaStream_t st = (cudaStream_t)stream;
+#define AUM_CX(T_) \
+  (NB == 32 ? launch_cx<T_, 32>(tmX, tmW, tmU, p, dtype, st) : NB == 64 ? launch_cx<T_, 64>(tmX, tmW, tmU, p, dtype, st) \
+   : NB == 96 ? launch_cx<T_, 96>(tmX, tmW, tmU, p, dtype, st) : launch_cx<T_, 128>(tmX, tmW, tmU, p, dtype, st))
+  return dtype == AUM_F16 ? AUM_CX(__half) : AUM_CX(__nv_bfloat16);
+#undef AUM_CX
+}

@@ -30,6 +30,10 @@
 namespace aum {
 
 constexpr int ST_TT = 8;      // tokens per tile
+// steps of a full tile unrolled per loop trip (the rest of the tile is a rolled loop over trips): 4 = two trips per tile
+#ifndef AUM_SCAN_UNROLL
+#define AUM_SCAN_UNROLL 4
+#endif
 
 // Which lane of a (converged) warp does the TMA bookkeeping: the one elect.sync picks (default), so that ptxas emits the
 // UTMALDG / UTMASTG / UBLKCP of the owner's duties straight instead of wrapping each one in an ELECT / BRA.U.ANY loop, as it
@@ -151,11 +155,12 @@ __device__ __forceinline__ void scan_tile_full(uint32_t a_u, uint32_t a_d, uint3
                                                float Dv, float oscale, bool active,
                                                f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2],
                                                T* pyp, ptrdiff_t ostep) {
-  constexpr int HALF = ST_TT / 2;
+  constexpr int HALF = AUM_SCAN_UNROLL;             // steps per trip
+  static_assert(ST_TT % HALF == 0, "AUM_SCAN_UNROLL must divide the tile");
   constexpr int P16 = CH * (int)sizeof(T), P32 = CH * 4, PBC = SCAN_ROW * 4;
-  if (REV) { a_u += HALF * P16; a_z += HALF * P16; a_p += HALF * P16; a_d += HALF * P32; a_bc += HALF * PBC; }
+  if (REV) { a_u += (ST_TT - HALF) * P16; a_z += (ST_TT - HALF) * P16; a_p += (ST_TT - HALF) * P16; a_d += (ST_TT - HALF) * P32; a_bc += (ST_TT - HALF) * PBC; }
 #pragma unroll 1
-  for (int hf = 0; hf < 2; ++hf) {
+  for (int hf = 0; hf < ST_TT / HALF; ++hf) {
 #pragma unroll
     for (int t = 0; t < HALF; ++t) {
       const int r = REV ? (HALF - 1 - t) : t;
@@ -197,7 +202,10 @@ __device__ __forceinline__ void scan_tile_tail(int nt, bool fin, bool partial, b
   }
 }
 
-template <typename T, int MINB, int NSTG, int CH>
+// CKPT: the training instantiation (state checkpoints before every tile, for aum_selective_scan_bwd); inference
+// launches run the CKPT = false instantiation, whose tile loops carry no checkpoint stores (smaller loop bodies: the
+// steady-state loops of the resident CTAs compete for the 32 KB instruction cache).
+template <typename T, int MINB, int NSTG, int CH, bool CKPT>
 __global__ void __launch_bounds__(CH <= 128 ? 2 * CH : 512, MINB)      // either way: at most 128 registers per thread
 scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p) {
   using SL = StageLayout<T, NSTG, CH>;
@@ -334,7 +342,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   const int sd = rev ? -(CH * 4) : (CH * 4);
   const int sbc = rev ? -(SCAN_ROW * 4) : (SCAN_ROW * 4);
 
-  float* ckp = d.ckpt ? d.ckpt + (int64_t)b * scan_ck_count_max(L) * SCAN_NS * p.Dch + ch : nullptr;
+  float* ckp = (CKPT && d.ckpt) ? d.ckpt + (int64_t)b * scan_ck_count_max(L) * SCAN_NS * p.Dch + ch : nullptr;
 
   // Loop state kept incrementally (no division / modulo / re-derivation of the tiling per trip: the bookkeeping
   // between two tile bodies is pure latency for the warp, and with four warps per scheduler it showed up as 19 % of
@@ -366,7 +374,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
         for (int kk = n1t; kk <= upto; ++kk) issue_partial(kk);
       }
     }
-    if (ckp != nullptr && active) {        // training: state before this tile (tiles == checkpoint chunks)
+    if (CKPT && ckp != nullptr && active) {        // training: state before this tile (tiles == checkpoint chunks)
       float* c = ckp + (int64_t)k * SCAN_NS * p.Dch;
 #pragma unroll
       for (int i = 0; i < SCAN_NS / 2; ++i) {
@@ -436,7 +444,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     constexpr int ZM = decltype(zm_c)::value;
     for (; k < kend; ++k) {
       const uint32_t st = ring + (uint32_t)stage * SL::STAGE_BYTES;
-      if (ckp != nullptr && active) {        // training: state before this tile (tiles == checkpoint chunks)
+      if (CKPT && ckp != nullptr && active) {        // training: state before this tile (tiles == checkpoint chunks)
         float* c = ckp + (int64_t)k * SCAN_NS * p.Dch;
 #pragma unroll
         for (int i = 0; i < SCAN_NS / 2; ++i) {
@@ -517,13 +525,16 @@ static int launch_n(const ScanTmaMaps& maps, const ScanParams& p, cudaStream_t s
   bool& attr_set = attr_set_dev.cur();
   // CH = 128: two resident CTAs per SM (128 registers, 90-110 KB of stages each); a 3-CTA / 80-register build measured slower
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, MINB, NSTG, CH>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, MINB, NSTG, CH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, MINB, NSTG, CH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("aum_selective_scan_fwd: cudaFuncSetAttribute(smem=%d): %s", SL::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
     attr_set = true;
   }
   dim3 grid(ceil_div(p.Dch, CH), p.batch);
   const int smem = p.ndirs * SL::GROUP_BYTES + 128 + 2 * 3 * NSTG * 8;     // one ring per direction actually launched
-  scan_fwd_tma_kernel<T, MINB, NSTG, CH><<<grid, CH * p.ndirs, smem, st>>>(maps, p);
+  const bool ckpt = p.dir[0].ckpt != nullptr || (p.ndirs == 2 && p.dir[1].ckpt != nullptr);
+  if (ckpt) scan_fwd_tma_kernel<T, MINB, NSTG, CH, true><<<grid, CH * p.ndirs, smem, st>>>(maps, p);
+  else      scan_fwd_tma_kernel<T, MINB, NSTG, CH, false><<<grid, CH * p.ndirs, smem, st>>>(maps, p);
   return check_launch("aum_selective_scan_fwd(tma)");
 }
 

@@ -99,6 +99,23 @@ AUM_API int aum_causal_conv1d_fwd(const void* x, int64_t ldx, const float* w, co
                           void* out, int64_t ldo, int batch, int L, int D, int W,
                           int dtype, int silu, int reverse, void* stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * Fused  u = SiLU(causal_conv1d(x) + bias)  and  x_dbl = u @ W_x^T  split into dt | [B|C]   (16-bit activations).
+ *   replaces causal_conv1d_cuda.causal_conv1d_fwd(x, w, b, None, True) followed by
+ *   F.linear(rearrange(conv1d_out, "b d l -> (b l) d"), x_proj_weight)
+ *   (selective_scan_interface.py:463+467, :177+181, :318+322) and the B / C slicing of :473-496.
+ *   The conv is the producer of the x_proj tensor-core operand (conv results are written into the swizzled
+ *   shared-memory tile tcgen05.mma reads, and the same tile leaves for HBM as u): one launch, x read once.
+ *   x: (batch*L, Di) token-major, ldx; conv_w (Di, 4) fp32 [d_conv == 4]; conv_b (Di) fp32 or NULL;
+ *   Wx: (R + N2, Di) dtype, K-contiguous; outputs u (batch*L, Di) dtype, dt (batch*L, >= R) dtype (columns [0, R)
+ *   written), bc (batch*L, N2) fp32 (N2 = 2 * d_state).  R % 8 == 0, R + N2 <= 128, Di % 8 == 0.
+ *   reverse = 1: anti-causal conv (Bi-Bi's second branch, mamba_simple.py:229-241, without flips).
+ * ------------------------------------------------------------------------------------------- */
+AUM_API int aum_conv_xproj_fwd(const void* x, int64_t ldx, const float* conv_w, const float* conv_b,
+                       const void* Wx, int64_t ldw, void* u, int64_t ldu,
+                       void* dt, int64_t ld_dt, float* bc, int64_t ld_bc,
+                       int batch, int L, int Di, int R, int N2, int dtype, int reverse, void* stream);
+
 /* Backward of the above.  replaces causal_conv1d_cuda.causal_conv1d_bwd(x, w, bias, dout, None, dx, silu)
  *   (selective_scan_interface.py:281-283, 425-427, 594-596).  dout (+ optional dout2, same pitch; the two are
  *   summed on the fly — the scan's du and the x_proj term of :590): fp32 gradient w.r.t. the conv output (after the

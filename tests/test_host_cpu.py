@@ -53,7 +53,8 @@ def test_flat_gradient_buffer_layout():
 
 
 def test_bench_reference_arm_prints_the_contract_line():
-    """`bench.py --impl reference` (the reference's CPU path through the oracle port): one JSON line with the same
+    """`bench.py --impl reference` (the reference's own CPU path from oracle/_ref, one whole clip per step; the oracle
+    port only where no staged reference exists): one JSON line with the same
     metric / unit as the GPU arm, impl = reference, a cpu_baseline describing the run and an e2e object of its own."""
     r = subprocess.run([sys.executable, os.path.join(ROOT, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "3"],
                        capture_output=True, text=True, timeout=600)
@@ -65,7 +66,11 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert d["metric"].startswith("clips/sec AuM-Base")
     assert d["value"] > 0 and d["steps"] == 1
     cb = d["cpu_baseline"]
-    assert cb["kind"] == "port" and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    staged = any(os.path.isfile(os.path.join(r_, "src", "models", "mamba_models.py"))
+                 for r_ in ("/root/reference", os.path.join(ROOT, "oracle", "_ref")))
+    assert cb["kind"] == ("reference" if staged else "port") and cb["cores"] >= 1 and cb["value"] == d["value"] and "sample" in cb
+    if staged:      # a step is one whole clip: the line's own clock agrees with its value
+        assert abs(d["ms_per_step"] / 1000.0 * d["value"] - 1.0) < 1e-6 and d["config"]["clips_per_step"] == 1
     assert d["e2e"] == {"value": d["value"], "unit": "clips/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     # a non-zero rank of a torchrun launch does no work and prints nothing
     env = dict(os.environ, RANK="1", WORLD_SIZE="2", LOCAL_RANK="1")

@@ -360,3 +360,39 @@ def test_patchify_and_token_assembly(dt):
             + torch.cat((pos[:, 1:tp + 1], pos[:, :1], pos[:, tp + 1:]), dim=1)
         out = ops.assemble_tokens(ref_tok.contiguous().to(DEV), pos[0].contiguous().to(DEV), cls.reshape(-1).to(DEV))
         torch.testing.assert_close(out.cpu(), ref, rtol=0, atol=0)
+
+
+# ----------------------------------------------------------------------------------------------------
+@pytest.mark.parametrize("dt", [torch.float16, torch.bfloat16])
+@pytest.mark.parametrize("reverse", [False, True])
+@pytest.mark.parametrize("B,Lq,Di,R,N", [(2, 513, 1536, 48, 16),      # AuM-Base: 80 outputs -> 96-wide MMA, 24 channel blocks
+                                         (3, 65, 768, 24, 16),        # AuM-Small: 56 outputs -> 64-wide MMA; tiles span sequences
+                                         (1, 7, 64, 8, 16),           # one short sequence, one channel block
+                                         (5, 130, 200, 16, 16)])      # Di not a multiple of 64 (channel tail), 650 tokens
+def test_fused_conv_xproj(dt, reverse, B, Lq, Di, R, N):
+    """aum_conv_xproj_fwd (conv + SiLU as the producer of x_proj's tensor-core operand) against the oracle's conv and a
+    float64 x_proj on the SAME rounded u, and against the two separate kernels it replaces."""
+    from aum_b200 import ops
+    g = gen(40 + Di)
+    xz = rnd((B, Lq, 2 * Di), g, dt)                      # x = first half of an xz buffer (z must never be read)
+    w = rnd((Di, 4), g, scale=0.5)
+    b = rnd((Di,), g, scale=0.5)
+    wx = rnd((R + 2 * N, Di), g, dt, scale=Di ** -0.5)
+    x = xz.to(DEV)[..., :Di]
+    M = B * Lq
+    dtb = torch.full((M, R + 8), 7.0, device=DEV, dtype=dt)
+    bc = torch.empty((M, 2 * N), device=DEV, dtype=torch.float32)
+    assert ops.conv_xproj_eligible(x, w.to(DEV), wx.to(DEV), R, 2 * N)
+    u = ops.conv_xproj(x, w.to(DEV), b.to(DEV), wx.to(DEV), R, dtb, bc, reverse=reverse)
+    # conv vs oracle
+    xc = xz[..., :Di].float().permute(0, 2, 1)
+    ref_u = (O.causal_conv1d_oracle(xc.flip(-1), w, b, True).flip(-1) if reverse else O.causal_conv1d_oracle(xc, w, b, True))
+    torch.testing.assert_close(u.float().cpu().permute(0, 2, 1), ref_u, **TOL[dt])
+    # x_proj of the u that was actually produced (exactly representable operands -> only fp32 accumulation differs)
+    ref_x = _gemm_ref(u.float().cpu().view(M, Di), wx.float())
+    torch.testing.assert_close(dtb[:, :R].float().cpu(), ref_x[:, :R], **TOL[dt])
+    assert (dtb[:, R:] == 7.0).all()
+    torch.testing.assert_close(bc.cpu(), ref_x[:, R:], rtol=1e-4, atol=1e-4)
+    # the two kernels it replaces
+    u2 = ops.causal_conv1d(x, w.to(DEV), b.to(DEV), silu=True, reverse=reverse)
+    torch.testing.assert_close(u.float(), u2.float(), **TOL[dt])

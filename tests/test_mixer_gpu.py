@@ -108,10 +108,15 @@ def test_rmsnorm_module_matches_reference_golden():
         torch.testing.assert_close(n(c["x"].to(DEV)).cpu(), c["out_nores"], rtol=2e-5, atol=2e-6)
 
 
-def test_functional_ops_are_forward_only_and_say_so():
-    """The module path trains (tests/test_backward_gpu.py); the bare functional ops refuse autograd loudly."""
+def test_functional_ops_refuse_modes_outside_the_aum_path_loudly():
+    """The functional ops are differentiable (tests/test_backward_gpu.py); what they do not implement they refuse loudly
+    instead of falling back: complex A, grouped B/C, and a differentiable scan with d_state != 16."""
     from mamba_ssm.ops.selective_scan_interface import selective_scan_fn
-    u = torch.randn(1, 8, 16, device=DEV, requires_grad=True)
+    u = torch.randn(1, 8, 16, device=DEV)
+    Bm = torch.randn(1, 16, 16, device=DEV)
     with pytest.raises(NotImplementedError):
-        selective_scan_fn(u, u, -torch.ones(8, 16, device=DEV), torch.randn(1, 16, 16, device=DEV),
-                          torch.randn(1, 16, 16, device=DEV))
+        selective_scan_fn(u, u, -torch.ones(8, 16, device=DEV, dtype=torch.complex64), Bm, Bm)
+    with pytest.raises(NotImplementedError):
+        selective_scan_fn(u, u, -torch.ones(8, 16, device=DEV), torch.randn(1, 2, 16, 16, device=DEV), Bm)
+    with pytest.raises(NotImplementedError):
+        selective_scan_fn(u.clone().requires_grad_(), u, -torch.ones(8, 8, device=DEV), Bm[:, :8], Bm[:, :8])
