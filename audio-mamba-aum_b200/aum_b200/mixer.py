@@ -27,7 +27,12 @@ from . import ops
 
 
 _PREGATE_Z = os.environ.get("AUM_PREGATE_Z", "1") == "1"
-_FUSE_CONV_XPROJ = os.environ.get("AUM_FUSE_CONV_XPROJ", "1") == "1"
+# conv + SiLU fused into x_proj's operand producer (aum_conv_xproj_fwd, csrc/conv_xproj.cu): parity-green, but measured
+# SLOWER than the two kernels it replaces (0.153 vs 0.053 + 0.035 ms at config 2: its 8 conv warps per SM run ~480
+# instructions per channel block at 1 IPC/SM - shared-memory and MUFU latency with two warps per scheduler, ncu
+# profiles/r2_ncu_conv_xproj_v2_summary.txt - where the stand-alone conv hides the same latencies with full occupancy).
+# Off by default; AUM_FUSE_CONV_XPROJ=1 selects it.
+_FUSE_CONV_XPROJ = os.environ.get("AUM_FUSE_CONV_XPROJ", "0") == "1"
 
 
 def _round_up(x: int, m: int) -> int:

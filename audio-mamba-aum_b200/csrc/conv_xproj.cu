@@ -23,6 +23,7 @@
 #include <stdlib.h>
 
 #include "gemm_common.cuh"
+#include "scan_common.cuh"     // packed fp32x2 helpers, bulk_g2s
 #include "tcgen05_ptx.cuh"
 #include "tma.cuh"
 
@@ -33,16 +34,23 @@ constexpr int CX_BK = 64;                  // channels per block (128 B of 16-bi
 constexpr int CX_HALO = 3;                 // d_conv - 1
 constexpr int CX_RAW_ROWS = CX_BM + CX_HALO;
 constexpr int CX_RAW_BYTES = 17 * 1024;    // 131 rows x 128 B = 16768, padded to keep 1024-byte alignment of what follows
+constexpr int CX_CW_BYTES = 2 * 1024;      // conv taps of the block's 64 channels (64 x 4 fp32 = 1 KB) + their biases (256 B)
+constexpr int CX_CW_BIAS_OFF = 1024;
 constexpr int CX_A_BYTES = CX_BM * 128;    // 16 KB, 128-byte swizzled
-constexpr int CX_STAGES = 4;
+constexpr int CX_STAGES = 6;                // load ring (raw x rows + W_x block + conv taps): 31 KB per stage at NB = 96.  The
+                                           // kernel is latency-bound below ~5 blocks of prefetch (ncu v1/v2: one DRAM round trip per
+                                           // channel block at 4 stages that also held the A tiles)
+constexpr int CX_ASTAGES = 2;              // A tiles (conv output = MMA operand = source of the u store)
 constexpr int CX_CONV_WARPS = 8;
 constexpr int CX_THREADS = 64 + 32 * CX_CONV_WARPS;
 constexpr int CX_BAR_ID = 3;               // named barrier of the conv warps
 
 template <int NB> struct CxCfg {
   static constexpr int W_BYTES = NB * 128;
-  static constexpr int STAGE_BYTES = CX_RAW_BYTES + W_BYTES + CX_A_BYTES;
-  static constexpr int SMEM_BYTES = CX_STAGES * STAGE_BYTES + 1024 + 256;
+  static constexpr int STAGE_BYTES = CX_RAW_BYTES + W_BYTES + CX_CW_BYTES;
+  static constexpr int STAGES = (NB <= 96) ? CX_STAGES : 5;        // NB = 128: 35 KB per stage
+  static constexpr int SMEM_BYTES = STAGES * STAGE_BYTES + CX_ASTAGES * CX_A_BYTES + 1024 + 256;
+  static_assert(SMEM_BYTES <= 227 * 1024, "shared memory budget");
   static constexpr int TMEM_COLS = NB <= 32 ? 32 : NB <= 64 ? 64 : 128;
   static_assert(NB % 16 == 0 && NB >= 16 && NB <= 128, "UMMA N");
   static_assert(W_BYTES % 1024 == 0 || NB % 8 == 0, "");
@@ -60,6 +68,9 @@ __device__ __forceinline__ void conv_bar() { asm volatile("bar.sync %0, %1;" ::"
 __device__ __forceinline__ uint4 lds_u4(uint32_t a) {
   uint4 v; asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
 }
+__device__ __forceinline__ float4 lds_f4x(uint32_t a) {
+  float4 v; asm volatile("ld.shared.v4.f32 {%0, %1, %2, %3}, [%4];" : "=f"(v.x), "=f"(v.y), "=f"(v.z), "=f"(v.w) : "r"(a)); return v;
+}
 template <typename T> __device__ __forceinline__ float2 unpack2(uint32_t v);
 template <> __device__ __forceinline__ float2 unpack2<__half>(uint32_t v) { return __half22float2(*reinterpret_cast<__half2*>(&v)); }
 template <> __device__ __forceinline__ float2 unpack2<__nv_bfloat16>(uint32_t v) {
@@ -69,30 +80,35 @@ template <typename T> __device__ __forceinline__ uint32_t pack2(float a, float b
 template <> __device__ __forceinline__ uint32_t pack2<__half>(float a, float b) { __half2 h = __floats2half2_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
 template <> __device__ __forceinline__ uint32_t pack2<__nv_bfloat16>(float a, float b) { __nv_bfloat162 h = __floats2bfloat162_rn(a, b); return *reinterpret_cast<uint32_t*>(&h); }
 
-template <typename T, int NB>
+template <typename T, int NB, bool REV>
 __global__ void __launch_bounds__(CX_THREADS, 1)
 conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant__ CUtensorMap tmW,
                   const __grid_constant__ CUtensorMap tmU, const CxParams p, uint32_t idesc) {
   using Cfg = CxCfg<NB>;
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem_base = (smem_u32(smem_raw) + 1023u) & ~1023u;
-  const uint32_t bar_base = smem_base + CX_STAGES * Cfg::STAGE_BYTES;
-  auto raw_full = [&](int s) { return bar_base + 8u * s; };                     // TMA: raw x rows + W block landed
-  auto a_full = [&](int s) { return bar_base + 8u * (CX_STAGES + s); };         // conv: A tile written
-  auto st_free = [&](int s) { return bar_base + 8u * (2 * CX_STAGES + s); };    // MMA: stage consumed
-  const uint32_t tfull = bar_base + 8u * (3 * CX_STAGES);
-  const uint32_t tempty = bar_base + 8u * (3 * CX_STAGES + 1);
-  const uint32_t tmem_slot = bar_base + 8u * (3 * CX_STAGES + 2);
+  constexpr int STAGES = Cfg::STAGES;
+  const uint32_t a_base = smem_base + STAGES * Cfg::STAGE_BYTES;                  // 1024-aligned
+  const uint32_t bar_base = a_base + CX_ASTAGES * CX_A_BYTES;
+  auto raw_full = [&](int s) { return bar_base + 8u * s; };                       // TMA: raw x rows + W block + taps landed
+  auto st_free = [&](int s) { return bar_base + 8u * (STAGES + s); };             // MMA: load stage consumed
+  auto a_full = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };          // conv: A tile written
+  auto a_done = [&](int s) { return bar_base + 8u * (2 * STAGES + CX_ASTAGES + s); };   // MMA: A tile consumed
+  const uint32_t tfull = bar_base + 8u * (2 * STAGES + 2 * CX_ASTAGES);
+  const uint32_t tempty = tfull + 8u;
+  const uint32_t tmem_slot = tfull + 16u;
   auto s_raw = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
   auto s_w = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + CX_RAW_BYTES; };
-  auto s_a = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + CX_RAW_BYTES + Cfg::W_BYTES; };
+  auto s_cw = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES + CX_RAW_BYTES + Cfg::W_BYTES; };
+  auto s_a = [&](int s) { return a_base + s * CX_A_BYTES; };
 
   const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
   const int n_tiles = (p.M + CX_BM - 1) / CX_BM;
   const int k_blocks = (p.Di + CX_BK - 1) / CX_BK;
 
   if (warp == 0 && lane == 0) {
-    for (int s = 0; s < CX_STAGES; ++s) { mbar_init(raw_full(s), 1); mbar_init(a_full(s), 1); mbar_init(st_free(s), 1); }
+    for (int s = 0; s < STAGES; ++s) { mbar_init(raw_full(s), 1); mbar_init(st_free(s), 1); }
+    for (int s = 0; s < CX_ASTAGES; ++s) { mbar_init(a_full(s), 1); mbar_init(a_done(s), 1); }
     mbar_init(tfull, 1); mbar_init(tempty, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -114,36 +130,44 @@ conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
         const int m0 = tile * CX_BM;
         // causal: rows [m0 - 3, m0 + 128); anti-causal: rows [m0, m0 + 131).  Out-of-range rows are zero-filled.
-        const int row0 = p.reverse ? m0 : m0 - CX_HALO;
+        const int row0 = REV ? m0 : m0 - CX_HALO;
         for (int kb = 0; kb < k_blocks; ++kb) {
           mbar_wait(st_free(stage), phase ^ 1u);
-          mbar_arrive_expect_tx(raw_full(stage), CX_RAW_ROWS * 128 + Cfg::W_BYTES);
+          const int nch = min(CX_BK, p.Di - kb * CX_BK);                       // channels of this block (Di % 8 == 0)
+          const uint32_t cw_bytes = (uint32_t)nch * 16u, cb_bytes = p.cb ? (uint32_t)nch * 4u : 0u;
+          mbar_arrive_expect_tx(raw_full(stage), CX_RAW_ROWS * 128 + Cfg::W_BYTES + cw_bytes + cb_bytes);
           tma_load_2d(s_raw(stage), &tmX, kb * CX_BK, row0, raw_full(stage));
           tma_load_2d(s_w(stage), &tmW, kb * CX_BK, 0, raw_full(stage));
-          if (++stage == CX_STAGES) { stage = 0; phase ^= 1u; }
+          // the block's conv taps and biases ride on the same barrier (a per-thread __ldg of them cost 4 long-scoreboard
+          // stalls per issue: every channel block brings new channels, i.e. L1 misses, right before they are needed)
+          bulk_g2s(s_cw(stage), p.cw + (int64_t)kb * CX_BK * 4, cw_bytes, raw_full(stage));
+          if (cb_bytes) bulk_g2s(s_cw(stage) + CX_CW_BIAS_OFF, p.cb + (int64_t)kb * CX_BK, cb_bytes, raw_full(stage));
+          if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         }
       }
     }
   } else if (warp == 1) {
     // ================= MMA issuer =================
-    int stage = 0; uint32_t phase = 0, tphase = 0;
+    int stage = 0, as = 0; uint32_t aphase = 0, tphase = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       mbar_wait(tempty, tphase ^ 1u);                 // epilogue of the previous tile has drained the accumulator
       tc_fence_after();
       for (int kb = 0; kb < k_blocks; ++kb) {
-        mbar_wait(a_full(stage), phase);
+        mbar_wait(a_full(as), aphase);                // (the conv warps waited for this block's raw_full: W_x is there too)
         tc_fence_after();
-        const uint64_t da = make_smem_desc_sw128(s_a(stage));
+        const uint64_t da = make_smem_desc_sw128(s_a(as));
         const uint64_t db = make_smem_desc_sw128(s_w(stage));
         if (elect_one()) {
 #pragma unroll
           for (int k = 0; k < CX_BK / 16; ++k)
             tc_mma_f16(tmem_base, da + (uint64_t)(2 * k), db + (uint64_t)(2 * k), idesc, (kb | k) != 0 ? 1u : 0u);
           tc_commit(st_free(stage));
+          tc_commit(a_done(as));
           if (kb == k_blocks - 1) tc_commit(tfull);
         }
         __syncwarp();
-        if (++stage == CX_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == STAGES) stage = 0;
+        if (++as == CX_ASTAGES) { as = 0; aphase ^= 1u; }
       }
       tphase ^= 1u;
     }
@@ -153,7 +177,7 @@ conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
     const int cg = ct & 7;                            // 8-channel group inside the 64-channel block (16 B)
     const int tr = ct >> 3;                           // 0..31: tokens 4 tr .. 4 tr + 3 of the tile
     const bool leader = ct == 0;
-    int stage = 0; uint32_t phase = 0, tphase = 0;
+    int stage = 0, as = 0; uint32_t phase = 0, aphase = 0, tphase = 0;
     int pending_stores = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int m0 = tile * CX_BM;
@@ -168,75 +192,94 @@ conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
         uint32_t mk = 0;
 #pragma unroll
         for (int j = 0; j < 4; ++j) {
-          const bool ok = p.reverse ? (l + j < p.L) : (l - CX_HALO + j >= 0);
+          const bool ok = REV ? (l + j < p.L) : (l - CX_HALO + j >= 0);
           mk |= ok ? (1u << j) : 0u;
         }
         mask[i] = mk; edge |= (mk != 0xfu);
       }
       for (int kb = 0; kb < k_blocks; ++kb) {
-        const int c0 = kb * CX_BK + cg * 8;           // first of this thread's 8 channels
-        // taps and bias of the 8 channels (L1-resident after the first tile)
-        float wv[4][8], bv[8];
-#pragma unroll
-        for (int c = 0; c < 8; ++c) {
-          const bool okc = c0 + c < p.Di;
-          const float4 w4 = okc ? __ldg(reinterpret_cast<const float4*>(p.cw) + (c0 + c)) : make_float4(0.f, 0.f, 0.f, 0.f);
-          // tap row j multiplies weight index j (causal) or 3 - j (anti-causal)
-          wv[0][c] = p.reverse ? w4.w : w4.x; wv[1][c] = p.reverse ? w4.z : w4.y;
-          wv[2][c] = p.reverse ? w4.y : w4.z; wv[3][c] = p.reverse ? w4.x : w4.w;
-          bv[c] = (okc && p.cb != nullptr) ? __ldg(p.cb + c0 + c) : 0.f;
-        }
         mbar_wait(raw_full(stage), phase);
-        // raw rows 4 tr .. 4 tr + 6 of the block, this thread's 16-byte channel group
+        // taps and biases of this thread's 8 channels, from the stage's weight slab, as channel pairs:
+        // wp[k][c2] = (w_k[2 c2], w_k[2 c2 + 1])
+        f32x2 wp[4][4], bp[4];
+        {
+          const bool okc = kb * CX_BK + cg * 8 < p.Di;                 // (channel tail: Di % 8 == 0, so all 8 or none)
+          const uint32_t wbase = s_cw(stage) + (uint32_t)cg * 128u;
+#pragma unroll
+          for (int c2 = 0; c2 < 4; ++c2) {
+            float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
+            if (okc) { wa = lds_f4x(wbase + (uint32_t)(2 * c2) * 16u); wb = lds_f4x(wbase + (uint32_t)(2 * c2 + 1) * 16u); }
+            wp[0][c2] = pk2(wa.x, wb.x); wp[1][c2] = pk2(wa.y, wb.y); wp[2][c2] = pk2(wa.z, wb.z); wp[3][c2] = pk2(wa.w, wb.w);
+          }
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
+          if (okc && p.cb != nullptr) {
+            b0 = lds_f4x(s_cw(stage) + CX_CW_BIAS_OFF + (uint32_t)cg * 32u);
+            b1 = lds_f4x(s_cw(stage) + CX_CW_BIAS_OFF + (uint32_t)cg * 32u + 16u);
+          }
+          bp[0] = pk2(b0.x, b0.y); bp[1] = pk2(b0.z, b0.w); bp[2] = pk2(b1.x, b1.y); bp[3] = pk2(b1.z, b1.w);
+        }
+        // raw rows 4 tr .. 4 tr + 6 of the block, this thread's 16-byte channel group, each converted once to 4 fp32 pairs
         const uint32_t rbase = s_raw(stage) + (uint32_t)(4 * tr) * 128u + (uint32_t)cg * 16u;
-        float xr[7][8];
+        f32x2 xr[7][4];
 #pragma unroll
         for (int r = 0; r < 7; ++r) {
           const uint4 q = lds_u4(rbase + (uint32_t)r * 128u);
           const float2 f0 = unpack2<T>(q.x), f1 = unpack2<T>(q.y), f2 = unpack2<T>(q.z), f3 = unpack2<T>(q.w);
-          xr[r][0] = f0.x; xr[r][1] = f0.y; xr[r][2] = f1.x; xr[r][3] = f1.y;
-          xr[r][4] = f2.x; xr[r][5] = f2.y; xr[r][6] = f3.x; xr[r][7] = f3.y;
+          xr[r][0] = pk2(f0.x, f0.y); xr[r][1] = pk2(f1.x, f1.y); xr[r][2] = pk2(f2.x, f2.y); xr[r][3] = pk2(f3.x, f3.y);
         }
         uint32_t outp[4][4];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          float acc[8];
+          f32x2 acc[4];
 #pragma unroll
-          for (int c = 0; c < 8; ++c) acc[c] = bv[c];
+          for (int c2 = 0; c2 < 4; ++c2) acc[c2] = bp[c2];
+          // tap row j of token i is raw row i + j; it multiplies tap k = j (causal) or k = 3 - j (anti-causal)
           if (!edge) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-              for (int c = 0; c < 8; ++c) acc[c] = fmaf(wv[j][c], xr[i + j][c], acc[c]);
+              for (int c2 = 0; c2 < 4; ++c2) acc[c2] = fma2(wp[REV ? 3 - j : j][c2], xr[i + j][c2], acc[c2]);
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
               const float mj = ((mask[i] >> j) & 1u) ? 1.f : 0.f;
+              const f32x2 m2 = pk2(mj, mj);
 #pragma unroll
-              for (int c = 0; c < 8; ++c) acc[c] = fmaf(wv[j][c] * mj, xr[i + j][c], acc[c]);
+              for (int c2 = 0; c2 < 4; ++c2) acc[c2] = fma2(mul2(wp[REV ? 3 - j : j][c2], m2), xr[i + j][c2], acc[c2]);
             }
           }
+          // SiLU on pairs: x * rcp(1 + ex2(-x log2 e)), flush-to-zero MUFU forms
 #pragma unroll
-          for (int c = 0; c < 8; c += 2) outp[i][c >> 1] = pack2<T>(silu_ftz(acc[c]), silu_ftz(acc[c + 1]));
+          for (int c2 = 0; c2 < 4; ++c2) {
+            float t0, t1, a0, a1;
+            upk2(mul2(acc[c2], pk2(-1.4426950408889634f, -1.4426950408889634f)), t0, t1);
+            upk2(acc[c2], a0, a1);
+            float r0, r1;
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r0) : "f"(1.f + ex2_approx(t0)));
+            asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r1) : "f"(1.f + ex2_approx(t1)));
+            outp[i][c2] = pack2<T>(a0 * r0, a1 * r1);
+          }
         }
         // the bulk store that read this A buffer CX_STAGES blocks ago must have drained before it is overwritten
-        if (leader && pending_stores >= CX_STAGES) { tma_store_wait_read<CX_STAGES - 1>(); }
+        if (leader && pending_stores >= CX_ASTAGES) { tma_store_wait_read<CX_ASTAGES - 1>(); }
+        mbar_wait(a_done(as), aphase ^ 1u);           // the MMAs that read this A buffer two blocks ago have retired
         conv_bar();
         // A tile: row = token (128 B = 64 channels), 16-byte chunk index XOR (row & 7)  (128-byte swizzle)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t row = (uint32_t)(4 * tr + i);
-          st_shared_v4(s_a(stage) + row * 128u + ((((uint32_t)cg) ^ (row & 7u)) << 4), outp[i][0], outp[i][1], outp[i][2], outp[i][3]);
+          st_shared_v4(s_a(as) + row * 128u + ((((uint32_t)cg) ^ (row & 7u)) << 4), outp[i][0], outp[i][1], outp[i][2], outp[i][3]);
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
         conv_bar();
         if (leader) {
-          mbar_arrive(a_full(stage));                                   // -> MMA warp
-          tma_store_2d(&tmU, s_a(stage), kb * CX_BK, m0);               // u[m0 .. m0+127, 64 channels] (clipped at M / Di)
+          mbar_arrive(a_full(as));                                      // -> MMA warp
+          tma_store_2d(&tmU, s_a(as), kb * CX_BK, m0);                  // u[m0 .. m0+127, 64 channels] (clipped at M / Di)
           tma_store_commit();
           ++pending_stores;
         }
-        if (++stage == CX_STAGES) { stage = 0; phase ^= 1u; }
+        if (++stage == STAGES) { stage = 0; phase ^= 1u; }
+        if (++as == CX_ASTAGES) { as = 0; aphase ^= 1u; }
       }
       // ---- epilogue of the tile: the first four conv warps, lane = token row (warp & 3 = TMEM lane quarter)
       if (warp < 6) {
@@ -280,13 +323,13 @@ conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   }
 }
 
-template <typename T, int NB>
+template <typename T, int NB, bool REV>
 static int launch_cx(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUtensorMap& tmU, const CxParams& p, int dt, cudaStream_t st) {
   using Cfg = CxCfg<NB>;
   static PerDevice<bool> attr_set_dev;
   bool& attr_set = attr_set_dev.cur();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(conv_xproj_kernel<T, NB>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(conv_xproj_kernel<T, NB, REV>, cudaFuncAttributeMaxDynamicSharedMemorySize, Cfg::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("aum_conv_xproj_fwd: cudaFuncSetAttribute(smem=%d): %s", Cfg::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
     attr_set = true;
   }
@@ -298,7 +341,7 @@ static int launch_cx(const CUtensorMap& tmX, const CUtensorMap& tmW, const CUten
   const int fmt = (dt == AUM_F16) ? 0 : 1;
   const uint32_t idesc = (1u << 4) | ((uint32_t)fmt << 7) | ((uint32_t)fmt << 10)
                        | ((uint32_t)(NB >> 3) << 17) | ((uint32_t)(CX_BM >> 4) << 24);
-  conv_xproj_kernel<T, NB><<<grid, CX_THREADS, Cfg::SMEM_BYTES, st>>>(tmX, tmW, tmU, p, idesc);
+  conv_xproj_kernel<T, NB, REV><<<grid, CX_THREADS, Cfg::SMEM_BYTES, st>>>(tmX, tmW, tmU, p, idesc);
   return check_launch("aum_conv_xproj_fwd");
 }
 
@@ -319,7 +362,8 @@ extern "C" int aum_conv_xproj_fwd(const void* x, int64_t ldx, const float* conv_
   AUM_REQUIRE(R % 8 == 0, "aum_conv_xproj_fwd: dt_rank must be a multiple of 8 (16-byte stores of the split output)");
   AUM_REQUIRE(ldx >= Di && ldu >= Di && ldw >= Di && ld_dt >= R && ld_bc >= N2, "aum_conv_xproj_fwd: leading dimension too small");
   auto ok16 = [](const void* p_, int64_t ld, int sz) { return aligned16(p_) && (ld * sz) % 16 == 0; };
-  AUM_REQUIRE(ok16(x, ldx, 2) && ok16(u, ldu, 2) && ok16(Wx, ldw, 2) && ok16(dt, ld_dt, 2) && ok16(bc, ld_bc, 4) && aligned16(conv_w),
+  AUM_REQUIRE(ok16(x, ldx, 2) && ok16(u, ldu, 2) && ok16(Wx, ldw, 2) && ok16(dt, ld_dt, 2) && ok16(bc, ld_bc, 4) && aligned16(conv_w) &&
+              (conv_b == nullptr || aligned16(conv_b)),
               "aum_conv_xproj_fwd: 16-byte aligned bases and row pitches required");
   AUM_REQUIRE(Di % 8 == 0, "aum_conv_xproj_fwd: d_inner must be a multiple of 8");
   AUM_REQUIRE(tma_available(), "aum_conv_xproj_fwd: cuTensorMapEncodeTiled unavailable");
@@ -334,9 +378,11 @@ extern "C" int aum_conv_xproj_fwd(const void* x, int64_t ldx, const float* conv_
   p.cw = conv_w; p.cb = conv_b; p.dt = dt; p.ld_dt = ld_dt; p.dt_dt = dtype; p.bc = bc; p.ld_bc = ld_bc;
   p.M = (int)M; p.L = L; p.Di = Di; p.R = R; p.Nout = Nout; p.reverse = reverse ? 1 : 0;
   cudaStream_t st = (cudaStream_t)stream;
-#define AUM_CX(T_) \
-  (NB == 32 ? launch_cx<T_, 32>(tmX, tmW, tmU, p, dtype, st) : NB == 64 ? launch_cx<T_, 64>(tmX, tmW, tmU, p, dtype, st) \
-   : NB == 96 ? launch_cx<T_, 96>(tmX, tmW, tmU, p, dtype, st) : launch_cx<T_, 128>(tmX, tmW, tmU, p, dtype, st))
+#define AUM_CX2(T_, R_) \
+  (NB == 32 ? launch_cx<T_, 32, R_>(tmX, tmW, tmU, p, dtype, st) : NB == 64 ? launch_cx<T_, 64, R_>(tmX, tmW, tmU, p, dtype, st) \
+   : NB == 96 ? launch_cx<T_, 96, R_>(tmX, tmW, tmU, p, dtype, st) : launch_cx<T_, 128, R_>(tmX, tmW, tmU, p, dtype, st))
+#define AUM_CX(T_) (reverse ? AUM_CX2(T_, true) : AUM_CX2(T_, false))
   return dtype == AUM_F16 ? AUM_CX(__half) : AUM_CX(__nv_bfloat16);
 #undef AUM_CX
+#undef AUM_CX2
 }

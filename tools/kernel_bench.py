@@ -71,6 +71,16 @@ def main():
         w, b = rn(Di, 4, dtype=torch.float32), rn(Di, dtype=torch.float32)
         ms = timeit(lambda: ops.causal_conv1d(xz[..., :Di], w, b), flush=flush)
         report("conv1d_silu", ms, bytes_=2 * M * Di * s)
+    if dt != torch.float32 and (not only or "fused" in only):
+        # conv + SiLU fused into x_proj's operand producer (aum_conv_xproj_fwd): reads x, writes u, dt, B|C
+        xz = rn(B, Lq, 2 * Di)
+        w, b = rn(Di, 4, dtype=torch.float32), rn(Di, dtype=torch.float32)
+        wx = rn(R + 2 * N, Di, sc=Di ** -0.5)
+        dt_o = torch.empty(M, (R + 7) // 8 * 8, device=dev, dtype=dt)
+        bc_o = torch.empty(M, 2 * N, device=dev, dtype=torch.float32)
+        u_o = torch.empty(B, Lq, Di, device=dev, dtype=dt)
+        ms = timeit(lambda: ops.conv_xproj(xz[..., :Di], w, b, wx, R, dt_o, bc_o, u=u_o), flush=flush)
+        report("conv_xproj_fused", ms, bytes_=2 * M * Di * s + M * (R * s + 2 * N * 4))
     if not only or "norm" in only:
         x, r_ = rn(M, Dm), rn(M, Dm, dtype=torch.float32)
         w = torch.ones(Dm, device=dev)
