@@ -38,8 +38,8 @@ template <typename T> struct BwdLayout {
   static constexpr int OFF_CK = 0, OFF_D = OFF_CK + CK_BYTES, OFF_BC = OFF_D + D_BYTES, OFF_U = OFF_BC + BC_BYTES;
   static constexpr int OFF_G = OFF_U + A_BYTES, OFF_Z = OFF_G + A_BYTES, OFF_Y = OFF_Z + A_BYTES;
   static constexpr int STAGE_BYTES = OFF_Y + A_BYTES;
-  static constexpr int RED_PITCH = 36;                             // floats per lane row of the dB|dC transpose tile
-  static constexpr int RED_BYTES = (BT_CH / 32) * 32 * RED_PITCH * 4;   // one 32 x 32 (+pad) tile per warp: 18 KB
+  static constexpr int RED_PITCH = 34;                             // floats per lane row of the dB|dC transpose tile (see below)
+  static constexpr int RED_BYTES = (BT_CH / 32) * 32 * RED_PITCH * 4;   // one 32 x 32 (+pad) tile per warp: 17 KB
   static constexpr int SMEM_BYTES = 2 * STAGE_BYTES + RED_BYTES + 128 /*align slack*/ + 64 /*mbarriers, TMEM base slot*/;
 };
 
@@ -85,7 +85,9 @@ __device__ __forceinline__ void red_add_f32(float* p, float v) {
   asm volatile("red.global.add.f32 [%0], %1;" ::"l"(p), "f"(v) : "memory");
 }
 
-// Replay one forward step: h <- exp(dl A) h + dl u B; the new state goes to history slot `slot` (a TMEM address).
+// Replay one forward step: h <- exp(dl A) h + dl u B; the new state goes to history slot `slot` (a TMEM address) unless
+// it is the chunk's last step, whose result stays in registers (it is the first h_s the reverse-time loop needs).
+template <bool STORE>
 __device__ __forceinline__ void replay_step(float u, float dl, uint32_t a_bc, uint32_t slot,
                                             f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2]) {
   const float du_ = dl * u;
@@ -98,30 +100,37 @@ __device__ __forceinline__ void replay_step(float u, float dl, uint32_t a_bc, ui
     h[2 * q] = fma2(pk2(ex2_approx(e0), ex2_approx(e1)), h[2 * q], mul2(du2, pk2(Bv.x, Bv.y)));
     h[2 * q + 1] = fma2(pk2(ex2_approx(e2), ex2_approx(e3)), h[2 * q + 1], mul2(du2, pk2(Bv.z, Bv.w)));
   }
-  tmem_st16(slot, h);
+  if (STORE) tmem_st16(slot, h);
 }
 
-// Cross-channel sums of one token: every lane contributes 32 values (dB[0..15] | dC[0..15] of its channel), lane i
-// gets the warp's sum of value i.  Through a padded 32 x 32 shared-memory tile owned by the warp: 8 conflict-free
-// 16-byte stores + 32 conflict-free loads + adds per lane = 74 instructions, against 124 for the 31-shuffle butterfly
-// (each of its steps is 2 selects + shuffle + add) - in a kernel that is issue-bound.
-__device__ __forceinline__ float smem_transpose_reduce(const float (&v)[32], uint32_t tile, int lane) {
-  constexpr int P = 36;
-  const uint32_t row = tile + (uint32_t)(lane * P * 4);
-#pragma unroll
-  for (int i = 0; i < 8; ++i)
-    asm volatile("st.shared.v4.f32 [%0], {%1, %2, %3, %4};" ::"r"(row + 16u * i), "f"(v[4 * i]), "f"(v[4 * i + 1]),
-                 "f"(v[4 * i + 2]), "f"(v[4 * i + 3]) : "memory");
+// Cross-channel sums of one token: every lane contributes 32 values (dB[0..15] | dC[0..15] of its channel) and the warp
+// needs the 32 column sums.  Through a padded 32 x 32 shared-memory tile owned by the warp, with everything kept as packed
+// fp32 pairs: each packed product is stored straight from its 64-bit register (16 x st.shared.b64, no unpacking, no
+// staging array), then lanes 0-15 sum rows 0-15 and lanes 16-31 rows 16-31 of column PAIR (2 hl, 2 hl + 1) with 16 x
+// ld.shared.b64 + add.f32x2, one shuffle pair joins the halves, and lanes 0-15 write the 32 sums as 16 float2.  Row pitch
+// 34 floats: the 16 lanes of a 64-bit access hit 16 distinct bank pairs in both the row-wise stores and the column-wise
+// loads.  ~55 instructions per step against 74 + 32 unpacking moves for the scalar version of round 1 (in a kernel that
+// is issue-bound).
+__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
+__device__ __forceinline__ void sts_pair(uint32_t a, f32x2 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+__device__ __forceinline__ f32x2 lds_pair(uint32_t a) { f32x2 v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
+
+// After every lane has stored its 16 pairs into its row: the column sums.  Returns, in lanes 0-15, the sums of columns
+// (2 lane, 2 lane + 1) as (lo, hi).
+__device__ __forceinline__ void smem_column_sums(uint32_t tile, int lane, float& lo, float& hi) {
+  constexpr int P = 34;
   __syncwarp();
-  const uint32_t col = tile + (uint32_t)(lane * 4);
-  float s0 = 0.f, s1 = 0.f, s2 = 0.f, s3 = 0.f;
+  const uint32_t base = tile + (uint32_t)(((lane >> 4) * 16 * P + 2 * (lane & 15)) * 4);
+  f32x2 s0 = pk2(0.f, 0.f), s1 = s0;
 #pragma unroll
-  for (int r = 0; r < 32; r += 4) {
-    s0 += ldsf(col + (uint32_t)((r + 0) * P * 4)); s1 += ldsf(col + (uint32_t)((r + 1) * P * 4));
-    s2 += ldsf(col + (uint32_t)((r + 2) * P * 4)); s3 += ldsf(col + (uint32_t)((r + 3) * P * 4));
+  for (int r = 0; r < 16; r += 2) {
+    s0 = add2(s0, lds_pair(base + (uint32_t)(r * P * 4)));
+    s1 = add2(s1, lds_pair(base + (uint32_t)((r + 1) * P * 4)));
   }
   __syncwarp();                     // the tile is rewritten at the next step
-  return (s0 + s1) + (s2 + s3);
+  upk2(add2(s0, s1), lo, hi);
+  lo += __shfl_xor_sync(0xffffffffu, lo, 16);
+  hi += __shfl_xor_sync(0xffffffffu, hi, 16);
 }
 
 template <typename T>
@@ -246,6 +255,7 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
     const uint32_t t_bc = st + BL::OFF_BC + (uint32_t)row_first * SCAN_ROW * 4u;
 
     // ---- replay: slot j = state before step j (slot 0 = the forward kernel's checkpoint)
+    f32x2 hcur[SCAN_NS / 2];          // h_s of the reverse-time step in progress
     {
       f32x2 h[SCAN_NS / 2];
       const uint32_t ck = st + BL::OFF_CK + (uint32_t)tig * 4u;
@@ -255,9 +265,14 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
       uint32_t a_u = t_u, a_d = t_d, a_bc = t_bc, slot = hcol + SCAN_NS;
 #pragma unroll 1
       for (int j = 0; j < ns - 1; ++j) {
-        replay_step(ldst<T>(a_u), ldsf(a_d), a_bc, slot, h, a2);
+        replay_step<true>(ldst<T>(a_u), ldsf(a_d), a_bc, slot, h, a2);
         a_u += s16; a_d += s32; a_bc += sbc; slot += SCAN_NS;
       }
+      // the chunk's last step: its result h_{ns-1} is not history (it is the next chunk's checkpoint) but the reverse-time
+      // loop below starts with it, and from there on carries h_s over from the h_{s-1} it loads - no recomputation
+      replay_step<false>(ldst<T>(a_u), ldsf(a_d), a_bc, slot, h, a2);
+#pragma unroll
+      for (int k = 0; k < SCAN_NS / 2; ++k) hcur[k] = h[k];
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // the history is read back by the same thread below
     }
 
@@ -272,7 +287,9 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
       const int64_t r_last = (int64_t)row0 + (rev ? (L - 1 - (s0 + jl)) : (s0 + jl));      // global row of step s0+jl
       float* dup = d.du + r_last * d.ld_du + ch;
       float* ddp = d.ddelta + r_last * d.ld_dd + ch;
-      float* wsp = d.dbc_ws + ((int64_t)part * rows_total + r_last) * 32 + lane;
+      float* wsp = d.dbc_ws + ((int64_t)part * rows_total + r_last) * 32 + 2 * (lane & 15);   // lanes 0-15 store float2
+      const uint32_t red_tile = redt + (uint32_t)((tig >> 5) * 32 * BL::RED_PITCH * 4);
+      const uint32_t red_row = red_tile + (uint32_t)(lane * BL::RED_PITCH * 4);
       T* dzp = p.dz ? reinterpret_cast<T*>(p.dz) + r_last * p.ld_dz + ch : nullptr;
       T* ozp = p.outz ? reinterpret_cast<T*>(p.outz) + r_last * p.ld_oz + ch : nullptr;
       // one step backwards in time moves one global row against the walk direction
@@ -286,7 +303,6 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
         const float sz = has_z ? silu_f(zv) : 1.f;
         const float dy = go * sz;
         dD_acc = fmaf(dy, u, dD_acc);
-        float red[32];
         const float dlu = dl * u;
         const f32x2 dl2 = pk2(dl, dl), dy2 = pk2(dy, dy), dlu2 = pk2(dlu, dlu);
         f32x2 sB2 = pk2(0.f, 0.f), dd2 = pk2(0.f, 0.f);
@@ -306,15 +322,13 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
             const f32x2 a = pk2(ex2_approx(e0), ex2_approx(e1));
             const f32x2 dh = fma2(Cp, dy2, gcar[k]);
             gcar[k] = mul2(a, dh);
-            const f32x2 hcur = fma2(a, hp[hq], mul2(dlu2, Bp));     // h_s recomputed (cheaper than another load)
             const f32x2 t1 = mul2(gcar[k], hp[hq]);                 // dh * a * h_{s-1}
             dA_acc[k] = fma2(t1, dl2, dA_acc[k]);
             dd2 = fma2(t1, Av2[k], dd2);
             sB2 = fma2(dh, Bp, sB2);
-            float r0, r1; upk2(mul2(dh, dlu2), r0, r1);             // dB contributions
-            red[2 * k] = r0; red[2 * k + 1] = r1;
-            upk2(mul2(hcur, dy2), r0, r1);                          // dC contributions
-            red[SCAN_NS + 2 * k] = r0; red[SCAN_NS + 2 * k + 1] = r1;
+            sts_pair(red_row + (uint32_t)(8 * k), mul2(dh, dlu2));                    // dB contributions
+            sts_pair(red_row + (uint32_t)(8 * (SCAN_NS / 2 + k)), mul2(hcur[k], dy2));   // dC contributions (h_s carried over)
+            hcur[k] = hp[hq];                                       // h_{s-1} is the next (earlier) step's h_s
           }
         }
         float s0_, s1_, d0_, d1_;
@@ -325,7 +339,11 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
         // cross-channel sums of this token: lane i of each warp ends up with value i; one plain 128-byte store per
         // warp into this warp's slice of the partial workspace (summed over warps by dbc_reduce_kernel).
         // Channels past D read zero-filled tiles, so their contributions are exact zeros.
-        *wsp = smem_transpose_reduce(red, redt + (uint32_t)((tig >> 5) * 32 * BL::RED_PITCH * 4), lane);
+        {
+          float c_lo, c_hi;
+          smem_column_sums(red_tile, lane, c_lo, c_hi);
+          if (lane < 16) *reinterpret_cast<float2*>(wsp) = make_float2(c_lo, c_hi);
+        }
         if (spg_on) dd *= 1.f - __expf(-dl);                       // softplus'(pre) = 1 - exp(-delta)
         if (active) {
           if (accumulate) { red_add_f32(dup, duv); red_add_f32(ddp, dd); }

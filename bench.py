@@ -399,7 +399,12 @@ def main():
         import torch.distributed as dist_
         dist = dist_
         with _StdoutToStderr():
-            dist.init_process_group("nccl", device_id=dev)
+            try:        # NCCL kernels on a high-priority stream: the gradient all-reduce pieces launched from backward
+                        # hooks then get SMs while the backward kernels of earlier layers are still queued
+                opts = dist.ProcessGroupNCCL.Options(is_high_priority_stream=True)
+                dist.init_process_group("nccl", device_id=dev, pg_options=opts)
+            except Exception:
+                dist.init_process_group("nccl", device_id=dev)
             dist.barrier()          # forces communicator creation (and NCCL's banner) now
             torch.cuda.synchronize()
 

@@ -24,7 +24,6 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--depth", type=int, default=24)
     ap.add_argument("--dtype", default="bf16")
-    ap.add_argument("--torch-adam", action="store_true", help="torch.optim.Adam instead of the fused flat-buffer step")
     args = ap.parse_args()
     rank, local = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -40,24 +39,15 @@ def main():
         for blk in model.layers:
             blk.mixer.A_log.add_(0.1 * torch.randn(blk.mixer.A_log.shape, generator=g).to(dev))
             blk.mixer.A_b_log.add_(0.1 * torch.randn(blk.mixer.A_b_log.shape, generator=g).to(dev))
-    red = D.FlatGradReducer(model.parameters())
-    if args.torch_adam:
-        opt = torch.optim.Adam(model.parameters(), lr=1e-5, betas=(0.95, 0.999), weight_decay=5e-7)
-    else:
-        opt = D.FlatAdam(red, lr=1e-5, betas=(0.95, 0.999), weight_decay=5e-7)
+    from aum_b200.trainer import TrainStep
+    ts = TrainStep(model, lr=1e-5, n_chunks=3)
+    red = ts.reducer
     x = (0.5 * torch.randn(args.batch, 1024, 128, generator=g)).to(dev)
     y = (torch.rand(args.batch, 309, generator=g) > 0.97).float().to(dev)
-    ar_ms = []
+    ts.timing = ar_ms = []
 
     def step():
-        red.zero()
-        loss = torch.nn.functional.binary_cross_entropy_with_logits(model(x), y)
-        loss.backward()
-        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        e0.record(); red.reduce(); e1.record()
-        opt.step()
-        ar_ms.append((e0, e1))
-        return loss
+        return ts(x, y)
 
     for _ in range(args.warmup):
         step()
