@@ -7,7 +7,6 @@
 // TL+3 input rows of a thread are independent loads issued up front (one DRAM latency per thread), kept PACKED
 // in registers (19 regs) so the kernel runs at full occupancy, and the 3-row halo is served by L1/L2.
 // Algorithmic bytes per (token, channel): read s + write s (s = itemsize).
-#include <stdlib.h>
 #include "scan_common.cuh"   // packed fp32x2 helpers
 
 namespace aum {
@@ -408,138 +407,6 @@ conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
   }
 }
 
-
-// ---- fast path: 4 adjacent channels per thread, packed fp32x2 math ----------------------------------------------
-// Same decomposition (lane = channel group, warp = one of 4 consecutive 8-token tiles of a sequence) with a channel QUAD
-// per lane: a warp row is 128 channels (256 B of 16-bit x, 512 B of fp32 dout), every loaded row is converted once into
-// two fp32x2 pairs and the pre-activation, dx and dw sums run as FFMA2 on the pairs - about half the instructions per
-// element of the pair kernel above, which was issue-bound at ~3.7x its HBM floor (0.171 ms per config-3 block).
-// Needs D % 4 == 0 and 16-byte aligned rows of x / dout / dx.
-template <typename T>
-__global__ void __launch_bounds__(128, 3)
-conv1d_bwd_vec4_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ bias,
-                       const float* __restrict__ dout, const float* __restrict__ dout2, int64_t ldd,
-                       T* __restrict__ dx, int64_t ld_dx, float* __restrict__ dw, float* __restrict__ dbias,
-                       int batch, int L, int D, int W, int silu, int reverse, int n_cgrp, int n_tgrp) {
-  __shared__ float red[4][20][32];
-  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
-  const int cg = blockIdx.x % n_cgrp;
-  const int tg = (blockIdx.x / n_cgrp) % n_tgrp;
-  const int b = blockIdx.x / (n_cgrp * n_tgrp);
-  const int c0 = (cg * 32 + lane) * 4;
-  const bool ok = c0 < D;                            // D % 4 == 0: the whole quad is in range or none of it
-  const int p0 = (tg * 4 + wrp) * CB_TL;             // first walk position of this warp's tile (4 warps per block)
-
-  // taps as channel pairs (a: channels c0, c0+1; b: c0+2, c0+3), zero-padded at the front to CONV_MAXW
-  f32x2 wa[CONV_MAXW], wb[CONV_MAXW], ba = pk2(0.f, 0.f), bb = ba;
-#pragma unroll
-  for (int j = 0; j < CONV_MAXW; ++j) {
-    const int k = j - (CONV_MAXW - W);
-    float t[4];
-#pragma unroll
-    for (int v = 0; v < 4; ++v) t[v] = (ok && k >= 0) ? __ldg(w + (int64_t)(c0 + v) * W + k) : 0.f;
-    wa[j] = pk2(t[0], t[1]); wb[j] = pk2(t[2], t[3]);
-  }
-  if (ok && bias != nullptr) { const float4 t = __ldg(reinterpret_cast<const float4*>(bias + c0)); ba = pk2(t.x, t.y); bb = pk2(t.z, t.w); }
-
-  f32x2 acc_a[5], acc_b[5];                          // dw taps 0..3 and dbias, per channel pair
-#pragma unroll
-  for (int i = 0; i < 5; ++i) { acc_a[i] = pk2(0.f, 0.f); acc_b[i] = pk2(0.f, 0.f); }
-
-  if (p0 < L && ok) {
-    const int64_t base = (int64_t)b * L;
-    auto tok = [&](int p) { return reverse ? (L - 1 - p) : p; };
-    constexpr int NX = CB_TL + 2 * (CONV_MAXW - 1);  // x at walk positions p0-3 .. p0+TL+2
-    constexpr int ND = CB_TL + (CONV_MAXW - 1);      // dout at p0 .. p0+TL+2
-    Quad<T> xq[NX];
-#pragma unroll
-    for (int j = 0; j < NX; ++j) {
-      const int p = p0 - (CONV_MAXW - 1) + j;
-      xq[j].zero();
-      if (p >= 0 && p < L) xq[j].load(x + (base + tok(p)) * ldx + c0);
-    }
-    f32x2 ga[ND], gb[ND];                            // dout (+ dout2), later overwritten by dc = dout * act'(c)
-#pragma unroll
-    for (int j = 0; j < ND; ++j) {
-      const int p = p0 + j;
-      ga[j] = pk2(0.f, 0.f); gb[j] = ga[j];
-      if (p < L) {
-        float4 g = __ldg(reinterpret_cast<const float4*>(dout + (base + tok(p)) * ldd + c0));
-        if (dout2 != nullptr) {
-          const float4 g2 = __ldg(reinterpret_cast<const float4*>(dout2 + (base + tok(p)) * ldd + c0));
-          g.x += g2.x; g.y += g2.y; g.z += g2.z; g.w += g2.w;
-        }
-        ga[j] = pk2(g.x, g.y); gb[j] = pk2(g.z, g.w);
-      }
-    }
-    f32x2 xa[NX], xb[NX];
-#pragma unroll
-    for (int j = 0; j < NX; ++j) xq[j].f(xa[j], xb[j]);
-    // dc[j] = dout * act'(c) at position p0 + j (zero past the end of the sequence: ga / gb are zero there)
-#pragma unroll
-    for (int j = 0; j < ND; ++j) {
-      f32x2 ca = ba, cb = bb;
-#pragma unroll
-      for (int k = 0; k < CONV_MAXW; ++k) { ca = fma2(wa[k], xa[j + k], ca); cb = fma2(wb[k], xb[j + k], cb); }
-      if (silu) {
-        float c[4], g[4];
-        upk2(ca, c[0], c[1]); upk2(cb, c[2], c[3]);
-        upk2(ga[j], g[0], g[1]); upk2(gb[j], g[2], g[3]);
-#pragma unroll
-        for (int v = 0; v < 4; ++v) {
-          float sg;
-          asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sg) : "f"(1.f + ex2_approx(-1.4426950408889634f * c[v])));
-          g[v] *= sg * fmaf(c[v], 1.f - sg, 1.f);                 // silu'(c) = s (1 + c (1 - s))
-        }
-        ga[j] = pk2(g[0], g[1]); gb[j] = pk2(g[2], g[3]);
-      }
-    }
-#pragma unroll
-    for (int i = 0; i < CB_TL; ++i) {
-      const int p = p0 + i;
-      if (p < L) {
-        f32x2 da = pk2(0.f, 0.f), db = da;
-#pragma unroll
-        for (int k = 0; k < CONV_MAXW; ++k) {        // dx[p] = sum_k w[k] dc[p + 3 - k]
-          da = fma2(wa[k], ga[i + (CONV_MAXW - 1) - k], da);
-          db = fma2(wb[k], gb[i + (CONV_MAXW - 1) - k], db);
-        }
-        float d0, d1, d2, d3;
-        upk2(da, d0, d1); upk2(db, d2, d3);
-        Quad<T>::store(dx + (base + tok(p)) * ld_dx + c0, d0, d1, d2, d3);
-#pragma unroll
-        for (int k = 0; k < CONV_MAXW; ++k) {        // dw[k] += dc[p] x[p-3+k]
-          acc_a[k] = fma2(ga[i], xa[i + k], acc_a[k]);
-          acc_b[k] = fma2(gb[i], xb[i + k], acc_b[k]);
-        }
-        acc_a[4] = fma2(ga[i], pk2(1.f, 1.f), acc_a[4]);
-        acc_b[4] = fma2(gb[i], pk2(1.f, 1.f), acc_b[4]);
-      }
-    }
-  }
-  // red[wrp][v * 5 + j][lane]: channel v of the quad, tap j (j == 4: bias)
-#pragma unroll
-  for (int j = 0; j < 5; ++j) {
-    float a0, a1, b0, b1;
-    upk2(acc_a[j], a0, a1); upk2(acc_b[j], b0, b1);
-    red[wrp][0 * 5 + j][lane] = a0; red[wrp][1 * 5 + j][lane] = a1;
-    red[wrp][2 * 5 + j][lane] = b0; red[wrp][3 * 5 + j][lane] = b1;
-  }
-  __syncthreads();
-  if (wrp < 4 && ok) {                               // warp v reduces channel v of every lane's quad
-    const int v = wrp;
-#pragma unroll
-    for (int j = 0; j < 5; ++j) {
-      float sum = 0.f;
-#pragma unroll
-      for (int k = 0; k < 4; ++k) sum += red[k][v * 5 + j][lane];
-      const int c = c0 + v;
-      if (j < 4) { const int k = j - (CONV_MAXW - W); if (k >= 0) atomicAdd(dw + (int64_t)c * W + k, sum); }
-      else if (dbias != nullptr) atomicAdd(dbias + c, sum);
-    }
-  }
-}
-
 }  // namespace aum
 
 extern "C" int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w, const float* bias,
@@ -553,31 +420,10 @@ extern "C" int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w,
   AUM_REQUIRE(batch >= 0 && L >= 0 && D >= 0, "aum_causal_conv1d_bwd: negative size");
   AUM_REQUIRE(ldx >= D && ldd >= D && ld_dx >= D, "aum_causal_conv1d_bwd: leading dimension smaller than D");
   if (batch == 0 || L == 0 || D == 0) return 0;
-  cudaStream_t st = (cudaStream_t)stream;
-  {
-    // 4-channel packed-math kernel when every row is 16-byte addressable (all AuM shapes); AUM_CONV_BWD_VEC4=0 disables
-    static const bool vec4_off = [] { const char* e = getenv("AUM_CONV_BWD_VEC4"); return e && atoi(e) == 0; }();
-    const int esz = dtype_size(dtype);
-    const bool al = D % 4 == 0 && aligned16(dout) && (ldd * 4) % 16 == 0 && (dout2 == nullptr || aligned16(dout2)) &&
-                    (reinterpret_cast<uintptr_t>(x) % (4 * esz) == 0) && (ldx * esz) % (4 * esz) == 0 &&
-                    (reinterpret_cast<uintptr_t>(dx) % (4 * esz) == 0) && (ld_dx * esz) % (4 * esz) == 0 &&
-                    (bias == nullptr || aligned16(bias));
-    if (al && !vec4_off) {
-      const int n_cgrp4 = ceil_div(D, 128), n_tgrp4 = ceil_div(L, 4 * CB_TL);
-      const int64_t blocks4 = (int64_t)batch * n_cgrp4 * n_tgrp4;
-      AUM_REQUIRE(blocks4 < (1ll << 31), "aum_causal_conv1d_bwd: grid too large");
-      switch (dtype) {
-        case AUM_F32:  conv1d_bwd_vec4_kernel<float><<<(unsigned)blocks4, 128, 0, st>>>((const float*)x, ldx, w, bias, dout, dout2, ldd, (float*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp4, n_tgrp4); break;
-        case AUM_F16:  conv1d_bwd_vec4_kernel<__half><<<(unsigned)blocks4, 128, 0, st>>>((const __half*)x, ldx, w, bias, dout, dout2, ldd, (__half*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp4, n_tgrp4); break;
-        case AUM_BF16: conv1d_bwd_vec4_kernel<__nv_bfloat16><<<(unsigned)blocks4, 128, 0, st>>>((const __nv_bfloat16*)x, ldx, w, bias, dout, dout2, ldd, (__nv_bfloat16*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp4, n_tgrp4); break;
-        default: set_error("aum_causal_conv1d_bwd: bad dtype %d", dtype); return 1;
-      }
-      return check_launch("aum_causal_conv1d_bwd(vec4)");
-    }
-  }
   const int n_cgrp = ceil_div(D, 64), n_tgrp = ceil_div(L, 8 * CB_TL);
   const int64_t blocks = (int64_t)batch * n_cgrp * n_tgrp;
   AUM_REQUIRE(blocks < (1ll << 31), "aum_causal_conv1d_bwd: grid too large");
+  cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
     case AUM_F32:  conv1d_bwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, ldx, w, bias, dout, dout2, ldd, (float*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
     case AUM_F16:  conv1d_bwd_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, ldx, w, bias, dout, dout2, ldd, (__half*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
