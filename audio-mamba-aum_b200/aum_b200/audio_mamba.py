@@ -142,18 +142,19 @@ class AudioMamba(nn.Module):
         return ops.assemble_tokens(tok.view(B, N, self.embed_dim), pos, cls)
 
     def _forward_train(self, x: torch.Tensor, return_features: bool) -> torch.Tensor:
-        """Autograd path (training): same data flow, differentiable glue.  The mixer and add+RMSNorm go through the
-        autograd.Functions of aum_b200.autograd (native backward kernels); the small front/back ends (patch-embed
-        conv, cls/pos assembly, head) use torch ops so autograd covers them."""
+        """Autograd path (training): same data flow.  Mixer, add+RMSNorm, the patch-embedding map and the head go through
+        the autograd.Functions of aum_b200.autograd (native forward and backward kernels, no cuBLAS / cuDNN); only the
+        cls / position assembly (a cat and three adds, once per step) is torch ops."""
+        from .autograd import LinearFn
         from .modules import rms_norm_fn
         act = torch.get_autocast_dtype("cuda") if torch.is_autocast_enabled() else self.act_dtype
         B = x.shape[0]
-        pf, pt = self.patch
         gf, gt = self.grid
-        # stride == kernel conv as im2col + linear (plain fp32 matmul: cuDNN convolutions would silently use TF32)
-        cols = x.float().view(B, gt, pt, gf, pf).permute(0, 3, 1, 4, 2).reshape(B, gf * gt, pf * pt)
-        tok = torch.nn.functional.linear(cols, self.patch_embed.proj.weight.reshape(self.embed_dim, -1),
-                                         self.patch_embed.proj.bias)
+        # stride == kernel conv as im2col (one gather kernel, no gradient needed: x is data) + the engine's linear map,
+        # fp32 out as on the inference path
+        cols = ops.patchify(x.float().contiguous(), self.patch, act)
+        tok = LinearFn.apply(cols, self.patch_embed.proj.weight, self.patch_embed.proj.bias,
+                             torch.float32).view(B, gf * gt, self.embed_dim)
         N = tok.shape[1]
         tp = N // 2
         pe = self.pos_embed.pos_embed
@@ -173,7 +174,7 @@ class AudioMamba(nn.Module):
                            residual_in_fp32=True, eps=self.norm_f.eps)
         if return_features:
             return feat
-        return torch.nn.functional.linear(feat.float(), self.head.weight, self.head.bias)
+        return LinearFn.apply(feat.to(act).contiguous(), self.head.weight, self.head.bias, torch.float32)
 
     def grad_ready_order(self, n_chunks: int = 3):
         """Parameters in the order their gradients become final during backward (head and final norm first, then layers

@@ -31,7 +31,7 @@ F32 = torch.float32
 
 def _t(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """W^T as a contiguous `dtype` matrix (cached per parameter version) — the K-contiguous operand of dX = dY @ W."""
-    return mixer._cache.get(w, f"wT:{dtype}", lambda p: p.t().to(dtype).contiguous())
+    return mixer._cache.get(w, f"wT:{dtype}", lambda p: p.reshape(p.shape[0], -1).t().to(dtype).contiguous())
 
 
 def _direct(p) -> bool:
@@ -75,12 +75,15 @@ def _wgrad(dy2d, x2d, p):
 
 # ------------------------------------------------------------------------------------------------------
 class LinearFn(torch.autograd.Function):
-    """y[M, N] = x[M, K] @ W[N, K]^T (+ b): the in_proj matmul (mamba_simple.py:185-191) under autograd."""
+    """y[M, N] = x[M, K] @ W[N, K]^T (+ b): the in_proj matmul (mamba_simple.py:185-191) under autograd; also the
+    patch-embedding conv as a linear map of im2col rows (weight (N, 1, pf, pt) is used as (N, pf * pt)) and the head.
+    out_dtype: dtype of y (default: x's)."""
 
     @staticmethod
-    def forward(ctx, x2, weight, bias):
+    def forward(ctx, x2, weight, bias, out_dtype=None):
         act = x2.dtype
-        y = ops.gemm_tn(x2, mixer._w(weight, act), bias=mixer._f32(bias) if bias is not None else None)
+        w2 = mixer._cache.get(weight, f"w2d:{act}", lambda p: p.reshape(p.shape[0], -1).to(act).contiguous())
+        y = ops.gemm_tn(x2, w2, bias=mixer._f32(bias) if bias is not None else None, out_dtype=out_dtype)
         ctx.save_for_backward(x2)
         ctx.weight, ctx.bias = weight, bias
         return y
@@ -94,7 +97,7 @@ class LinearFn(torch.autograd.Function):
         dx = ops.gemm_tn(dy2, _t(w, act)) if ctx.needs_input_grad[0] else None
         dw = _wgrad(dy2, x2, w) if ctx.needs_input_grad[1] else None
         db = _deliver_value(b, dy2.float().sum(0)) if (b is not None and ctx.needs_input_grad[2]) else None
-        return dx, dw, db
+        return dx, dw, db, None
 
 
 # ------------------------------------------------------------------------------------------------------
@@ -309,7 +312,7 @@ def mamba_mixer_autograd(module, hidden_states):
     x2 = x.reshape(B * Lq, Dm)
     if x2.stride(-1) != 1:
         x2 = x2.contiguous()
-    xz = LinearFn.apply(x2, module.in_proj.weight, module.in_proj.bias).view(B, Lq, 2 * module.d_inner)
+    xz = LinearFn.apply(x2, module.in_proj.weight, module.in_proj.bias, None).view(B, Lq, 2 * module.d_inner)
     scale = 0.5 if (module.bimamba_type == "v2" and module.if_devide_out) else 1.0
     cfg = InnerCfg(module.bimamba_type, True, scale, True)
     out = InnerFn.apply(cfg, xz, *_inner_args(module))

@@ -52,6 +52,41 @@ def test_flat_gradient_buffer_layout():
     assert D.shard_range(10, 0, 4) == (0, 3) and D.shard_range(10, 3, 4) == (8, 10)
 
 
+def test_audio_mamba_mirror_accepts_the_reference_constructor_call():
+    """The reference builds its model with src/run.py:248-274's keyword set; the mirror takes exactly that call (options
+    that cannot change the default forward are accepted and ignored) and refuses options that would change it."""
+    import pytest
+    from aum_b200.audio_mamba import AudioMamba
+    m = AudioMamba(spectrogram_size=(128, 128), patch_size=(16, 16), strides=(16, 16), depth=2, embed_dim=96, num_classes=35,
+                   imagenet_pretrain=False, imagenet_pretrain_path=None, imagenet_pretrain_modelkey="model",
+                   aum_pretrain=False, aum_pretrain_path=None, aum_pretrain_fstride=16, aum_pretrain_tstride=16,
+                   pt_hw_seq_len=None, bilinear_rope=False, drop_path_rate=0.0, imagenet_load_double_cls_token=False,
+                   imagenet_load_middle_cls_token=True, use_double_cls_token=False, use_middle_cls_token=True,
+                   use_end_cls_token=False, bimamba_type="v1", transpose_token_sequence=False, if_cls_token=True,
+                   flexible_patch_sizes=None)
+    assert len(m.layers) == 2 and m.layers[0].mixer.bimamba_type == "v1"
+    for bad in (dict(bilinear_rope=True), dict(use_end_cls_token=True), dict(aum_pretrain=True), dict(drop_path_rate=0.1),
+                dict(some_unknown_option=1)):
+        with pytest.raises(NotImplementedError):
+            AudioMamba(depth=1, embed_dim=96, **bad)
+
+
+def test_weight_generation_invalidates_derived_caches():
+    """The fused Adam kernel writes parameters through raw pointers; FlatAdam bumps the engine's weight generation, which
+    every derived-weight cache entry (and AudioMamba's CUDA-graph key) is keyed on."""
+    import torch
+    from aum_b200 import mixer
+    p = torch.nn.Parameter(torch.ones(4, 4))
+    a = mixer._cache.get(p, "t:neg", lambda t: -t)
+    assert mixer._cache.get(p, "t:neg", lambda t: -t) is a
+    with torch.no_grad():
+        p.data.view(-1)[0] = 5.0                      # a raw write: no version bump
+    g0 = mixer.generation()
+    assert mixer.bump_generation() == g0 + 1
+    b = mixer._cache.get(p, "t:neg", lambda t: -t)
+    assert b is not a and float(b[0, 0]) == -5.0
+
+
 def test_bench_reference_arm_prints_the_contract_line():
     """`bench.py --impl reference` (the reference's own CPU path from oracle/_ref, one whole clip per step; the oracle
     port only where no staged reference exists): one JSON line with the same

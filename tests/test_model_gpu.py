@@ -106,3 +106,43 @@ def test_cuda_graph_and_sequence_groups_match_eager(bt):
         fast.head.weight.mul_(2.0); fast.head.bias.mul_(2.0)
         g2 = fast(x.pin_memory())
     torch.testing.assert_close(g2, 2.0 * g_out, rtol=1e-5, atol=1e-5)
+
+
+def test_cold_cache_multi_stream_forward_matches_single_stream():
+    """the FIRST eager forward of a model that splits its batch over two streams (derived-weight caches cold:
+    16-bit copies, -exp(A_log), padded dt_proj are built by that very forward) must equal the single-stream result, and
+    so must the first forward after a weight update."""
+    from aum_b200.audio_mamba import AudioMamba
+    torch.manual_seed(9)
+    kw = dict(embed_dim=192, depth=4, num_classes=35, spectrogram_size=(128, 256), bimamba_type="v1", act_dtype=torch.float16)
+    plain = AudioMamba(**kw).to(DEV).eval()
+    x = 0.5 * torch.randn(8, 256, 128, device=DEV)
+    with torch.no_grad():
+        want = torch.cat([plain(xc) for xc in x.chunk(2, dim=0)], dim=0)
+    for _ in range(3):                      # fresh models: every first call is a cold-cache call
+        two = AudioMamba(**kw, micro_batches=2).to(DEV).eval()
+        two.load_state_dict(plain.state_dict(), strict=True)
+        with torch.no_grad():
+            got_cold = two(x)
+            got_warm = two(x)               # second call forks onto the two streams
+            assert torch.equal(got_cold, want) and torch.equal(got_warm, want)
+            two.head.weight.mul_(2.0); two.head.bias.mul_(2.0)      # in-place update: caches cold again
+            got_upd = two(x)
+        torch.testing.assert_close(got_upd, 2.0 * want, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.skipif(torch.cuda.device_count() < 2, reason="needs two GPUs")
+def test_ops_run_on_the_tensors_device_not_the_current_one():
+    """a model on cuda:1 while cuda:0 is current (the reference's kernels take a CUDAGuard from their tensors)."""
+    from aum_b200.audio_mamba import AudioMamba
+    torch.manual_seed(10)
+    kw = dict(embed_dim=192, depth=2, num_classes=35, spectrogram_size=(128, 128), bimamba_type="v1", act_dtype=torch.float16)
+    m0 = AudioMamba(**kw).to("cuda:0").eval()
+    m1 = AudioMamba(**kw).to("cuda:1").eval()
+    m1.load_state_dict(m0.state_dict(), strict=True)
+    x = 0.5 * torch.randn(2, 128, 128)
+    torch.cuda.set_device(0)
+    with torch.no_grad():
+        a = m0(x.to("cuda:0"))
+        b = m1(x.to("cuda:1"))              # current device is still 0
+    assert b.device.index == 1 and torch.equal(a.cpu(), b.cpu())

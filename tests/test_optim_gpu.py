@@ -41,3 +41,20 @@ def test_adam_grad_scale_and_empty():
     torch.testing.assert_close(p, torch.full_like(p, 0.9), rtol=1e-6, atol=1e-6)
     e = torch.empty(0, device=DEV)
     ops.adam_step(e, e, e, e, lr=0.1)
+
+
+def test_flat_adam_skips_a_step_with_non_finite_gradients():
+    """The fp16 recipe's GradScaler behaviour (accelerate --mixed_precision=fp16, which the reference's scripts use):
+    an inf / NaN anywhere in the flat gradient skips the update - p, m, v and the step count untouched."""
+    from aum_b200 import dist as D
+    ps = [torch.nn.Parameter(torch.ones(33, device=DEV)), torch.nn.Parameter(torch.ones(5, 7, device=DEV))]
+    red = D.FlatGradReducer(ps)
+    opt = D.FlatAdam(red, lr=0.1)
+    ps[0].grad.fill_(1.0); ps[1].grad.fill_(1.0)
+    ps[1].grad[2, 3] = float("inf")
+    before = opt.flat_p.clone()
+    assert opt.step(grad_scale=0.5, skip_nonfinite=True) is False
+    assert torch.equal(opt.flat_p, before) and opt.t == 0 and float(opt.m.abs().sum()) == 0.0
+    ps[1].grad[2, 3] = 1.0
+    assert opt.step(grad_scale=0.5, skip_nonfinite=True) is True
+    assert opt.t == 1 and not torch.equal(opt.flat_p, before)
