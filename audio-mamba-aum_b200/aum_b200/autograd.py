@@ -223,10 +223,16 @@ class InnerFn(torch.autograd.Function):
         d_f = ops.ScanBwdDirection(u, delta, A_f, bc, Dv, du, ddelta, dA, dD_buf.view(Di) if dD_buf is not None else None,
                                    dbc, ck_f, ckpt_valid=True)
         d_b = None
+        du_b = ddelta_b = None
         if cfg.mode == "v1":
+            # each direction writes its own du / ddelta with plain stores (sharing one pair costs a 2 x 100 MB zero fill
+            # plus atomic read-modify-writes from both directions at AuM-Base size); their sum is formed where they are
+            # consumed anyway: in the conv backward's input and in the cast + column-sum pass of the dt_proj chain
             A_r = _A(A_b, cfg)
             dA_b = torch.zeros((Di, N), **f32)
-            d_b = ops.ScanBwdDirection(u, delta, A_r, bc, Dv, du, ddelta, dA_b,
+            du_b = torch.empty((B, Lq, Di), **f32)
+            ddelta_b = torch.empty((B, Lq, Di), **f32)
+            d_b = ops.ScanBwdDirection(u, delta, A_r, bc, Dv, du_b, ddelta_b, dA_b,
                                        dD_buf.view(Di) if dD_buf is not None else None, dbc, ck_b, ckpt_valid=True)
         elif cfg.mode == "v2":
             ub, deltab = recompute(cw_b, cb_b, dtw_b, dtb_b, dt_b, True)
@@ -250,11 +256,23 @@ class InnerFn(torch.autograd.Function):
         dxc = torch.empty((B, Lq, Di), device=dev, dtype=act) if cfg.mode == "v2" else None
         dxc_b = torch.empty_like(dxc) if cfg.mode == "v2" else None
 
-        def branch_bwd(sfx, cw_, cb_, xw_, dtw_, dtb_, u_, dt_, du_, ddelta_, dbc_, reverse, dx_out):
+        def branch_bwd(sfx, cw_, cb_, xw_, dtw_, dtb_, u_, dt_, du_, ddelta_, dbc_, reverse, dx_out, du2_=None, ddelta2_=None):
             R = dtw_.shape[1]
-            dpre = ddelta_.view(M, Di)                      # gradient w.r.t. dt_proj's pre-activation (see above)
-            g["dtb" + sfx] = _deliver_value(dtb_, dpre.sum(0)) if dtb_ is not None else None
-            dpre_h = dpre.to(act)
+            # gradient w.r.t. dt_proj's pre-activation (see above): sum of the directions, its 16-bit copy for the two
+            # GEMMs below and its column sums (the bias gradient) in ONE pass (:556, :583-586)
+            if dtb_ is not None and dtb_.requires_grad:
+                db_buf_, db_direct_ = _grad_buffer(dtb_, (1, Di))
+            else:
+                db_buf_, db_direct_ = None, False
+            if Di % 4 == 0:
+                dpre_h = ops.sum_cast_colsum(ddelta_.view(M, Di), ddelta2_.view(M, Di) if ddelta2_ is not None else None, act,
+                                             db_buf_.view(Di) if db_buf_ is not None else None)
+            else:           # odd widths (never AuM's: d_inner = 2 d_model): the same three steps as torch ops
+                dpre = ddelta_.view(M, Di) if ddelta2_ is None else ddelta_.view(M, Di) + ddelta2_.view(M, Di)
+                if db_buf_ is not None:
+                    db_buf_.view(Di).add_(dpre.sum(0))
+                dpre_h = dpre.to(act)
+            g["dtb" + sfx] = _deliver(dtb_, db_buf_, db_direct_) if db_buf_ is not None else None
             g["dtw" + sfx] = _wgrad(dpre_h, dt_[:, :R], dtw_)                                  # (Di, R)   (:586)
             # dx_dbl = [d(dt) | dB | dC]   (M, R+2N)
             wdb = mixer._round_up(R + 2 * N, 8)
@@ -273,11 +291,13 @@ class InnerFn(torch.autograd.Function):
             db_buf, db_direct = _grad_buffer(cb_, (1, Di)) if cb_ is not None else (None, False)
             ops.causal_conv1d_bwd(xz[..., :Di], mixer._conv_w(cw_), mixer._f32(cb_) if cb_ is not None else None,
                                   du_.view(B, Lq, Di), dx_out, dw_buf, db_buf.view(Di) if db_buf is not None else None,
-                                  silu=True, reverse=reverse, dout2=du_x.view(B, Lq, Di))   # sums both terms on the fly
+                                  silu=True, reverse=reverse, dout2=du_x.view(B, Lq, Di),
+                                  dout3=du2_.view(B, Lq, Di) if du2_ is not None else None)   # sums the terms on the fly
             g["cw" + sfx] = _deliver(cw_, dw_buf, dw_direct)
             g["cb" + sfx] = _deliver(cb_, db_buf, db_direct) if cb_ is not None else None
 
-        branch_bwd("", cw, cb, xw, dtw, dtb, u, dt, du, ddelta, dbc, False, dxz[..., :Di] if cfg.mode != "v2" else dxc)
+        branch_bwd("", cw, cb, xw, dtw, dtb, u, dt, du, ddelta, dbc, False, dxz[..., :Di] if cfg.mode != "v2" else dxc,
+                   du2_=du_b if cfg.mode == "v1" else None, ddelta2_=ddelta_b if cfg.mode == "v1" else None)
         # A = -exp(A_log)  =>  dA_log = dA * A
         g["A"] = _deliver_value(A, dA * A_f if cfg.a_is_log else dA)
         g["D"] = _deliver(D, dD_buf, dD_direct) if D is not None else None

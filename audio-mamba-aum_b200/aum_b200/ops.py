@@ -267,19 +267,39 @@ def transpose(src: torch.Tensor, dst: Optional[torch.Tensor] = None, dst_dtype: 
 
 def causal_conv1d_bwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Tensor], dout: torch.Tensor,
                       dx: torch.Tensor, dw: torch.Tensor, dbias: Optional[torch.Tensor], *, silu: bool = True,
-                      reverse: bool = False, dout2: Optional[torch.Tensor] = None) -> None:
-    """Backward of causal_conv1d.  x, dx: (B, L, D) token-major (dtype); dout: (B, L, D) fp32;
-    dw (D, W) / dbias (D) fp32 are accumulated into."""
+                      reverse: bool = False, dout2: Optional[torch.Tensor] = None,
+                      dout3: Optional[torch.Tensor] = None) -> None:
+    """Backward of causal_conv1d.  x, dx: (B, L, D) token-major (dtype); dout (+ dout2 + dout3, summed on the fly):
+    (B, L, D) fp32; dw (D, W) / dbias (D) fp32 are accumulated into."""
     L.require_cuda(x, w, dout, dx, dw)
     B, Lq, D = x.shape
     if dout.dtype != torch.float32 or dw.dtype != torch.float32 or dx.dtype != x.dtype:
         raise L.AumError("causal_conv1d_bwd: dout/dw must be fp32 and dx must match x")
-    if dout2 is not None and (dout2.dtype != torch.float32 or _as_rows(dout2)[2] != _as_rows(dout)[2]):
-        raise L.AumError("causal_conv1d_bwd: dout2 must be fp32 with dout's pitch")
-    rc = L.lib().aum_causal_conv1d_bwd(L.ptr(x), _as_rows(x)[2], L.ptr(w), L.ptr(bias), L.ptr(dout), L.ptr(dout2), _as_rows(dout)[2],
+    for extra in (dout2, dout3):
+        if extra is not None and (extra.dtype != torch.float32 or _as_rows(extra)[2] != _as_rows(dout)[2]):
+            raise L.AumError("causal_conv1d_bwd: dout2 / dout3 must be fp32 with dout's pitch")
+    rc = L.lib().aum_causal_conv1d_bwd(L.ptr(x), _as_rows(x)[2], L.ptr(w), L.ptr(bias), L.ptr(dout), L.ptr(dout2), L.ptr(dout3),
+                                       _as_rows(dout)[2],
                                        L.ptr(dx), _as_rows(dx)[2], L.ptr(dw), L.ptr(dbias), B, Lq, D, w.shape[1],
                                        L.dt(x.dtype), int(silu), int(reverse), L.stream())
     L.check(rc, "aum_causal_conv1d_bwd")
+
+
+def sum_cast_colsum(a: torch.Tensor, b: Optional[torch.Tensor], out_dtype: torch.dtype,
+                    colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
+    """out = (a + b).to(out_dtype) and colsum += (a + b).sum(0) in one pass (aum_sum_cast_colsum).  a, b: fp32 (rows, cols)."""
+    L.require_cuda(a, b, colsum)
+    rows, cols, ld = _as_rows(a)
+    if a.dtype != torch.float32 or (b is not None and (b.dtype != torch.float32 or _as_rows(b) != (rows, cols, ld))):
+        raise L.AumError("sum_cast_colsum: a and b must be fp32 with one shape and pitch")
+    if colsum is not None and (colsum.dtype != torch.float32 or colsum.numel() != cols or not colsum.is_contiguous()):
+        raise L.AumError("sum_cast_colsum: colsum must be a contiguous fp32 vector of `cols` elements")
+    if cols % 4 != 0 or ld % 4 != 0 or a.data_ptr() % 16 != 0 or (b is not None and b.data_ptr() % 16 != 0):
+        raise L.AumError("sum_cast_colsum: rows must be addressable as 4-element vectors (cols % 4 == 0, 16-byte aligned)")
+    out = torch.empty((rows, cols), device=a.device, dtype=out_dtype)
+    rc = L.lib().aum_sum_cast_colsum(L.ptr(a), L.ptr(b), ld, L.ptr(out), cols, L.dt(out_dtype), L.ptr(colsum), rows, cols, L.stream())
+    L.check(rc, "aum_sum_cast_colsum")
+    return out
 
 
 class ScanBwdDirection:

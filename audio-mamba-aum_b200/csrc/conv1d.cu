@@ -283,7 +283,7 @@ constexpr int CB_TL = 8;
 template <typename T>
 __global__ void __launch_bounds__(256, 3)
 conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ bias,
-                  const float* __restrict__ dout, const float* __restrict__ dout2, int64_t ldd,
+                  const float* __restrict__ dout, const float* __restrict__ dout2, const float* __restrict__ dout3, int64_t ldd,
                   T* __restrict__ dx, int64_t ld_dx, float* __restrict__ dw, float* __restrict__ dbias,
                   int batch, int L, int D, int W, int silu, int reverse, int n_cgrp, int n_tgrp) {
   __shared__ float red[8][10][32];
@@ -296,7 +296,8 @@ conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
   const bool pair_ok = ok1 && (ldx % 2 == 0) && (ldd % 2 == 0) && (ld_dx % 2 == 0) &&
                        (reinterpret_cast<uintptr_t>(x) % (2 * sizeof(T)) == 0) &&
                        (reinterpret_cast<uintptr_t>(dx) % (2 * sizeof(T)) == 0) &&
-                       (reinterpret_cast<uintptr_t>(dout) % 8 == 0) && (reinterpret_cast<uintptr_t>(dout2) % 8 == 0);
+                       (reinterpret_cast<uintptr_t>(dout) % 8 == 0) && (reinterpret_cast<uintptr_t>(dout2) % 8 == 0) &&
+                       (reinterpret_cast<uintptr_t>(dout3) % 8 == 0);
   const int p0 = (tg * 8 + wrp) * CB_TL;           // first walk position of this warp's tile
 
   float wk[CONV_MAXW][2], bs[2];
@@ -344,6 +345,11 @@ conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
           const float* g2 = dout2 + (base + tok(p)) * ldd + c0;
           if (pair_ok) { const float2 t = *reinterpret_cast<const float2*>(g2); gr[j].x += t.x; gr[j].y += t.y; }
           else { gr[j].x += g2[0]; if (ok1) gr[j].y += g2[1]; }
+        }
+        if (dout3 != nullptr) {          // third term (the other scan direction's du when the two are kept apart)
+          const float* g3 = dout3 + (base + tok(p)) * ldd + c0;
+          if (pair_ok) { const float2 t = *reinterpret_cast<const float2*>(g3); gr[j].x += t.x; gr[j].y += t.y; }
+          else { gr[j].x += g3[0]; if (ok1) gr[j].y += g3[1]; }
         }
       }
     }
@@ -410,7 +416,7 @@ conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
 }  // namespace aum
 
 extern "C" int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w, const float* bias,
-                                     const float* dout, const float* dout2, int64_t ldd, void* dx, int64_t ld_dx,
+                                     const float* dout, const float* dout2, const float* dout3, int64_t ldd, void* dx, int64_t ld_dx,
                                      float* dw, float* dbias, int batch, int L, int D, int W,
                                      int dtype, int silu, int reverse, void* stream) {
   using namespace aum;
@@ -425,9 +431,9 @@ extern "C" int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w,
   AUM_REQUIRE(blocks < (1ll << 31), "aum_causal_conv1d_bwd: grid too large");
   cudaStream_t st = (cudaStream_t)stream;
   switch (dtype) {
-    case AUM_F32:  conv1d_bwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, ldx, w, bias, dout, dout2, ldd, (float*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
-    case AUM_F16:  conv1d_bwd_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, ldx, w, bias, dout, dout2, ldd, (__half*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
-    case AUM_BF16: conv1d_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, w, bias, dout, dout2, ldd, (__nv_bfloat16*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
+    case AUM_F32:  conv1d_bwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, ldx, w, bias, dout, dout2, dout3, ldd, (float*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
+    case AUM_F16:  conv1d_bwd_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, ldx, w, bias, dout, dout2, dout3, ldd, (__half*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
+    case AUM_BF16: conv1d_bwd_kernel<__nv_bfloat16><<<(unsigned)blocks, 256, 0, st>>>((const __nv_bfloat16*)x, ldx, w, bias, dout, dout2, dout3, ldd, (__nv_bfloat16*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
     default: set_error("aum_causal_conv1d_bwd: bad dtype %d", dtype); return 1;
   }
   return check_launch("aum_causal_conv1d_bwd");

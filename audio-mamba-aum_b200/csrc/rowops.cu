@@ -1,0 +1,68 @@
+// Row-wise helper of the training path:  out[r, c] = cast(a[r, c] + b[r, c]),  colsum[c] += sum_r (a + b)[r, c].
+// One pass instead of the three torch launches it replaces in BiMambaInnerFn.backward's dt_proj chain
+// (/root/reference/vim-mamba_ssm/mamba_ssm/ops/selective_scan_interface.py:566-586: ddelta of the two directions summed
+// (:556), delta_proj bias gradient = its sum over tokens, and the 16-bit operand of the d(dt_proj.weight) / d(x_dbl)
+// products).  HBM-bound: reads 4 (+4) bytes, writes s bytes per element.
+#include "common.cuh"
+
+namespace aum {
+
+constexpr int RO_ROWS = 64;      // rows per block
+constexpr int RO_THREADS = 256;  // 4 columns per thread -> 1024 columns per block
+
+template <typename T>
+__global__ void __launch_bounds__(RO_THREADS)
+sum_cast_colsum_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t ld, T* __restrict__ out, int64_t ldo,
+                       float* __restrict__ colsum, int rows, int cols) {
+  const int c0 = (blockIdx.x * RO_THREADS + threadIdx.x) * 4;
+  if (c0 >= cols) return;
+  const int r0 = blockIdx.y * RO_ROWS, r1 = min(rows, r0 + RO_ROWS);
+  float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
+#pragma unroll 4
+  for (int r = r0; r < r1; ++r) {
+    float4 v = __ldg(reinterpret_cast<const float4*>(a + (int64_t)r * ld + c0));
+    if (b != nullptr) {
+      const float4 w = __ldg(reinterpret_cast<const float4*>(b + (int64_t)r * ld + c0));
+      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+    }
+    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+    T* o = out + (int64_t)r * ldo + c0;
+    if constexpr (sizeof(T) == 4) {
+      *reinterpret_cast<float4*>(o) = v;
+    } else {
+      const T t0 = from_f<T>(v.x), t1 = from_f<T>(v.y), t2 = from_f<T>(v.z), t3 = from_f<T>(v.w);
+      uint2 pk;
+      pk.x = (uint32_t)(*reinterpret_cast<const unsigned short*>(&t0)) | ((uint32_t)(*reinterpret_cast<const unsigned short*>(&t1)) << 16);
+      pk.y = (uint32_t)(*reinterpret_cast<const unsigned short*>(&t2)) | ((uint32_t)(*reinterpret_cast<const unsigned short*>(&t3)) << 16);
+      *reinterpret_cast<uint2*>(o) = pk;
+    }
+  }
+  if (colsum != nullptr) {
+    atomicAdd(colsum + c0, s.x); atomicAdd(colsum + c0 + 1, s.y); atomicAdd(colsum + c0 + 2, s.z); atomicAdd(colsum + c0 + 3, s.w);
+  }
+}
+
+}  // namespace aum
+
+extern "C" int aum_sum_cast_colsum(const float* a, const float* b, int64_t ld, void* out, int64_t ld_out, int out_dtype,
+                                   float* colsum, int rows, int cols, void* stream) {
+  using namespace aum;
+  DeviceGuard device_guard(out);
+  if (rows == 0 || cols == 0) return 0;
+  AUM_REQUIRE(a && out, "aum_sum_cast_colsum: null pointer");
+  AUM_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, "aum_sum_cast_colsum: cols must be a positive multiple of 4");
+  AUM_REQUIRE(out_dtype >= AUM_F32 && out_dtype <= AUM_BF16, "aum_sum_cast_colsum: bad dtype %d", out_dtype);
+  AUM_REQUIRE(ld >= cols && ld_out >= cols, "aum_sum_cast_colsum: leading dimension smaller than the row length");
+  const int osz = dtype_size(out_dtype);
+  AUM_REQUIRE(aligned16(a) && (b == nullptr || aligned16(b)) && (ld * 4) % 16 == 0 &&
+              (reinterpret_cast<uintptr_t>(out) % (4 * osz) == 0) && (ld_out * osz) % (4 * osz) == 0,
+              "aum_sum_cast_colsum: rows must be addressable in 4-element vectors");
+  dim3 grid(ceil_div(cols, RO_THREADS * 4), ceil_div(rows, RO_ROWS));
+  cudaStream_t st = (cudaStream_t)stream;
+  switch (out_dtype) {
+    case AUM_F32:  sum_cast_colsum_kernel<float><<<grid, RO_THREADS, 0, st>>>(a, b, ld, (float*)out, ld_out, colsum, rows, cols); break;
+    case AUM_F16:  sum_cast_colsum_kernel<__half><<<grid, RO_THREADS, 0, st>>>(a, b, ld, (__half*)out, ld_out, colsum, rows, cols); break;
+    default:       sum_cast_colsum_kernel<__nv_bfloat16><<<grid, RO_THREADS, 0, st>>>(a, b, ld, (__nv_bfloat16*)out, ld_out, colsum, rows, cols); break;
+  }
+  return check_launch("aum_sum_cast_colsum");
+}

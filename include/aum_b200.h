@@ -117,13 +117,20 @@ AUM_API int aum_conv_xproj_fwd(const void* x, int64_t ldx, const float* conv_w, 
                        int batch, int L, int Di, int R, int N2, int dtype, int reverse, void* stream);
 
 /* Backward of the above.  replaces causal_conv1d_cuda.causal_conv1d_bwd(x, w, bias, dout, None, dx, silu)
- *   (selective_scan_interface.py:281-283, 425-427, 594-596).  dout (+ optional dout2, same pitch; the two are
- *   summed on the fly — the scan's du and the x_proj term of :590): fp32 gradient w.r.t. the conv output (after the
- *   activation); dx: written (dtype); dw (D, W) and dbias (D) are ACCUMULATED (+=): zero them first. */
+ *   (selective_scan_interface.py:281-283, 425-427, 594-596).  dout (+ optional dout2, dout3, same pitch; summed on the
+ *   fly — the scan's du of either direction (:556) and the x_proj term of :590): fp32 gradient w.r.t. the conv output
+ *   (after the activation); dx: written (dtype); dw (D, W) and dbias (D) are ACCUMULATED (+=): zero them first. */
 AUM_API int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w, const float* bias,
-                          const float* dout, const float* dout2, int64_t ldd, void* dx, int64_t ld_dx,
+                          const float* dout, const float* dout2, const float* dout3, int64_t ldd, void* dx, int64_t ld_dx,
                           float* dw, float* dbias, int batch, int L, int D, int W,
                           int dtype, int silu, int reverse, void* stream);
+
+/* out[r, c] = (out_dtype)(a[r, c] + b[r, c]),  colsum[c] += sum_r (a + b)[r, c]   (b and colsum optional).
+ *   One pass for the dt_proj chain of the three backward functions (selective_scan_interface.py:556 ddelta of the two
+ *   directions summed, :583-586 delta_proj bias gradient = sum over tokens, and the 16-bit operand of the
+ *   d(dt_proj.weight) / d(x_dbl) products).  a, b: fp32 (rows, cols) with pitch ld; cols % 4 == 0. */
+AUM_API int aum_sum_cast_colsum(const float* a, const float* b, int64_t ld, void* out, int64_t ld_out, int out_dtype,
+                        float* colsum, int rows, int cols, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Selective scan, one or both time directions in ONE launch.

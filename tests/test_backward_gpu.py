@@ -399,3 +399,32 @@ def test_direct_gradient_accumulation_into_a_flat_buffer():
         assert pb.grad.data_ptr() >= red.flat.data_ptr() and pb.grad.data_ptr() < red.flat.data_ptr() + red.flat.numel() * 4, n
         scale = max(pa.grad.abs().max().item(), 1e-9)
         assert (pa.grad - pb.grad).abs().max().item() <= 2e-2 * scale, (n, scale)
+
+
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
+def test_sum_cast_colsum(dt):
+    """aum_sum_cast_colsum: (a + b) cast to the activation dtype and its column sums in one pass (dt_proj chain of the
+    backward, selective_scan_interface.py:556,583-586); a third gradient term of the conv backward."""
+    from aum_b200 import ops
+    g = gen(31)
+    for rows, cols in [(513, 1536), (70, 128), (1, 4), (130, 768)]:
+        a, b = rnd((rows, cols), g), rnd((rows, cols), g)
+        cs = torch.full((cols,), 2.0, device=DEV)
+        out = ops.sum_cast_colsum(a.to(DEV), b.to(DEV), dt, cs)
+        torch.testing.assert_close(out.cpu(), (a + b).to(dt), rtol=0, atol=0)
+        torch.testing.assert_close(cs.cpu(), 2.0 + (a + b).sum(0), rtol=1e-5, atol=1e-4)
+        out1 = ops.sum_cast_colsum(a.to(DEV), None, dt)
+        torch.testing.assert_close(out1.cpu(), a.to(dt), rtol=0, atol=0)
+    # conv backward with three gradient terms == with their sum
+    B, Lq, D = 2, 37, 64
+    x, w, bias = rnd((B, Lq, D), g), rnd((D, 4), g, 0.5), rnd((D,), g, 0.5)
+    g1, g2, g3 = rnd((B, Lq, D), g), rnd((B, Lq, D), g), rnd((B, Lq, D), g)
+    res = []
+    for terms in ((g1 + g2 + g3, None, None), (g1, g2, g3)):
+        dx = torch.empty((B, Lq, D), device=DEV); dw = torch.zeros((D, 4), device=DEV); db = torch.zeros((D,), device=DEV)
+        ops.causal_conv1d_bwd(x.to(DEV), w.to(DEV), bias.to(DEV), terms[0].to(DEV), dx, dw, db,
+                              dout2=terms[1].to(DEV) if terms[1] is not None else None,
+                              dout3=terms[2].to(DEV) if terms[2] is not None else None)
+        res.append((dx.cpu(), dw.cpu(), db.cpu()))
+    for p_, q_ in zip(res[0], res[1]):
+        torch.testing.assert_close(p_, q_, rtol=1e-5, atol=1e-5)
