@@ -27,12 +27,11 @@ from . import ops
 
 
 _PREGATE_Z = os.environ.get("AUM_PREGATE_Z", "1") == "1"
-# conv + SiLU fused into x_proj's operand producer (aum_conv_xproj_fwd, csrc/conv_xproj.cu): parity-green, but measured
-# SLOWER than the two kernels it replaces (0.153 vs 0.053 + 0.035 ms at config 2: its 8 conv warps per SM run ~480
-# instructions per channel block at 1 IPC/SM - shared-memory and MUFU latency with two warps per scheduler, ncu
-# profiles/r2_ncu_conv_xproj_v2_summary.txt - where the stand-alone conv hides the same latencies with full occupancy).
-# Off by default; AUM_FUSE_CONV_XPROJ=1 selects it.
-_FUSE_CONV_XPROJ = os.environ.get("AUM_FUSE_CONV_XPROJ", "0") == "1"
+# conv + SiLU fused into x_proj's operand producer (aum_conv_xproj_fwd, csrc/conv_xproj.cu): one launch and one pass over
+# x instead of conv (write u) + x_proj (re-read u).  Measured at config 2: 0.082 ms per 64 sequences / 0.045 ms per 32
+# against 0.053 + 0.035 / 0.031 + 0.025 ms for the two kernels it replaces (the first builds - 8 conv warps, CTA-wide
+# barriers - were slower than the pair: profiles/r2_ncu_conv_xproj_v2_summary.txt).  AUM_FUSE_CONV_XPROJ=0 disables it.
+_FUSE_CONV_XPROJ = os.environ.get("AUM_FUSE_CONV_XPROJ", "1") == "1"
 
 
 def _round_up(x: int, m: int) -> int:

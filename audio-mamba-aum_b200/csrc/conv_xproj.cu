@@ -10,13 +10,15 @@
 // One persistent CTA per SM walks 128-token tiles; per tile it loops over the Di channels in blocks of 64:
 //   warp 0      TMA producer: the raw x rows of the block (128 tokens + 3 halo rows x 64 channels, un-swizzled) and the
 //               x_proj weight block W_x[:, 64 channels] (K-major, 128-byte swizzle) into a 4-stage ring.
-//   warps 2..9  conv: each thread takes 8 channels x 4 tokens: 7 LDS.128 of raw rows, 4 taps as fp32 FMAs, bias, SiLU
+//   warps 2..17 conv: each thread takes 4 channels x 4 tokens: 7 LDS.64 of raw rows, 4 taps as packed fp32 FMAs, bias, SiLU
 //               (ftz MUFU), and writes the 16-bit results into the stage's A tile in the 128-byte-swizzled K-major layout
 //               the tensor core reads.  One elected thread then (a) publishes the tile to the MMA warp and (b) sends the
 //               SAME tile to HBM as u with one bulk tensor store.
 //   warp 1      tcgen05.mma 128 x NB x 16 (NB = 96 for AuM-Base's 80 outputs), accumulating over all channel blocks in
 //               TMEM; tcgen05.commit frees the stage.
 //   epilogue    (conv warps 2..5, lane = token row): TMEM -> registers -> dt (16-bit, first R columns) | [B|C] (fp32).
+// 16 conv warps (4 per scheduler) at <= 113 registers: with 8 warps of 8-channel threads (166 registers) the conv ran at
+// 1 IPC per SM, its shared-memory and MUFU latencies exposed (profiles/r2_ncu_conv_xproj_v2_summary.txt).
 // Sequence boundaries: the halo rows of a token near the start (causal) or end (anti-causal, Bi-Bi's second branch) of
 // its sequence belong to the neighbouring sequence or lie outside the tensor: those taps are masked.
 #include <cuda.h>
@@ -41,7 +43,7 @@ constexpr int CX_STAGES = 6;                // load ring (raw x rows + W_x block
                                            // kernel is latency-bound below ~5 blocks of prefetch (ncu v1/v2: one DRAM round trip per
                                            // channel block at 4 stages that also held the A tiles)
 constexpr int CX_ASTAGES = 2;              // A tiles (conv output = MMA operand = source of the u store)
-constexpr int CX_CONV_WARPS = 8;
+constexpr int CX_CONV_WARPS = 16;          // 4 per scheduler: the conv is latency-bound below that (ncu v1-v3 at 8 warps: 1 IPC/SM)
 constexpr int CX_THREADS = 64 + 32 * CX_CONV_WARPS;
 constexpr int CX_BAR_ID = 3;               // named barrier of the conv warps
 
@@ -64,7 +66,6 @@ struct CxParams {
   int reverse;
 };
 
-__device__ __forceinline__ void conv_bar() { asm volatile("bar.sync %0, %1;" ::"n"(CX_BAR_ID), "n"(32 * CX_CONV_WARPS) : "memory"); }
 __device__ __forceinline__ uint4 lds_u4(uint32_t a) {
   uint4 v; asm volatile("ld.shared.v4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a)); return v;
 }
@@ -94,7 +95,8 @@ conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
   auto st_free = [&](int s) { return bar_base + 8u * (STAGES + s); };             // MMA: load stage consumed
   auto a_full = [&](int s) { return bar_base + 8u * (2 * STAGES + s); };          // conv: A tile written
   auto a_done = [&](int s) { return bar_base + 8u * (2 * STAGES + CX_ASTAGES + s); };   // MMA: A tile consumed
-  const uint32_t tfull = bar_base + 8u * (2 * STAGES + 2 * CX_ASTAGES);
+  auto a_free = [&](int s) { return bar_base + 8u * (2 * STAGES + 2 * CX_ASTAGES + s); };   // u store has read the A tile
+  const uint32_t tfull = bar_base + 8u * (2 * STAGES + 3 * CX_ASTAGES);
   const uint32_t tempty = tfull + 8u;
   const uint32_t tmem_slot = tfull + 16u;
   auto s_raw = [&](int s) { return smem_base + s * Cfg::STAGE_BYTES; };
@@ -108,7 +110,7 @@ conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
 
   if (warp == 0 && lane == 0) {
     for (int s = 0; s < STAGES; ++s) { mbar_init(raw_full(s), 1); mbar_init(st_free(s), 1); }
-    for (int s = 0; s < CX_ASTAGES; ++s) { mbar_init(a_full(s), 1); mbar_init(a_done(s), 1); }
+    for (int s = 0; s < CX_ASTAGES; ++s) { mbar_init(a_full(s), CX_CONV_WARPS); mbar_init(a_done(s), 1); mbar_init(a_free(s), 1); }
     mbar_init(tfull, 1); mbar_init(tempty, 128);
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
@@ -147,9 +149,13 @@ conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
     }
   } else if (warp == 1) {
-    // ================= MMA issuer =================
+    // ================= MMA issuer + u store =================
+    // (whole warp converged; the elected lane - the same one every time - issues the MMAs of a block and then sends the
+    //  block's A tile to HBM as u: both read the tile through the async proxy once all 16 conv warps have published it)
     int stage = 0, as = 0; uint32_t aphase = 0, tphase = 0;
+    int nblk = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
+      const int m0 = tile * CX_BM;
       mbar_wait(tempty, tphase ^ 1u);                 // epilogue of the previous tile has drained the accumulator
       tc_fence_after();
       for (int kb = 0; kb < k_blocks; ++kb) {
@@ -164,27 +170,33 @@ conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           tc_commit(st_free(stage));
           tc_commit(a_done(as));
           if (kb == k_blocks - 1) tc_commit(tfull);
+          tma_store_2d(&tmU, s_a(as), kb * CX_BK, m0);          // u[m0 .. m0+127, 64 channels] (clipped at M / Di)
+          tma_store_commit();
+          tma_store_wait_read<1>();                             // the PREVIOUS block's store has left its A buffer
+          if (nblk >= 1) mbar_arrive(a_free(as ^ 1));
         }
         __syncwarp();
+        ++nblk;
         if (++stage == STAGES) stage = 0;
         if (++as == CX_ASTAGES) { as = 0; aphase ^= 1u; }
       }
       tphase ^= 1u;
     }
+    if (elect_one()) tma_store_wait_read<0>();        // shared memory must outlive the last bulk store
+    __syncwarp();
   } else {
-    // ================= conv warps (2..9) + epilogue (2..5) =================
-    const int ct = threadIdx.x - 64;                  // 0..255
-    const int cg = ct & 7;                            // 8-channel group inside the 64-channel block (16 B)
-    const int tr = ct >> 3;                           // 0..31: tokens 4 tr .. 4 tr + 3 of the tile
-    const bool leader = ct == 0;
+    // ================= conv warps (2..17) + epilogue (2..5) =================
+    // thread = 4 channels (8 bytes of a row) x 4 tokens: 512 threads cover the 64-channel x 128-token block
+    const int ct = threadIdx.x - 64;                  // 0..511
+    const int cq = ct & 15;                           // 4-channel group inside the 64-channel block
+    const int tr = ct >> 4;                           // 0..31: tokens 4 tr .. 4 tr + 3 of the tile
     int stage = 0, as = 0; uint32_t phase = 0, aphase = 0, tphase = 0;
-    int pending_stores = 0;
     for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
       const int m0 = tile * CX_BM;
       // position of this thread's first token in its sequence, and the per-token edge masks (bit j of mask[i]: tap row
       // j of token i is valid).  Causal: tap row j of a token at position l holds x[l - 3 + j]; anti-causal: x[l + j].
       int l0 = (m0 + 4 * tr) % p.L;
-      uint32_t mask[4];
+      uint32_t mask4 = 0;                             // 4 bits per token
       bool edge = false;
 #pragma unroll
       for (int i = 0; i < 4; ++i) {
@@ -195,62 +207,60 @@ conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
           const bool ok = REV ? (l + j < p.L) : (l - CX_HALO + j >= 0);
           mk |= ok ? (1u << j) : 0u;
         }
-        mask[i] = mk; edge |= (mk != 0xfu);
+        mask4 |= mk << (4 * i); edge |= (mk != 0xfu);
       }
       for (int kb = 0; kb < k_blocks; ++kb) {
         mbar_wait(raw_full(stage), phase);
-        // taps and biases of this thread's 8 channels, from the stage's weight slab, as channel pairs:
+        // taps and biases of this thread's 4 channels, from the stage's weight slab, as channel pairs:
         // wp[k][c2] = (w_k[2 c2], w_k[2 c2 + 1])
-        f32x2 wp[4][4], bp[4];
+        f32x2 wp[4][2], bp[2];
         {
-          const bool okc = kb * CX_BK + cg * 8 < p.Di;                 // (channel tail: Di % 8 == 0, so all 8 or none)
-          const uint32_t wbase = s_cw(stage) + (uint32_t)cg * 128u;
+          const bool okc = kb * CX_BK + cq * 4 < p.Di;                 // (channel tail: Di % 8 == 0, so all 4 or none)
+          const uint32_t wbase = s_cw(stage) + (uint32_t)cq * 64u;
 #pragma unroll
-          for (int c2 = 0; c2 < 4; ++c2) {
+          for (int c2 = 0; c2 < 2; ++c2) {
             float4 wa = make_float4(0.f, 0.f, 0.f, 0.f), wb = wa;
             if (okc) { wa = lds_f4x(wbase + (uint32_t)(2 * c2) * 16u); wb = lds_f4x(wbase + (uint32_t)(2 * c2 + 1) * 16u); }
             wp[0][c2] = pk2(wa.x, wb.x); wp[1][c2] = pk2(wa.y, wb.y); wp[2][c2] = pk2(wa.z, wb.z); wp[3][c2] = pk2(wa.w, wb.w);
           }
-          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f), b1 = b0;
-          if (okc && p.cb != nullptr) {
-            b0 = lds_f4x(s_cw(stage) + CX_CW_BIAS_OFF + (uint32_t)cg * 32u);
-            b1 = lds_f4x(s_cw(stage) + CX_CW_BIAS_OFF + (uint32_t)cg * 32u + 16u);
-          }
-          bp[0] = pk2(b0.x, b0.y); bp[1] = pk2(b0.z, b0.w); bp[2] = pk2(b1.x, b1.y); bp[3] = pk2(b1.z, b1.w);
+          float4 b0 = make_float4(0.f, 0.f, 0.f, 0.f);
+          if (okc && p.cb != nullptr) b0 = lds_f4x(s_cw(stage) + CX_CW_BIAS_OFF + (uint32_t)cq * 16u);
+          bp[0] = pk2(b0.x, b0.y); bp[1] = pk2(b0.z, b0.w);
         }
-        // raw rows 4 tr .. 4 tr + 6 of the block, this thread's 16-byte channel group, each converted once to 4 fp32 pairs
-        const uint32_t rbase = s_raw(stage) + (uint32_t)(4 * tr) * 128u + (uint32_t)cg * 16u;
-        f32x2 xr[7][4];
+        // raw rows 4 tr .. 4 tr + 6 of the block, this thread's 8-byte channel group, each converted once to 2 fp32 pairs
+        const uint32_t rbase = s_raw(stage) + (uint32_t)(4 * tr) * 128u + (uint32_t)cq * 8u;
+        f32x2 xr[7][2];
 #pragma unroll
         for (int r = 0; r < 7; ++r) {
-          const uint4 q = lds_u4(rbase + (uint32_t)r * 128u);
-          const float2 f0 = unpack2<T>(q.x), f1 = unpack2<T>(q.y), f2 = unpack2<T>(q.z), f3 = unpack2<T>(q.w);
-          xr[r][0] = pk2(f0.x, f0.y); xr[r][1] = pk2(f1.x, f1.y); xr[r][2] = pk2(f2.x, f2.y); xr[r][3] = pk2(f3.x, f3.y);
+          uint32_t q0, q1;
+          asm volatile("ld.shared.v2.b32 {%0, %1}, [%2];" : "=r"(q0), "=r"(q1) : "r"(rbase + (uint32_t)r * 128u));
+          const float2 f0 = unpack2<T>(q0), f1 = unpack2<T>(q1);
+          xr[r][0] = pk2(f0.x, f0.y); xr[r][1] = pk2(f1.x, f1.y);
         }
-        uint32_t outp[4][4];
+        uint32_t outp[4][2];
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
-          f32x2 acc[4];
+          f32x2 acc[2];
 #pragma unroll
-          for (int c2 = 0; c2 < 4; ++c2) acc[c2] = bp[c2];
+          for (int c2 = 0; c2 < 2; ++c2) acc[c2] = bp[c2];
           // tap row j of token i is raw row i + j; it multiplies tap k = j (causal) or k = 3 - j (anti-causal)
           if (!edge) {
 #pragma unroll
             for (int j = 0; j < 4; ++j)
 #pragma unroll
-              for (int c2 = 0; c2 < 4; ++c2) acc[c2] = fma2(wp[REV ? 3 - j : j][c2], xr[i + j][c2], acc[c2]);
+              for (int c2 = 0; c2 < 2; ++c2) acc[c2] = fma2(wp[REV ? 3 - j : j][c2], xr[i + j][c2], acc[c2]);
           } else {
 #pragma unroll
             for (int j = 0; j < 4; ++j) {
-              const float mj = ((mask[i] >> j) & 1u) ? 1.f : 0.f;
+              const float mj = ((mask4 >> (4 * i + j)) & 1u) ? 1.f : 0.f;
               const f32x2 m2 = pk2(mj, mj);
 #pragma unroll
-              for (int c2 = 0; c2 < 4; ++c2) acc[c2] = fma2(mul2(wp[REV ? 3 - j : j][c2], m2), xr[i + j][c2], acc[c2]);
+              for (int c2 = 0; c2 < 2; ++c2) acc[c2] = fma2(mul2(wp[REV ? 3 - j : j][c2], m2), xr[i + j][c2], acc[c2]);
             }
           }
           // SiLU on pairs: x * rcp(1 + ex2(-x log2 e)), flush-to-zero MUFU forms
 #pragma unroll
-          for (int c2 = 0; c2 < 4; ++c2) {
+          for (int c2 = 0; c2 < 2; ++c2) {
             float t0, t1, a0, a1;
             upk2(mul2(acc[c2], pk2(-1.4426950408889634f, -1.4426950408889634f)), t0, t1);
             upk2(acc[c2], a0, a1);
@@ -260,24 +270,21 @@ conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
             outp[i][c2] = pack2<T>(a0 * r0, a1 * r1);
           }
         }
-        // the bulk store that read this A buffer CX_STAGES blocks ago must have drained before it is overwritten
-        if (leader && pending_stores >= CX_ASTAGES) { tma_store_wait_read<CX_ASTAGES - 1>(); }
-        mbar_wait(a_done(as), aphase ^ 1u);           // the MMAs that read this A buffer two blocks ago have retired
-        conv_bar();
+        // the A buffer is free once the MMAs (a_done) and the u store (a_free) that read it two blocks ago are done.
+        // No CTA-wide barrier anywhere in this loop: every warp publishes its own rows, so the 16 warps drift apart and
+        // one warp's LDS / FMA phase overlaps another's MUFU / store phase.
+        mbar_wait(a_done(as), aphase ^ 1u);
+        mbar_wait(a_free(as), aphase ^ 1u);
         // A tile: row = token (128 B = 64 channels), 16-byte chunk index XOR (row & 7)  (128-byte swizzle)
 #pragma unroll
         for (int i = 0; i < 4; ++i) {
           const uint32_t row = (uint32_t)(4 * tr + i);
-          st_shared_v4(s_a(as) + row * 128u + ((((uint32_t)cg) ^ (row & 7u)) << 4), outp[i][0], outp[i][1], outp[i][2], outp[i][3]);
+          const uint32_t addr = s_a(as) + row * 128u + ((((uint32_t)(cq >> 1)) ^ (row & 7u)) << 4) + (((uint32_t)cq & 1u) << 3);
+          asm volatile("st.shared.v2.b32 [%0], {%1, %2};" ::"r"(addr), "r"(outp[i][0]), "r"(outp[i][1]) : "memory");
         }
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");
-        conv_bar();
-        if (leader) {
-          mbar_arrive(a_full(as));                                      // -> MMA warp
-          tma_store_2d(&tmU, s_a(as), kb * CX_BK, m0);                  // u[m0 .. m0+127, 64 channels] (clipped at M / Di)
-          tma_store_commit();
-          ++pending_stores;
-        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(a_full(as));                         // -> MMA warp (16 arrivals complete the phase)
         if (++stage == STAGES) { stage = 0; phase ^= 1u; }
         if (++as == CX_ASTAGES) { as = 0; aphase ^= 1u; }
       }
@@ -312,7 +319,6 @@ conv_xproj_kernel(const __grid_constant__ CUtensorMap tmX, const __grid_constant
       }
       tphase ^= 1u;
     }
-    if (leader) tma_store_wait_read<0>();             // shared memory must outlive the last bulk stores
   }
 
   tc_fence_before();
