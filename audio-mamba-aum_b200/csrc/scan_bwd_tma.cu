@@ -18,6 +18,7 @@
 // Eligibility (launch_scan_bwd_tma): d_state == 16, forward checkpoints present, packed fp32 [B|C] rows,
 // 16-byte aligned bases and row pitches.  Anything else runs scan_bwd.cu.
 #include <cuda.h>
+#include <stdlib.h>
 
 #include "scan_bwd_common.cuh"
 #include "tma.cuh"
@@ -133,11 +134,24 @@ __device__ __forceinline__ void smem_column_sums(uint32_t tile, int lane, float&
   hi += __shfl_xor_sync(0xffffffffu, hi, 16);
 }
 
-template <typename T>
-__global__ void __launch_bounds__(BT_CH, 3)
-scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParams p) {
+// sigmoid(x) with flush-to-zero MUFU ops (exp2 overflow -> rcp(inf) = 0)
+__device__ __forceinline__ float sigmoid_ftz(float x) {
+  float r;
+  const float e = ex2_approx(-1.4426950408889634f * x);
+  asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(r) : "f"(1.f + e));
+  return r;
+}
+
+// The walk of one CTA.  SPEC = the training configuration of the AuM mixers with every per-launch option folded into the
+// instruction stream: direction 0 walks forwards and owns the gate (z, y_pre, dz and out_z all present), direction 1 walks
+// backwards and has none; du / ddelta are plain stores (one pair per direction), ddelta leaves multiplied by softplus',
+// every channel of the CTA exists (D % 128 == 0).  The general instantiation (SPEC = false) reads the same options from
+// the parameter block at run time; in the 2-step unrolled reverse-time loop that is ~90 of ~340 instructions per step
+// (uniform branches, predicate set-up, 64-bit pointer selects) and, worse for a latency-bound kernel, it cuts the step
+// into basic blocks the scheduler cannot interleave across.
+template <typename T, bool SPEC, bool REV_, bool GATE_>
+__device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const ScanBwdParams& p, uint8_t* smem_raw) {
   using BL = BwdLayout<T>;
-  extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (s_u32(smem_raw) + 127u) & ~127u;
   const uint32_t stages = smem0;
   const uint32_t redt = stages + 2 * BL::STAGE_BYTES;
@@ -148,17 +162,17 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
   const ScanBwdDirDev& d = p.dir[g];
   const int tig = threadIdx.x, lane = tig & 31;
   const int ch_raw = blockIdx.x * BT_CH + tig;
-  const bool active = ch_raw < p.Dch;
+  const bool active = SPEC ? true : (ch_raw < p.Dch);
   const int ch = active ? ch_raw : (p.Dch - 1);
   const int b = blockIdx.y;
   const int L = p.L;
-  const bool rev = d.reverse != 0;
+  const bool rev = SPEC ? REV_ : (d.reverse != 0);
   const int row0 = b * L;
   const bool bidir = p.ndirs == 2;
-  const bool accumulate = bidir && p.shared_du;
-  const bool has_z = p.z != nullptr;
-  const bool gate = (g == 0) && has_z && (p.dz != nullptr || p.outz != nullptr);
-  const bool want_y = gate && p.ypre != nullptr;
+  const bool accumulate = SPEC ? false : (bidir && p.shared_du);
+  const bool has_z = SPEC ? true : (p.z != nullptr);
+  const bool gate = SPEC ? GATE_ : ((g == 0) && has_z && (p.dz != nullptr || p.outz != nullptr));
+  const bool want_y = SPEC ? GATE_ : (gate && p.ypre != nullptr);
   const float scale = p.scale;
   const int64_t rows_total = (int64_t)p.batch * L;
 
@@ -214,14 +228,14 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
     if (nchunks > 1) issue(nchunks - 2);
   }
 
-  // ---- per-channel constants and accumulators
-  f32x2 a2[SCAN_NS / 2], Av2[SCAN_NS / 2];
+  // ---- per-channel constants and accumulators.  a2 = A log2(e) serves both the decay exp2(dl a2) and - with one
+  // multiplication by ln 2 at the end of the step - the A factor of d(delta) (no second copy of A in registers).
+  f32x2 a2[SCAN_NS / 2];
   {
     const float4* ap = reinterpret_cast<const float4*>(d.A + (int64_t)ch * SCAN_NS);
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
       const float4 v = __ldg(ap + i);
-      Av2[2 * i] = pk2(v.x, v.y); Av2[2 * i + 1] = pk2(v.z, v.w);
       a2[2 * i] = pk2(v.x * 1.4426950408889634f, v.y * 1.4426950408889634f);
       a2[2 * i + 1] = pk2(v.z * 1.4426950408889634f, v.w * 1.4426950408889634f);
     }
@@ -239,7 +253,13 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
   const int rstep = rev ? -1 : 1;
   const int part = blockIdx.x * (BT_CH / 32) + (tig >> 5);     // this warp's slice of the dB|dC partial workspace
   const uint32_t hcol = tmem_base + ((uint32_t)((tig >> 5) * 32) << 16);   // slot 0 of this warp's TMEM lane quarter
-  const bool spg_on = p.softplus_grad != 0;
+  const bool spg_on = SPEC ? true : (p.softplus_grad != 0);
+  const uint32_t red_tile = redt + (uint32_t)((tig >> 5) * 32 * BL::RED_PITCH * 4);
+  const uint32_t red_row = red_tile + (uint32_t)(lane * BL::RED_PITCH * 4);
+  // one step backwards in time moves one global row against the walk direction
+  const int64_t gdu = -(int64_t)rstep * d.ld_du, gdd = -(int64_t)rstep * d.ld_dd;
+  const int64_t gdz = -(int64_t)rstep * p.ld_dz, goz = -(int64_t)rstep * p.ld_oz;
+  const int gws = -rstep * 32;
 
   for (int q = 0; q < nchunks; ++q) {
     const int c = nchunks - 1 - q;
@@ -262,15 +282,24 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
 #pragma unroll
       for (int k = 0; k < SCAN_NS / 2; ++k) h[k] = pk2(ldsf(ck + (uint32_t)(2 * k) * (BT_CH * 4)), ldsf(ck + (uint32_t)(2 * k + 1) * (BT_CH * 4)));
       tmem_st16(hcol, h);
-      uint32_t a_u = t_u, a_d = t_d, a_bc = t_bc, slot = hcol + SCAN_NS;
+      if (SPEC && ns == BT_TT) {       // full chunk: every shared-memory / tensor-memory address is base + immediate
+#pragma unroll
+        for (int j = 0; j < BT_TT - 1; ++j)
+          replay_step<true>(ldst<T>(t_u + (uint32_t)(j * s16)), ldsf(t_d + (uint32_t)(j * s32)), t_bc + (uint32_t)(j * sbc),
+                            hcol + (uint32_t)(j + 1) * SCAN_NS, h, a2);
+        replay_step<false>(ldst<T>(t_u + (uint32_t)((BT_TT - 1) * s16)), ldsf(t_d + (uint32_t)((BT_TT - 1) * s32)),
+                           t_bc + (uint32_t)((BT_TT - 1) * sbc), 0u, h, a2);
+      } else {
+        uint32_t a_u = t_u, a_d = t_d, a_bc = t_bc, slot = hcol + SCAN_NS;
 #pragma unroll 1
-      for (int j = 0; j < ns - 1; ++j) {
-        replay_step<true>(ldst<T>(a_u), ldsf(a_d), a_bc, slot, h, a2);
-        a_u += s16; a_d += s32; a_bc += sbc; slot += SCAN_NS;
+        for (int j = 0; j < ns - 1; ++j) {
+          replay_step<true>(ldst<T>(a_u), ldsf(a_d), a_bc, slot, h, a2);
+          a_u += s16; a_d += s32; a_bc += sbc; slot += SCAN_NS;
+        }
+        // the chunk's last step: its result h_{ns-1} is not history (it is the next chunk's checkpoint) but the
+        // reverse-time loop below starts with it, and from there on carries h_s over from the h_{s-1} it loads
+        replay_step<false>(ldst<T>(a_u), ldsf(a_d), a_bc, slot, h, a2);
       }
-      // the chunk's last step: its result h_{ns-1} is not history (it is the next chunk's checkpoint) but the reverse-time
-      // loop below starts with it, and from there on carries h_s over from the h_{s-1} it loads - no recomputation
-      replay_step<false>(ldst<T>(a_u), ldsf(a_d), a_bc, slot, h, a2);
 #pragma unroll
       for (int k = 0; k < SCAN_NS / 2; ++k) hcur[k] = h[k];
       asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory");   // the history is read back by the same thread below
@@ -288,30 +317,26 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
       float* dup = d.du + r_last * d.ld_du + ch;
       float* ddp = d.ddelta + r_last * d.ld_dd + ch;
       float* wsp = d.dbc_ws + ((int64_t)part * rows_total + r_last) * 32 + 2 * (lane & 15);   // lanes 0-15 store float2
-      const uint32_t red_tile = redt + (uint32_t)((tig >> 5) * 32 * BL::RED_PITCH * 4);
-      const uint32_t red_row = red_tile + (uint32_t)(lane * BL::RED_PITCH * 4);
-      T* dzp = p.dz ? reinterpret_cast<T*>(p.dz) + r_last * p.ld_dz + ch : nullptr;
-      T* ozp = p.outz ? reinterpret_cast<T*>(p.outz) + r_last * p.ld_oz + ch : nullptr;
-      // one step backwards in time moves one global row against the walk direction
-      const int64_t gdu = -(int64_t)rstep * d.ld_du, gdd = -(int64_t)rstep * d.ld_dd;
-      const int64_t gdz = -(int64_t)rstep * p.ld_dz, goz = -(int64_t)rstep * p.ld_oz;
-      const int gws = -rstep * 32;
-#pragma unroll 2
-      for (int j = jl; j >= 0; --j) {
-        const float u = ldst<T>(a_u), dl = ldsf(a_d), go = ldst<T>(a_g) * scale;
-        const float zv = has_z ? ldst<T>(a_z) : 0.f;
-        const float sz = has_z ? silu_f(zv) : 1.f;
+      T* dzp = (SPEC ? GATE_ : (p.dz != nullptr)) ? reinterpret_cast<T*>(p.dz) + r_last * p.ld_dz + ch : nullptr;
+      T* ozp = (SPEC ? GATE_ : (p.outz != nullptr)) ? reinterpret_cast<T*>(p.outz) + r_last * p.ld_oz + ch : nullptr;
+
+      // one reverse-time step; every o* is the (compile-time, when unrolled) offset of the step from the a_* bases
+      auto rstep_fn = [&](const uint32_t o16, const uint32_t o32, const uint32_t obc, const uint32_t oslot) {
+        const float u = ldst<T>(a_u + o16), dl = ldsf(a_d + o32), go = ldst<T>(a_g + o16) * scale;
+        const float zv = has_z ? ldst<T>(a_z + o16) : 0.f;
+        const float sg = has_z ? sigmoid_ftz(zv) : 1.f;          // sigmoid(z); silu(z) = z sg
+        const float sz = has_z ? zv * sg : 1.f;
         const float dy = go * sz;
         dD_acc = fmaf(dy, u, dD_acc);
         const float dlu = dl * u;
         const f32x2 dl2 = pk2(dl, dl), dy2 = pk2(dy, dy), dlu2 = pk2(dlu, dlu);
         f32x2 sB2 = pk2(0.f, 0.f), dd2 = pk2(0.f, 0.f);
         f32x2 hprev[SCAN_NS / 2];
-        tmem_ld16(slot, hprev);                                                 // h_{s-1}, all 16 states
+        tmem_ld16(slot + oslot, hprev);                                         // h_{s-1}, all 16 states
 #pragma unroll
         for (int qq = 0; qq < 4; ++qq) {
-          const float4 Bv = ldsf4(a_bc + 16u * qq);
-          const float4 Cv = ldsf4(a_bc + 16u * (4 + qq));
+          const float4 Bv = ldsf4(a_bc + obc + 16u * qq);
+          const float4 Cv = ldsf4(a_bc + obc + 16u * (4 + qq));
           const f32x2 hp[2] = {hprev[2 * qq], hprev[2 * qq + 1]};
 #pragma unroll
           for (int hq = 0; hq < 2; ++hq) {
@@ -324,7 +349,7 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
             gcar[k] = mul2(a, dh);
             const f32x2 t1 = mul2(gcar[k], hp[hq]);                 // dh * a * h_{s-1}
             dA_acc[k] = fma2(t1, dl2, dA_acc[k]);
-            dd2 = fma2(t1, Av2[k], dd2);
+            dd2 = fma2(t1, a2[k], dd2);                             // x log2(e); undone below
             sB2 = fma2(dh, Bp, sB2);
             sts_pair(red_row + (uint32_t)(8 * k), mul2(dh, dlu2));                    // dB contributions
             sts_pair(red_row + (uint32_t)(8 * (SCAN_NS / 2 + k)), mul2(hcur[k], dy2));   // dC contributions (h_s carried over)
@@ -334,7 +359,7 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
         float s0_, s1_, d0_, d1_;
         upk2(sB2, s0_, s1_); upk2(dd2, d0_, d1_);
         const float sB = s0_ + s1_;
-        float dd = fmaf(sB, u, d0_ + d1_);
+        float dd = fmaf(sB, u, (d0_ + d1_) * 0.6931471805599453f);
         const float duv = fmaf(dl, sB, Dv * dy);
         // cross-channel sums of this token: lane i of each warp ends up with value i; one plain 128-byte store per
         // warp into this warp's slice of the partial workspace (summed over warps by dbc_reduce_kernel).
@@ -344,23 +369,38 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
           smem_column_sums(red_tile, lane, c_lo, c_hi);
           if (lane < 16) *reinterpret_cast<float2*>(wsp) = make_float2(c_lo, c_hi);
         }
-        if (spg_on) dd *= 1.f - __expf(-dl);                       // softplus'(pre) = 1 - exp(-delta)
+        if (spg_on) dd *= 1.f - ex2_approx(-1.4426950408889634f * dl);   // softplus'(pre) = 1 - exp(-delta), delta >= 0
         if (active) {
           if (accumulate) { red_add_f32(dup, duv); red_add_f32(ddp, dd); }
           else { *dup = duv; *ddp = dd; }
           if (gate) {
-            const float yp = want_y ? ldst<T>(a_y) : 0.f;
-            if (dzp) {
-              const float sg = __fdividef(1.f, 1.f + __expf(-zv));             // sigmoid(z)
-              *dzp = from_f<T>(go * yp * (sg * (1.f + zv * (1.f - sg))));
-            }
+            const float yp = want_y ? ldst<T>(a_y + o16) : 0.f;
+            if (dzp) *dzp = from_f<T>(go * yp * (sg * (1.f + zv * (1.f - sg))));
             if (ozp) *ozp = from_f<T>(scale * yp * sz);
           }
         }
-        a_u -= s16; a_g -= s16; a_z -= s16; a_y -= s16; a_d -= s32; a_bc -= sbc; slot -= SCAN_NS;
         dup += gdu; ddp += gdd; wsp += gws;
         if (dzp) dzp += gdz;
         if (ozp) ozp += goz;
+      };
+
+      if (SPEC && ns == BT_TT) {
+        // full chunk: two steps per trip, the second at compile-time offsets from the same bases
+        constexpr int S16 = REV_ ? -(BT_CH * (int)sizeof(T)) : (BT_CH * (int)sizeof(T));
+        constexpr int S32 = REV_ ? -(BT_CH * 4) : (BT_CH * 4);
+        constexpr int SBC = REV_ ? -(SCAN_ROW * 4) : (SCAN_ROW * 4);
+#pragma unroll 1
+        for (int j = 0; j < BT_TT / 2; ++j) {
+          rstep_fn(0u, 0u, 0u, 0u);
+          rstep_fn((uint32_t)(-S16), (uint32_t)(-S32), (uint32_t)(-SBC), (uint32_t)(-SCAN_NS));
+          a_u -= 2 * S16; a_g -= 2 * S16; a_z -= 2 * S16; a_y -= 2 * S16; a_d -= 2 * S32; a_bc -= 2 * SBC; slot -= 2 * SCAN_NS;
+        }
+      } else {
+#pragma unroll 1
+        for (int j = jl; j >= 0; --j) {
+          rstep_fn(0u, 0u, 0u, 0u);
+          a_u -= s16; a_g -= s16; a_z -= s16; a_y -= s16; a_d -= s32; a_bc -= sbc; slot -= SCAN_NS;
+        }
       }
     }
 
@@ -383,18 +423,42 @@ scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParam
   if (tig < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BT_TMEM_COLS) : "memory");
 }
 
+template <typename T, bool SPEC>
+__global__ void __launch_bounds__(BT_CH, 3)
+scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParams p) {
+  extern __shared__ uint8_t smem_raw[];
+  if (SPEC) {
+    if (blockIdx.z == 0) scan_bwd_cta<T, true, false, true>(maps, p, smem_raw);
+    else                 scan_bwd_cta<T, true, true, false>(maps, p, smem_raw);
+  } else {
+    scan_bwd_cta<T, false, false, false>(maps, p, smem_raw);
+  }
+}
+
+// SPEC eligibility: see scan_bwd_cta
+static bool bwd_spec_ok(const ScanBwdParams& p) {
+  if (p.z == nullptr || p.ypre == nullptr || p.dz == nullptr || p.outz == nullptr || !p.softplus_grad) return false;
+  if (p.Dch % BT_CH != 0 || p.dir[0].reverse != 0) return false;
+  if (p.ndirs == 2 && (p.dir[1].reverse == 0 || p.shared_du)) return false;
+  static int off = -1;
+  if (off < 0) off = getenv("AUM_SCAN_BWD_NOSPEC") != nullptr ? 1 : 0;
+  return off == 0;
+}
+
 template <typename T>
 static int launch_bt(const ScanBwdMaps& maps, const ScanBwdParams& p, cudaStream_t st) {
   using BL = BwdLayout<T>;
   static PerDevice<bool> attr_set_dev;
   bool& attr_set = attr_set_dev.cur();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("aum_selective_scan_bwd: cudaFuncSetAttribute(smem=%d): %s", BL::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
     attr_set = true;
   }
   dim3 grid(ceil_div(p.Dch, BT_CH), p.batch, p.ndirs);
-  scan_bwd_tma_kernel<T><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
+  if (bwd_spec_ok(p)) scan_bwd_tma_kernel<T, true><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
+  else                scan_bwd_tma_kernel<T, false><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
   return check_launch("aum_selective_scan_bwd(tma)");
 }
 

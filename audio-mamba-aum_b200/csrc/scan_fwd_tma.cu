@@ -18,7 +18,7 @@
 //     the walk direction being a template parameter).
 //   * the partial y of the first half-walk is parked in `out` exactly as in the generic kernel; the second
 //     half receives it back as a fourth TMA tile per stage (issued after the CTA-wide phase barrier).
-// Eligibility (checked in launch_scan_tma): d_state == 16, packed fp32 [B|C] rows, fp32 delta without
+// Eligibility (checked in launch_scan_tma): d_state == 16, packed fp32 [B|C] rows, delta in fp32 or in the activation dtype, without
 // bias/softplus left to apply, 16-byte aligned bases and row pitches.  Anything else runs scan_fwd.cu.
 #include <cuda.h>
 #include <stdlib.h>
@@ -63,10 +63,11 @@ __device__ __forceinline__ bool scan_elect() {
 // next to a half-size tcgen05 GEMM CTA on every SM (so that the XU and the tensor pipe overlap) was tried as well:
 // the scan loses more (8 warps: -35 %) than the overlap wins, whole-model throughput -5 %; see DESIGN.md.
 
-// NSTG: ring depth per direction
-template <typename T, int NSTG, int CH> struct StageLayout {
+// NSTG: ring depth per direction.  TD: element type of delta (float, or T when dt_proj's epilogue already rounded
+// delta to the activation dtype - the reference rounds it there too, selective_scan_interface.py:468 under autocast).
+template <typename T, typename TD, int NSTG, int CH> struct StageLayout {
   static constexpr int U_BYTES = ST_TT * CH * (int)sizeof(T);
-  static constexpr int D_BYTES = ST_TT * CH * 4;
+  static constexpr int D_BYTES = ST_TT * CH * (int)sizeof(TD);
   static constexpr int Z_BYTES = U_BYTES;
   static constexpr int BC_BYTES = ST_TT * SCAN_ROW * 4;
   static constexpr int P_BYTES = U_BYTES;                  // parked partials of the other direction (rows of `out`)
@@ -150,14 +151,14 @@ __device__ __forceinline__ float scan_step(float u, float dl, uint32_t a_bc, flo
 // The body is unrolled by 4 steps and run twice: ~5.5 KB of SASS per instantiation, so that the four bodies a
 // resident CTA pair can be in at once (2 directions x 2 phases) stay inside the 32 KB L1.5 instruction cache; the
 // fully unrolled 8-step bodies did not and lost 7% to instruction-fetch stalls.
-template <typename T, int CH, bool FIN, bool PARTIAL, int ZM, bool REV, bool YPRE>
+template <typename T, typename TD, int CH, bool FIN, bool PARTIAL, int ZM, bool REV, bool YPRE>
 __device__ __forceinline__ void scan_tile_full(uint32_t a_u, uint32_t a_d, uint32_t a_z, uint32_t a_bc, uint32_t a_p,
                                                float Dv, float oscale, bool active,
                                                f32x2 (&h)[SCAN_NS / 2], const f32x2 (&a2)[SCAN_NS / 2],
                                                T* pyp, ptrdiff_t ostep) {
   constexpr int HALF = AUM_SCAN_UNROLL;             // steps per trip
   static_assert(ST_TT % HALF == 0, "AUM_SCAN_UNROLL must divide the tile");
-  constexpr int P16 = CH * (int)sizeof(T), P32 = CH * 4, PBC = SCAN_ROW * 4;
+  constexpr int P16 = CH * (int)sizeof(T), P32 = CH * (int)sizeof(TD), PBC = SCAN_ROW * 4;
   if (REV) { a_u += (ST_TT - HALF) * P16; a_z += (ST_TT - HALF) * P16; a_p += (ST_TT - HALF) * P16; a_d += (ST_TT - HALF) * P32; a_bc += (ST_TT - HALF) * PBC; }
 #pragma unroll 1
   for (int hf = 0; hf < ST_TT / HALF; ++hf) {
@@ -165,7 +166,7 @@ __device__ __forceinline__ void scan_tile_full(uint32_t a_u, uint32_t a_d, uint3
     for (int t = 0; t < HALF; ++t) {
       const int r = REV ? (HALF - 1 - t) : t;
       const uint32_t o16 = (uint32_t)(r * P16);
-      float y = scan_step(lds_t<T>(a_u + o16), lds_f(a_d + (uint32_t)(r * P32)), a_bc + (uint32_t)(r * PBC), Dv, h, a2);
+      float y = scan_step(lds_t<T>(a_u + o16), lds_t<TD>(a_d + (uint32_t)(r * P32)), a_bc + (uint32_t)(r * PBC), Dv, h, a2);
       if (FIN) {
         if (PARTIAL) y += lds_t<T>(a_p + o16);
         if (YPRE) { if (active) *pyp = from_f<T>(y); pyp += ostep; }   // pre-gate y saved for the backward pass
@@ -181,7 +182,7 @@ __device__ __forceinline__ void scan_tile_full(uint32_t a_u, uint32_t a_d, uint3
 }
 
 // A short tile (first tile of the walk or its last): rolled loop, parked partials read directly.
-template <typename T>
+template <typename T, typename TD>
 __device__ __forceinline__ void scan_tile_tail(int nt, bool fin, bool partial, bool has_z,
                                                uint32_t a_u, uint32_t a_d, uint32_t a_z, uint32_t a_bc, uint32_t a_p,
                                                int su, int sd, int sbc, float Dv, float oscale, bool active,
@@ -189,7 +190,7 @@ __device__ __forceinline__ void scan_tile_tail(int nt, bool fin, bool partial, b
                                                T* po, ptrdiff_t ostep, ptrdiff_t ypre_off, bool zpre) {
 #pragma unroll 1
   for (int t = 0; t < nt; ++t) {
-    float y = scan_step(lds_t<T>(a_u), lds_f(a_d), a_bc, Dv, h, a2);
+    float y = scan_step(lds_t<T>(a_u), lds_t<TD>(a_d), a_bc, Dv, h, a2);
     if (fin) {
       if (partial) y += lds_t<T>(a_p);
       if (ypre_off != 0 && active) po[ypre_off] = from_f<T>(y);
@@ -205,10 +206,10 @@ __device__ __forceinline__ void scan_tile_tail(int nt, bool fin, bool partial, b
 // CKPT: the training instantiation (state checkpoints before every tile, for aum_selective_scan_bwd); inference
 // launches run the CKPT = false instantiation, whose tile loops carry no checkpoint stores (smaller loop bodies: the
 // steady-state loops of the resident CTAs compete for the 32 KB instruction cache).
-template <typename T, int MINB, int NSTG, int CH, bool CKPT>
+template <typename T, typename TD, int MINB, int NSTG, int CH, bool CKPT>
 __global__ void __launch_bounds__(CH <= 128 ? 2 * CH : 512, MINB)      // either way: at most 128 registers per thread
 scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p) {
-  using SL = StageLayout<T, NSTG, CH>;
+  using SL = StageLayout<T, TD, NSTG, CH>;
   constexpr int NW = CH / 32;                 // warps per direction
   extern __shared__ uint8_t smem_raw[];
   const uint32_t smem0 = (s_u32(smem_raw) + 127u) & ~127u;
@@ -339,7 +340,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   // the pre-gate output (if requested) shares out's row pitch: address it as an element offset from the out row
   const ptrdiff_t ypre_off = p.ypre ? (reinterpret_cast<T*>(p.ypre) - reinterpret_cast<T*>(p.out)) : 0;
   const int su = rev ? -(int)(CH * sizeof(T)) : (int)(CH * sizeof(T));
-  const int sd = rev ? -(CH * 4) : (CH * 4);
+  const int sd = rev ? -(CH * (int)sizeof(TD)) : (CH * (int)sizeof(TD));
   const int sbc = rev ? -(SCAN_ROW * 4) : (SCAN_ROW * 4);
 
   float* ckp = (CKPT && d.ckpt) ? d.ckpt + (int64_t)b * scan_ck_count_max(L) * SCAN_NS * p.Dch + ch : nullptr;
@@ -348,7 +349,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   // between two tile bodies is pure latency for the warp, and with four warps per scheduler it showed up as 19 % of
   // all stall samples): walk position, ring stage, the parity bits of the stage barriers, k mod NW.
   const int m_store = (warp_in_group + 1) % NW, m_refill = (warp_in_group + 2) % NW;   // k mod NW at which this warp stores / refills
-  const uint32_t o_u = SL::OFF_U + (uint32_t)tig * (uint32_t)sizeof(T), o_d = SL::OFF_D + (uint32_t)tig * 4u;
+  const uint32_t o_u = SL::OFF_U + (uint32_t)tig * (uint32_t)sizeof(T), o_d = SL::OFF_D + (uint32_t)tig * (uint32_t)sizeof(TD);
   const uint32_t o_z = SL::OFF_Z + (uint32_t)tig * (uint32_t)sizeof(T), o_p = SL::OFF_P + (uint32_t)tig * (uint32_t)sizeof(T);
   const bool save_ypre = ypre_off != 0;
   int s0 = 0, stage = 0, m = 0;
@@ -391,7 +392,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     if (nt == ST_TT) {
       T* pyp = nullptr;
       if (fin && save_ypre) pyp = ob + (int64_t)(row0 + (rev ? (L - 1 - s0) : s0)) * ldo + ypre_off;
-#define AUM_TILE(F, P, Z, R, Y) scan_tile_full<T, CH, F, P, Z, R, Y>(b_u, b_d, b_z, b_bc, b_p, Dv, oscale, active, h, a2, pyp, ostep)
+#define AUM_TILE(F, P, Z, R, Y) scan_tile_full<T, TD, CH, F, P, Z, R, Y>(b_u, b_d, b_z, b_bc, b_p, Dv, oscale, active, h, a2, pyp, ostep)
 #define AUM_TILE_Z(F, P, R) do { if (zmode == 0) AUM_TILE(F, P, 0, R, false); else if (zmode == 2) AUM_TILE(F, P, 2, R, false); \
                                  else if (save_ypre) AUM_TILE(F, P, 1, R, true); else AUM_TILE(F, P, 1, R, false); } while (0)
       if (rev) {
@@ -409,8 +410,8 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
     } else {
       const int row_first = rev ? (ST_TT - 1) : 0;
       T* po = ob + (int64_t)(row0 + (rev ? (L - 1 - s0) : s0)) * ldo;    // global row of step s0
-      scan_tile_tail<T>(nt, fin, partial, has_z, b_u + (uint32_t)(row_first * CH * (int)sizeof(T)),
-                        b_d + (uint32_t)(row_first * CH * 4), b_z + (uint32_t)(row_first * CH * (int)sizeof(T)),
+      scan_tile_tail<T, TD>(nt, fin, partial, has_z, b_u + (uint32_t)(row_first * CH * (int)sizeof(T)),
+                        b_d + (uint32_t)(row_first * CH * (int)sizeof(TD)), b_z + (uint32_t)(row_first * CH * (int)sizeof(T)),
                         b_bc + (uint32_t)(row_first * SCAN_ROW * 4), b_p + (uint32_t)(row_first * CH * (int)sizeof(T)),
                         su, sd, sbc, Dv, oscale, active, h, a2, po, ostep, ypre_off, zpre);
     }
@@ -457,7 +458,7 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
       if (PART) { sbar_wait(pfull_bar(stage), (ppar >> stage) & 1u); ppar ^= 1u << stage; }
       T* pyp = nullptr;
       if (YPRE) pyp = ob + (int64_t)(row0 + (REV ? (L - 1 - s0) : s0)) * ldo + ypre_off;
-      scan_tile_full<T, CH, FIN, PART, ZM, REV, YPRE>(st + o_u, st + o_d, st + o_z, st + SL::OFF_BC, st + o_p, Dv, oscale,
+      scan_tile_full<T, TD, CH, FIN, PART, ZM, REV, YPRE>(st + o_u, st + o_d, st + o_z, st + SL::OFF_BC, st + o_p, Dv, oscale,
                                                       active, h, a2, pyp, ostep);
       asm volatile("fence.proxy.async.shared::cta;" ::: "memory");   // y tile (generic proxy) -> bulk store (async proxy)
       __syncwarp();
@@ -517,44 +518,47 @@ scan_fwd_tma_kernel(const __grid_constant__ ScanTmaMaps maps, const ScanParams p
   }
 }
 
-template <typename T, int NSTG, int CH>
+template <typename T, typename TD, int NSTG, int CH>
 static int launch_n(const ScanTmaMaps& maps, const ScanParams& p, cudaStream_t st) {
-  using SL = StageLayout<T, NSTG, CH>;
+  using SL = StageLayout<T, TD, NSTG, CH>;
   constexpr int MINB = CH <= 128 ? 2 : 1;
   static PerDevice<bool> attr_set_dev;
   bool& attr_set = attr_set_dev.cur();
   // CH = 128: two resident CTAs per SM (128 registers, 90-110 KB of stages each); a 3-CTA / 80-register build measured slower
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, MINB, NSTG, CH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, MINB, NSTG, CH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, TD, MINB, NSTG, CH, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_fwd_tma_kernel<T, TD, MINB, NSTG, CH, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, SL::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("aum_selective_scan_fwd: cudaFuncSetAttribute(smem=%d): %s", SL::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
     attr_set = true;
   }
   dim3 grid(ceil_div(p.Dch, CH), p.batch);
   const int smem = p.ndirs * SL::GROUP_BYTES + 128 + 2 * 3 * NSTG * 8;     // one ring per direction actually launched
   const bool ckpt = p.dir[0].ckpt != nullptr || (p.ndirs == 2 && p.dir[1].ckpt != nullptr);
-  if (ckpt) scan_fwd_tma_kernel<T, MINB, NSTG, CH, true><<<grid, CH * p.ndirs, smem, st>>>(maps, p);
-  else      scan_fwd_tma_kernel<T, MINB, NSTG, CH, false><<<grid, CH * p.ndirs, smem, st>>>(maps, p);
+  if (ckpt) scan_fwd_tma_kernel<T, TD, MINB, NSTG, CH, true><<<grid, CH * p.ndirs, smem, st>>>(maps, p);
+  else      scan_fwd_tma_kernel<T, TD, MINB, NSTG, CH, false><<<grid, CH * p.ndirs, smem, st>>>(maps, p);
   return check_launch("aum_selective_scan_fwd(tma)");
 }
 
-// AUM_SCAN_TMA_CH=192 selects the one-CTA-per-SM build (see the note on CH above); ring depth 3 there (98 KB).
+// AUM_SCAN_TMA_CH=192 selects the one-CTA-per-SM build (see the note on CH above; ring depth 3 there: 98 KB).  The
+// production build is CH = 128 with a 4-deep ring (3 and 5 were measured: 5 is 1-3 % slower, 3 starves the walk).
 int scan_tma_ch() {
   static int ch = 0;
   if (ch == 0) { const char* e = getenv("AUM_SCAN_TMA_CH"); ch = (e && atoi(e) == 192) ? 192 : 128; }
   return ch;
 }
 
-template <typename T>
+template <typename T, typename TD>
 static int launch_t(const ScanTmaMaps& maps, const ScanParams& p, cudaStream_t st) {
-  static int nstg = 0;
-  if (nstg == 0) { const char* e = getenv("AUM_SCAN_NSTG"); nstg = (e && atoi(e) == 5) ? 5 : (e && atoi(e) == 3) ? 3 : 4; }   // 4 measured best (5: 1-3% slower)
-  if (scan_tma_ch() == 192) return nstg == 3 ? launch_n<T, 3, 192>(maps, p, st) : launch_n<T, 4, 192>(maps, p, st);
-  return nstg == 4 ? launch_n<T, 4, 128>(maps, p, st) : nstg == 3 ? launch_n<T, 3, 128>(maps, p, st) : launch_n<T, 5, 128>(maps, p, st);
+  if (scan_tma_ch() == 192) {
+    if constexpr (std::is_same<TD, float>::value) return launch_n<T, float, 3, 192>(maps, p, st);
+    else return -1;                                      // the 192-channel experiment build takes fp32 delta only
+  }
+  return launch_n<T, TD, 4, 128>(maps, p, st);
 }
 
 int launch_scan_tma(const ScanParams& p, int dtype, int delta_dt, cudaStream_t st) {
-  if (p.N != SCAN_NS || delta_dt != AUM_F32 || !tma_available()) return -1;
+  if (p.N != SCAN_NS || (delta_dt != AUM_F32 && delta_dt != dtype) || !tma_available()) return -1;
+  const int dsz = dtype_size(delta_dt);
   const int esz = dtype_size(dtype);
   auto ok_mat = [](const void* base, int64_t ld, int sz) { return aligned16(base) && (ld * sz) % 16 == 0; };
   if (!ok_mat(p.out, p.ld_out, esz) || p.ld_out * esz % 2 != 0) return -1;
@@ -564,7 +568,7 @@ int launch_scan_tma(const ScanParams& p, int dtype, int delta_dt, cudaStream_t s
   for (int g = 0; g < p.ndirs; ++g) {
     const ScanDirDev& d = p.dir[g];
     if (!d.bc_packed || d.delta_softplus || d.delta_bias != nullptr) return -1;
-    if (!ok_mat(d.u, d.ld_u, esz) || !ok_mat(d.delta, d.ld_delta, 4) || !aligned16(d.A)) return -1;
+    if (!ok_mat(d.u, d.ld_u, esz) || !ok_mat(d.delta, d.ld_delta, dsz) || !aligned16(d.A)) return -1;
   }
   ScanTmaMaps maps;
   const int CH = scan_tma_ch();
@@ -572,15 +576,15 @@ int launch_scan_tma(const ScanParams& p, int dtype, int delta_dt, cudaStream_t s
   for (int g = 0; g < 2; ++g) {
     const ScanDirDev& d = p.dir[g < p.ndirs ? g : 0];
     if (int rc = tma_encode_2d(&maps.u[g], d.u, dtype, rows, p.Dch, d.ld_u, ST_TT, CH, false, "aum_selective_scan_fwd(u)")) return rc;
-    if (int rc = tma_encode_2d(&maps.d[g], d.delta, AUM_F32, rows, p.Dch, d.ld_delta, ST_TT, CH, false, "aum_selective_scan_fwd(delta)")) return rc;
+    if (int rc = tma_encode_2d(&maps.d[g], d.delta, delta_dt, rows, p.Dch, d.ld_delta, ST_TT, CH, false, "aum_selective_scan_fwd(delta)")) return rc;
   }
   if (p.z) { if (int rc = tma_encode_2d(&maps.z, p.z, dtype, rows, p.Dch, p.ld_z, ST_TT, CH, false, "aum_selective_scan_fwd(z)")) return rc; }
   else maps.z = maps.u[0];
   if (int rc = tma_encode_2d(&maps.o, p.out, dtype, rows, p.Dch, p.ld_out, ST_TT, CH, false, "aum_selective_scan_fwd(out)")) return rc;
   switch (dtype) {
-    case AUM_F32:  return launch_t<float>(maps, p, st);
-    case AUM_F16:  return launch_t<__half>(maps, p, st);
-    case AUM_BF16: return launch_t<__nv_bfloat16>(maps, p, st);
+    case AUM_F32:  return launch_t<float, float>(maps, p, st);
+    case AUM_F16:  return delta_dt == AUM_F32 ? launch_t<__half, float>(maps, p, st) : launch_t<__half, __half>(maps, p, st);
+    case AUM_BF16: return delta_dt == AUM_F32 ? launch_t<__nv_bfloat16, float>(maps, p, st) : launch_t<__nv_bfloat16, __nv_bfloat16>(maps, p, st);
   }
   return -1;
 }

@@ -106,6 +106,11 @@ def main():
             report(f"biscan_pregated_ch{ch}", ms, bytes_=alg, exp_per_s_T=round(M * Di * 32 / ms / 1e9, 3))
             ms = timeit(lambda: ops.selective_scan(mk(A), None, z, out=out), flush=flush)
             report(f"uniscan_ch{ch}", ms, bytes_=alg, exp_per_s_T=round(M * Di * 16 / ms / 1e9, 3))
+        if dt != torch.float32:       # delta in the activation dtype (the inference default): SURVEY 8(d)'s byte count exactly
+            d16 = delta.to(dt)
+            mk16 = lambda Ax: ops.ScanDirection(u, d16, Ax, bc[..., :N], bc[..., N:], Dv)
+            ms = timeit(lambda: ops.selective_scan(mk16(A), mk16(A_b), z, out=out, z_pregated=True), flush=flush)
+            report("biscan_pregated_delta16", ms, bytes_=M * Di * 4 * s + M * 2 * N * 4, exp_per_s_T=round(M * Di * 32 / ms / 1e9, 3))
     if "bwd" in only:
         u, z = rn(B, Lq, Di), rn(B, Lq, Di)
         ypre, dout = rn(B, Lq, Di), rn(B, Lq, Di)
@@ -162,6 +167,9 @@ def main():
                 bias = rn(n_, dtype=torch.float32)
                 ms = timeit(lambda: ops.gemm_tn(a, w, out=out, k=k_, bias=bias, act=L.ACT_SOFTPLUS, backend=L.GEMM_TCGEN05), flush=flush)
                 report("gemm_dt_proj(+bias+softplus)", ms, bytes_=by)
+                out16 = torch.empty(m_, n_, device=dev, dtype=dt)
+                ms = timeit(lambda: ops.gemm_tn(a, w, out=out16, k=k_, bias=bias, act=L.ACT_SOFTPLUS, backend=L.GEMM_TCGEN05), flush=flush)
+                report("gemm_dt_proj(+bias+softplus, 16-bit delta)", ms, bytes_=(m_ * k_ + n_ * k_) * 2 + m_ * n_ * 2)
             if name == "in_proj":
                 ms = timeit(lambda: ops.gemm_tn(a, w, out=out, k=k_, backend=L.GEMM_TCGEN05,
                                                 act=L.act_from(L.ACT_SILU, n_ // 2)), flush=flush)
