@@ -112,8 +112,9 @@ __device__ __forceinline__ void replay_step(float u, float dl, uint32_t a_bc, ui
 // 34 floats: the 16 lanes of a 64-bit access hit 16 distinct bank pairs in both the row-wise stores and the column-wise
 // loads.  ~55 instructions per step against 74 + 32 unpacking moves for the scalar version of round 1 (in a kernel that
 // is issue-bound).
-__device__ __forceinline__ f32x2 add2(f32x2 a, f32x2 b) { f32x2 r; asm("add.rn.f32x2 %0, %1, %2;" : "=l"(r) : "l"(a), "l"(b)); return r; }
-__device__ __forceinline__ void sts_pair(uint32_t a, f32x2 v) { asm volatile("st.shared.b64 [%0], %1;" ::"r"(a), "l"(v) : "memory"); }
+// (a plain C++ store: through an asm statement ptxas copied every packed product into one fixed register pair first,
+// 2 MOVs per store, 32 per step)
+__device__ __forceinline__ void sts_pair(uint8_t* a, f32x2 v) { *reinterpret_cast<volatile f32x2*>(a) = v; }
 __device__ __forceinline__ f32x2 lds_pair(uint32_t a) { f32x2 v; asm volatile("ld.shared.b64 %0, [%1];" : "=l"(v) : "r"(a)); return v; }
 
 // After every lane has stored its 16 pairs into its row: the column sums.  Returns, in lanes 0-15, the sums of columns
@@ -255,7 +256,7 @@ __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const Scan
   const uint32_t hcol = tmem_base + ((uint32_t)((tig >> 5) * 32) << 16);   // slot 0 of this warp's TMEM lane quarter
   const bool spg_on = SPEC ? true : (p.softplus_grad != 0);
   const uint32_t red_tile = redt + (uint32_t)((tig >> 5) * 32 * BL::RED_PITCH * 4);
-  const uint32_t red_row = red_tile + (uint32_t)(lane * BL::RED_PITCH * 4);
+  uint8_t* const red_row = smem_raw + (red_tile - s_u32(smem_raw)) + lane * BL::RED_PITCH * 4;
   // one step backwards in time moves one global row against the walk direction
   const int64_t gdu = -(int64_t)rstep * d.ld_du, gdd = -(int64_t)rstep * d.ld_dd;
   const int64_t gdz = -(int64_t)rstep * p.ld_dz, goz = -(int64_t)rstep * p.ld_oz;
@@ -351,8 +352,8 @@ __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const Scan
             dA_acc[k] = fma2(t1, dl2, dA_acc[k]);
             dd2 = fma2(t1, a2[k], dd2);                             // x log2(e); undone below
             sB2 = fma2(dh, Bp, sB2);
-            sts_pair(red_row + (uint32_t)(8 * k), mul2(dh, dlu2));                    // dB contributions
-            sts_pair(red_row + (uint32_t)(8 * (SCAN_NS / 2 + k)), mul2(hcur[k], dy2));   // dC contributions (h_s carried over)
+            sts_pair(red_row + 8 * k, mul2(dh, dlu2));                    // dB contributions
+            sts_pair(red_row + 8 * (SCAN_NS / 2 + k), mul2(hcur[k], dy2));   // dC contributions (h_s carried over)
             hcur[k] = hp[hq];                                       // h_{s-1} is the next (earlier) step's h_s
           }
         }

@@ -137,6 +137,14 @@ def main():
                 ops.ScanBwdDirection(u, delta, A_b, bc, Dv, du, dd, dAb, dD, dbc, ckb, ckpt_valid=valid),
                 z, ypre, dout, dz, oz)
             report(f"biscan_bwd(ckpt_valid={valid})", timeit(bw, iters=5, flush=flush))
+        # as the training step calls it (autograd.py): one du / ddelta pair per direction, softplus' folded in ->
+        # the compile-time specialised instantiation of scan_bwd_tma_kernel
+        du2, dd2 = torch.empty((B, Lq, Di), **f32), torch.empty((B, Lq, Di), **f32)
+        bw = lambda: ops.selective_scan_bwd(
+            ops.ScanBwdDirection(u, delta, A, bc, Dv, du, dd, dA, dD, dbc, ckf, ckpt_valid=True),
+            ops.ScanBwdDirection(u, delta, A_b, bc, Dv, du2, dd2, dAb, dD, dbc, ckb, ckpt_valid=True),
+            z, ypre, dout, dz, oz, softplus_grad=True)
+        report("biscan_bwd(training call: per-direction du/ddelta, softplus')", timeit(bw, iters=5, flush=flush))
         x = rn(B, Lq, 2 * Di)
         w, b_ = rn(Di, 4, dtype=torch.float32), rn(Di, dtype=torch.float32)
         g32 = rn(B, Lq, Di, dtype=torch.float32)
