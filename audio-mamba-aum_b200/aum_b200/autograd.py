@@ -31,7 +31,7 @@ F32 = torch.float32
 
 def _t(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
     """W^T as a contiguous `dtype` matrix (cached per parameter version) — the K-contiguous operand of dX = dY @ W."""
-    return mixer._cache.get(w, f"wT:{dtype}", lambda p: p.reshape(p.shape[0], -1).t().to(dtype).contiguous())
+    return mixer._wT(w, dtype)
 
 
 def _direct(p) -> bool:
@@ -82,7 +82,7 @@ class LinearFn(torch.autograd.Function):
     @staticmethod
     def forward(ctx, x2, weight, bias, out_dtype=None):
         act = x2.dtype
-        w2 = mixer._cache.get(weight, f"w2d:{act}", lambda p: p.reshape(p.shape[0], -1).to(act).contiguous())
+        w2 = mixer._w2d(weight, act)
         y = ops.gemm_tn(x2, w2, bias=mixer._f32(bias) if bias is not None else None, out_dtype=out_dtype)
         ctx.save_for_backward(x2)
         ctx.weight, ctx.bias = weight, bias
@@ -283,8 +283,11 @@ class InnerFn(torch.autograd.Function):
                 dxdbl[:, R + 2 * N:] = 0
             g["xw" + sfx] = _wgrad(dxdbl[:, :R + 2 * N], u_.view(M, Di), xw_)                  # (R+2N, Di) (:589)
             # d(conv_out) = du_scan + dx_dbl @ W_x                                              (:590)
-            wxT = mixer._cache.get(xw_, f"wT_pad:{act}:{wdb}",
-                                   lambda p: torch.nn.functional.pad(p.t().to(act), (0, wdb - p.shape[0])).contiguous())
+            if wdb == xw_.shape[0]:
+                wxT = _t(xw_, act)
+            else:
+                wxT = mixer._cache.get(xw_, f"wT_pad:{act}:{wdb}",
+                                       lambda p: torch.nn.functional.pad(p.t().to(act), (0, wdb - p.shape[0])).contiguous())
             du_x = ops.gemm_tn(dxdbl, wxT, out_dtype=F32)                                      # (M, Di) fp32
             Wc = cw_.shape[-1]
             dw_buf, dw_direct = _grad_buffer(cw_, (Di, Wc))

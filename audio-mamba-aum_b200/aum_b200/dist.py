@@ -146,7 +146,7 @@ class FlatAdam:
     caller can lower its scale."""
 
     def __init__(self, reducer: FlatGradReducer, lr: float = 1e-3, betas=(0.9, 0.999), eps: float = 1e-8,
-                 weight_decay: float = 0.0):
+                 weight_decay: float = 0.0, shadow_dtype: Optional[torch.dtype] = None):
         self.reducer, self.lr, self.betas, self.eps, self.weight_decay = reducer, lr, tuple(betas), eps, weight_decay
         self.t = 0
         self.generation = 0          # bumped by every applied step: derived-weight caches / CUDA graphs key on versions
@@ -159,19 +159,36 @@ class FlatAdam:
         self.flat_p = flat
         self.m = torch.zeros_like(flat)
         self.v = torch.zeros_like(flat)
+        # the step number also lives on the device (aum_adam_step_dev increments it and forms the bias corrections from
+        # it): no argument of the launch changes from step to step, which is what lets TrainStep replay a CUDA graph
+        self.step_dev = torch.zeros((), device=flat.device, dtype=torch.int32)
+        # 16-bit shadow of the parameters, written by the Adam kernel in the same pass (shadow_dtype = the activation
+        # dtype of the model): mixer._w / _w2d hand out views of it instead of launching one cast per weight per step
+        self.flat16 = None
+        if shadow_dtype is not None and shadow_dtype != torch.float32:
+            self.flat16 = flat.to(shadow_dtype)
+            for p, off in zip(reducer.params, reducer.offsets):
+                p._aum_w16 = self.flat16[off:off + p.numel()].view_as(p)
+            self._mark_shadow_current()
 
-    def step(self, grad_scale: float = 1.0, skip_nonfinite: bool = False) -> bool:
-        from . import ops
-        if skip_nonfinite and not bool(torch.isfinite(self.reducer.flat).all()):     # (one host sync, fp16 recipe only)
-            return False
-        self.t += 1
-        ops.adam_step(self.flat_p, self.reducer.flat, self.m, self.v, lr=self.lr, betas=self.betas, eps=self.eps,
-                      weight_decay=self.weight_decay, step=self.t, grad_scale=grad_scale)
-        # the kernel wrote through a raw pointer, which autograd's version counters do not see: bump the engine's weight
-        # generation, which every derived-weight cache entry (16-bit copies, -exp(A_log), ...) and every captured CUDA
-        # graph is keyed on, so both are rebuilt before the next forward.  (Version counters are bumped too where torch
-        # exposes that, for third-party observers; nothing here depends on it.)
+    def _mark_shadow_current(self):
+        if self.flat16 is not None:
+            for p in self.reducer.params:
+                p._aum_w16_ver = p._version
+
+    def resync_shadow(self):
+        """Call after changing parameter values by anything but step() (load_state_dict, manual edits)."""
+        if self.flat16 is not None:
+            self.flat16.copy_(self.flat_p)
+            self._mark_shadow_current()
+
+    def after_device_step(self):
+        """Host-side bookkeeping of one applied update (also called by TrainStep after a CUDA-graph replay, where no
+        Python ran): step count, weight generation (every derived-weight cache entry - transposed copies, -exp(A_log),
+        ... - and every captured inference graph is keyed on it, so both are rebuilt before the next eager forward)
+        and, where torch exposes it, the parameters' version counters for third-party observers."""
         from . import mixer
+        self.t += 1
         mixer.bump_generation()
         bump = getattr(torch._C, "_increment_version", None)
         if bump is not None:
@@ -183,7 +200,17 @@ class FlatAdam:
                         bump(p)
                 except (TypeError, RuntimeError):
                     pass
+        self._mark_shadow_current()
         self.generation += 1
+
+    def step(self, grad_scale: float = 1.0, skip_nonfinite: bool = False) -> bool:
+        from . import ops
+        if skip_nonfinite and not bool(torch.isfinite(self.reducer.flat).all()):     # (one host sync, fp16 recipe only)
+            return False
+        ops.adam_step_dev(self.flat_p, self.reducer.flat, self.m, self.v, self.step_dev, lr=self.lr, betas=self.betas,
+                          eps=self.eps, weight_decay=self.weight_decay, grad_scale=grad_scale, p16=self.flat16)
+        # the kernel wrote through raw pointers, which autograd's version counters do not see
+        self.after_device_step()
         return True
 
     def zero_grad(self):

@@ -89,8 +89,23 @@ class _DerivedCache:
 _cache = _DerivedCache()
 
 
+def shadow16(param: torch.Tensor, dtype: torch.dtype) -> Optional[torch.Tensor]:
+    """The optimiser-maintained 16-bit copy of `param` (aum_b200.dist.FlatAdam(shadow_dtype=...): written by the fused
+    Adam kernel in the same pass as the fp32 update), or None when there is none, it has another dtype, or the parameter
+    was modified behind the optimiser's back since (version counter moved)."""
+    sh = getattr(param, "_aum_w16", None)
+    if sh is None or sh.dtype != dtype or getattr(param, "_aum_w16_ver", None) != param._version:
+        return None
+    return sh
+
+
 def _w(param: torch.Tensor, dtype: torch.dtype, pad_cols: Optional[int] = None) -> torch.Tensor:
     """Weight as contiguous `dtype`, optionally zero-padded to pad_cols columns."""
+    if param.dim() == 2 and (pad_cols is None or pad_cols == param.shape[1]):
+        sh = shadow16(param, dtype)
+        if sh is not None:
+            return sh                 # no cast kernel: the optimiser step already produced it
+
     def make(p):
         t = p.to(dtype)
         if pad_cols is not None and pad_cols != t.shape[1]:
@@ -99,6 +114,24 @@ def _w(param: torch.Tensor, dtype: torch.dtype, pad_cols: Optional[int] = None) 
             t = t2
         return t.contiguous()
     return _cache.get(param, f"w:{dtype}:{pad_cols}", make)
+
+
+def _w2d(param: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """Weight of any rank as a contiguous (out, rest) `dtype` matrix (Linear weights, the patch-embedding conv)."""
+    sh = shadow16(param, dtype)
+    if sh is not None:
+        return sh.reshape(sh.shape[0], -1)
+    return _cache.get(param, f"w2d:{dtype}", lambda p: p.reshape(p.shape[0], -1).to(dtype).contiguous())
+
+
+def _wT(param: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
+    """W^T as a contiguous `dtype` matrix (the K-contiguous operand of dX = dY @ W), cached per parameter version: ONE
+    transpose + cast launch (aum_transpose), reading the 16-bit shadow copy when there is one."""
+    def make(p):
+        sh = shadow16(param, dtype)
+        src = (sh if sh is not None else p).reshape(p.shape[0], -1)
+        return ops.transpose(src.unsqueeze(0), dst_dtype=dtype).squeeze(0)
+    return _cache.get(param, f"wT:{dtype}", make)
 
 
 def _f32(param: torch.Tensor) -> torch.Tensor:

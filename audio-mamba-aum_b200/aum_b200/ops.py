@@ -389,6 +389,27 @@ def adam_step(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor
     L.check(rc, "aum_adam_step")
 
 
+def adam_step_dev(p: torch.Tensor, g: torch.Tensor, m: torch.Tensor, v: torch.Tensor, step_dev: torch.Tensor, *, lr: float,
+                  betas=(0.9, 0.999), eps: float = 1e-8, weight_decay: float = 0.0, grad_scale: float = 1.0,
+                  p16: Optional[torch.Tensor] = None) -> None:
+    """adam_step with the step number in device memory (step_dev: int32 scalar tensor, incremented by the call) and an
+    optional 16-bit shadow copy of the updated parameters (aum_adam_step_dev): every argument of the launch is then
+    step-independent, so a captured CUDA graph of the training step can be replayed."""
+    L.require_cuda(p, g, m, v, step_dev, p16)
+    for t in (p, g, m, v):
+        if t.dtype != torch.float32 or not t.is_contiguous() or t.numel() != p.numel():
+            raise L.AumError("adam_step_dev: p, g, m, v must be contiguous fp32 buffers of one size")
+    if step_dev.dtype != torch.int32 or step_dev.numel() != 1:
+        raise L.AumError("adam_step_dev: step_dev must be an int32 scalar tensor")
+    if p16 is not None and (p16.dtype not in (torch.float16, torch.bfloat16) or p16.numel() != p.numel() or not p16.is_contiguous()):
+        raise L.AumError("adam_step_dev: p16 must be a contiguous fp16 / bf16 buffer of p's size")
+    rc = L.lib().aum_adam_step_dev(L.ptr(p), L.ptr(g), L.ptr(m), L.ptr(v), p.numel(), float(lr), float(betas[0]),
+                                   float(betas[1]), float(eps), float(weight_decay), L.ptr(step_dev), float(grad_scale),
+                                   L.ptr(p16), L.dt(p16.dtype) if p16 is not None else L.BF16, L.stream())
+    L.check(rc, "aum_adam_step_dev")
+    L._launches += 1      # two kernels: the counter increment and the update
+
+
 def patchify(x: torch.Tensor, patch, out_dtype: torch.dtype) -> torch.Tensor:
     """(B, T, F) fp32 spectrogram -> (B * gf * gt, pf * pt) im2col rows of the stride == kernel patch conv
     (aum_patchify; reference: tokenization.py:278-310 via mamba_models.py:510-515)."""

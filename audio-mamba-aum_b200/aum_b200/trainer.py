@@ -18,24 +18,32 @@ from .dist import FlatAdam, FlatGradReducer
 class TrainStep:
     """model: aum_b200.audio_mamba.AudioMamba (fp32 parameters, act_dtype = the mixed-precision dtype).
     n_chunks: pieces the gradient all-reduce is split into (last layers first).  Adam defaults: the reference's recipe
-    (traintest.py:32-34: betas (0.95, 0.999), weight_decay 5e-7, lr from the experiment script)."""
+    (traintest.py:32-34: betas (0.95, 0.999), weight_decay 5e-7, lr from the experiment script).
+    shadow16: the fused Adam kernel also writes the parameters' copy in the activation dtype (no per-weight cast kernels
+    in the next forward).  cuda_graph: capture the WHOLE step (zero, forward, loss, backward incl. the all-reduce pieces
+    launched from its hooks, Adam with a device-side step counter) once per input shape and replay it; inputs are copied
+    into the captured buffers, the returned loss is the captured tensor (overwritten by the next call)."""
 
     def __init__(self, model, lr: float = 1e-5, betas=(0.95, 0.999), eps: float = 1e-8, weight_decay: float = 5e-7,
-                 n_chunks: int = 3, loss: str = "bce"):
+                 n_chunks: int = 3, loss: str = "bce", shadow16: bool = True, cuda_graph: bool = False):
         self.model = model
         params, chunk_after, self.hook_layers = model.grad_ready_order(n_chunks)
         self.reducer = FlatGradReducer(params, chunk_after=chunk_after)
-        self.opt = FlatAdam(self.reducer, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay)
+        act = getattr(model, "act_dtype", torch.float32)
+        self.opt = FlatAdam(self.reducer, lr=lr, betas=betas, eps=eps, weight_decay=weight_decay,
+                            shadow_dtype=act if (shadow16 and act != torch.float32) else None)
         model._grad_sync = (self.reducer, self.hook_layers)
         self.loss_name = loss
         self.timing: Optional[List] = None     # when a list: (start, end) CUDA events around the exposed part of the all-reduce
+        self.cuda_graph = cuda_graph
+        self._graph = None                     # (key, CUDAGraph, static x, static labels, static loss)
 
     def loss_fn(self, logits, labels):
         if self.loss_name == "bce":
             return torch.nn.functional.binary_cross_entropy_with_logits(logits, labels)
         return torch.nn.functional.cross_entropy(logits, torch.argmax(labels.long(), dim=1))     # (traintest.py:150)
 
-    def __call__(self, x: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+    def _eager(self, x: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         self.reducer.zero()                                   # optimizer.zero_grad()   (traintest.py:167)
         loss = self.loss_fn(self.model(x), labels)            # (:144-152)
         loss.backward()                                       # accelerator.backward: chunks launch from hooks (:168)
@@ -48,3 +56,47 @@ class TrainStep:
             self.timing.append((e0, e1))
         self.opt.step()                                       # (:169)
         return loss
+
+    def _capture(self, x: torch.Tensor, labels: torch.Tensor, key):
+        from . import mixer
+        dev = x.device
+        sx, sy = x.clone(), labels.clone()
+        opt = self.opt
+        # two eager steps on a side stream (allocator pools, kernel attributes, NCCL buffers) - and undone afterwards, so
+        # that capturing does not train on the first batch three times
+        snap = (opt.flat_p.clone(), opt.m.clone(), opt.v.clone(), opt.step_dev.clone(), opt.t)
+        cur = torch.cuda.current_stream(dev)
+        side = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)
+        with torch.cuda.stream(side):
+            for _ in range(2):
+                self._eager(sx, sy)
+        cur.wait_stream(side)
+        with torch.no_grad():
+            opt.flat_p.copy_(snap[0]); opt.m.copy_(snap[1]); opt.v.copy_(snap[2]); opt.step_dev.copy_(snap[3])
+        opt.t = snap[4]
+        opt.resync_shadow()
+        mixer.bump_generation()              # every derived-weight entry is stale: the capture re-derives (and records) them
+        torch.cuda.synchronize(dev)
+        g = torch.cuda.CUDAGraph()
+        timing, self.timing = self.timing, None
+        try:
+            with torch.cuda.graph(g):
+                sloss = self._eager(sx, sy)
+        finally:
+            self.timing = timing
+        opt.t = snap[4]                      # the captured opt.step() did its host bookkeeping, but no kernel has run yet
+        self._graph = (key, g, sx, sy, sloss)
+
+    def __call__(self, x: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
+        if not self.cuda_graph or self.timing is not None:
+            return self._eager(x, labels)
+        key = (tuple(x.shape), x.dtype, tuple(labels.shape), labels.dtype, x.device)
+        if self._graph is None or self._graph[0] != key:
+            self._capture(x, labels, key)
+        _, g, sx, sy, sloss = self._graph
+        sx.copy_(x, non_blocking=True)
+        sy.copy_(labels, non_blocking=True)
+        g.replay()
+        self.opt.after_device_step()         # host mirror of the update the replay just enqueued
+        return sloss

@@ -115,7 +115,11 @@ __device__ __forceinline__ void tc_epilogue_tile(const EpiParams& ep, const CUte
                 for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(silu_ftz(__uint_as_float(r[i])));
               } else {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(softplus_fast(__uint_as_float(r[i])));
+                for (int i = 0; i < 32; i += 2) {
+                  float v0, v1;
+                  upk2(softplus_fast2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]))), v0, v1);
+                  r[i] = __float_as_uint(v0); r[i + 1] = __float_as_uint(v1);
+                }
               }
             } else {                                // chunk straddles act_col0 (not 32-aligned): per element
 #pragma unroll

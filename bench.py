@@ -277,7 +277,7 @@ def train_leg(dev, world, dist, rank, steps=6, warmup=3, batch=32):
         for blk in model.layers:
             blk.mixer.A_log.add_(0.1 * torch.randn(blk.mixer.A_log.shape, generator=g).to(dev))
             blk.mixer.A_b_log.add_(0.1 * torch.randn(blk.mixer.A_b_log.shape, generator=g).to(dev))
-    ts = TrainStep(model, lr=1e-5, n_chunks=3)
+    ts = TrainStep(model, lr=1e-5, n_chunks=3, cuda_graph=os.environ.get("AUM_TRAIN_GRAPH", "1") == "1")
     x = (0.5 * torch.randn(batch, 1024, 128, generator=g)).to(dev)
     y = (torch.rand(batch, 309, generator=g) > 0.97).float().to(dev)
 
@@ -286,23 +286,30 @@ def train_leg(dev, world, dist, rank, steps=6, warmup=3, batch=32):
             dist.barrier()
         torch.cuda.synchronize()
 
+    # an eagerly launched pass first: counts the step's launches and all-reduce pieces and times the exposed part of the
+    # all-reduce with CUDA events (which a captured graph cannot hold); it doubles as extra warm-up
+    ts.timing = []
+    l0, a0 = _lib.launch_count(), ts.reducer.async_launches
+    for _ in range(2):
+        ts(x, y)
+    barrier()
+    launches = (_lib.launch_count() - l0) // 2
+    pieces = (ts.reducer.async_launches - a0) // 2
+    exposed_local = sum(a.elapsed_time(b) for a, b in ts.timing) / 2
+    ts.timing = None
     for _ in range(warmup):
         ts(x, y)
     barrier()
-    ts.timing = []
-    l0, a0 = _lib.launch_count(), ts.reducer.async_launches
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record()
     for _ in range(steps):
         loss = ts(x, y)
     e1.record()
     barrier()
-    t = torch.tensor([e0.elapsed_time(e1) / steps, sum(a.elapsed_time(b) for a, b in ts.timing) / steps], device=dev)
+    t = torch.tensor([e0.elapsed_time(e1) / steps, exposed_local], device=dev)
     if dist is not None:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms, exposed = t[0].item(), t[1].item()
-    launches = (_lib.launch_count() - l0) // steps
-    pieces = (ts.reducer.async_launches - a0) // steps
     # what the same all-reduce costs when nothing overlaps it (one piece, after backward)
     alone = None
     if dist is not None:
@@ -321,6 +328,8 @@ def train_leg(dev, world, dist, rank, steps=6, warmup=3, batch=32):
            "allreduce": {"bytes": ts.reducer.numel * 4, "pieces_per_step": pieces, "launched_from_backward_hooks": max(pieces - 1, 0),
                          "exposed_ms": exposed, "alone_ms": alone,
                          "note": "exposed = device time between the end of backward and the gradient buffer being final"},
+           "launch_mode": ("cuda-graph replay of the whole step (forward, loss, backward with the all-reduce pieces, Adam with a "
+                           "device-side step counter)") if ts.cuda_graph else "eager launches",
            "gpu_launches": launches, "loss": loss.item(), "peak_mem_gb": torch.cuda.max_memory_allocated(dev) / 2 ** 30}
     del ts, model
     torch.cuda.empty_cache()

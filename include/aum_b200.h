@@ -257,6 +257,15 @@ AUM_API int aum_assemble_tokens(const float* tok, const float* pos, const float*
 AUM_API int aum_adam_step(float* p, const float* g, float* m, float* v, int64_t n,
                   float lr, float beta1, float beta2, float eps, float weight_decay,
                   int step, float grad_scale, void* stream);
+/* The same update with the step number held in DEVICE memory: *step_dev is incremented first (a one-thread kernel), then
+ * used for the bias corrections, so that a CUDA graph of the whole training step (src/traintest.py:144-169: forward,
+ * loss, backward, all-reduce, optimizer.step()) can be replayed without host-side state.  Initialise *step_dev to the
+ * number of steps already taken (0 for a fresh optimiser).  p16 (optional, may be NULL): a 16-bit shadow of the updated
+ * parameters (p16_dtype AUM_F16 / AUM_BF16, n elements, 8-byte aligned) written in the same pass - the autocast copies
+ * of the weights the next forward needs (the reference's autocast casts them once per use, mamba_simple.py:185-189).  */
+AUM_API int aum_adam_step_dev(float* p, const float* g, float* m, float* v, int64_t n,
+                      float lr, float beta1, float beta2, float eps, float weight_decay,
+                      int* step_dev, float grad_scale, void* p16, int p16_dtype, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Layout adapters for the reference's channel-major (batch, C, L) tensors:

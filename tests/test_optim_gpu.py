@@ -58,3 +58,80 @@ def test_flat_adam_skips_a_step_with_non_finite_gradients():
     ps[1].grad[2, 3] = 1.0
     assert opt.step(grad_scale=0.5, skip_nonfinite=True) is True
     assert opt.t == 1 and not torch.equal(opt.flat_p, before)
+
+
+@pytest.mark.parametrize("sh", [torch.bfloat16, torch.float16])
+def test_adam_step_dev_counts_on_the_device_and_writes_the_16bit_shadow(sh):
+    """aum_adam_step_dev == aum_adam_step with the step number read from (and incremented in) device memory, plus the
+    parameters' 16-bit copy written in the same pass (what a captured training step replays)."""
+    from aum_b200 import ops
+    g = torch.Generator().manual_seed(5)
+    n = 4099                                                        # a 3-element tail
+    p0, gr = torch.randn(n, generator=g).to(DEV), torch.randn(n, generator=g).to(DEV)
+    pa, ma, va = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    pb, mb, vb = p0.clone(), torch.zeros(n, device=DEV), torch.zeros(n, device=DEV)
+    step_dev = torch.zeros((), device=DEV, dtype=torch.int32)
+    p16 = torch.zeros(n, device=DEV, dtype=sh)
+    for t in range(1, 5):
+        ops.adam_step(pa, gr, ma, va, lr=1e-2, betas=(0.95, 0.999), weight_decay=5e-7, step=t)
+        ops.adam_step_dev(pb, gr, mb, vb, step_dev, lr=1e-2, betas=(0.95, 0.999), weight_decay=5e-7, p16=p16)
+        assert int(step_dev) == t
+        torch.testing.assert_close(pb, pa, rtol=2e-6, atol=1e-7)
+        torch.testing.assert_close(vb, va, rtol=1e-6, atol=1e-12)
+        assert torch.equal(p16, pb.to(sh))
+    with pytest.raises(Exception):
+        ops.adam_step_dev(pb, gr, mb, vb, torch.zeros((), device=DEV), lr=1e-2)           # the counter must be int32
+
+
+def test_shadow_weights_follow_the_optimiser_and_yield_to_manual_edits():
+    """FlatAdam(shadow_dtype=...): mixer._w hands out the optimiser-maintained 16-bit copy (no cast kernel) while the
+    parameter is untouched since the last step, and falls back to a fresh cast once somebody edits it in place."""
+    from aum_b200 import dist as D, mixer
+    w = torch.nn.Parameter(torch.randn(16, 24, device=DEV))
+    red = D.FlatGradReducer([w])
+    opt = D.FlatAdam(red, lr=0.1, shadow_dtype=torch.bfloat16)
+    assert mixer._w(w, torch.bfloat16).data_ptr() == opt.flat16.data_ptr()
+    w.grad.fill_(1.0)
+    opt.step()
+    sh = mixer._w(w, torch.bfloat16)
+    assert sh.data_ptr() == opt.flat16.data_ptr() and torch.equal(sh, w.detach().to(torch.bfloat16))
+    assert mixer._w(w, torch.float16).dtype == torch.float16                                # other dtype: ordinary cast
+    with torch.no_grad():
+        w.mul_(2.0)                                                                          # behind the optimiser's back
+    fresh = mixer._w(w, torch.bfloat16)
+    assert fresh.data_ptr() != opt.flat16.data_ptr() and torch.equal(fresh, w.detach().to(torch.bfloat16))
+    opt.resync_shadow()
+    assert mixer._w(w, torch.bfloat16).data_ptr() == opt.flat16.data_ptr()
+    tw = mixer._wT(w, torch.bfloat16)
+    assert torch.equal(tw, w.detach().to(torch.bfloat16).t().contiguous())
+
+
+@pytest.mark.parametrize("act", [torch.float32, torch.bfloat16])
+def test_graphed_training_step_equals_the_eager_one(act):
+    """TrainStep(cuda_graph=True): the replayed CUDA graph of the whole step (zero, forward, loss, backward, fused Adam with
+    the device-side step counter) leaves the same parameters and losses as the eagerly launched step, step after step,
+    with a different batch every time; capturing does not consume a training step of its own."""
+    from aum_b200.audio_mamba import AudioMamba
+    from aum_b200.trainer import TrainStep
+    kw = dict(embed_dim=64, depth=2, num_classes=11, bimamba_type="v1", spectrogram_size=(32, 64), act_dtype=act)
+    torch.manual_seed(21)
+    ma = AudioMamba(**kw).to(DEV)
+    mb = AudioMamba(**kw).to(DEV)
+    mb.load_state_dict(ma.state_dict())
+    ta = TrainStep(ma, lr=1e-3)
+    tb = TrainStep(mb, lr=1e-3, cuda_graph=True)
+    g = torch.Generator().manual_seed(22)
+    for it in range(4):
+        x = torch.randn(3, 64, 32, generator=g).to(DEV)
+        y = (torch.rand(3, 11, generator=g) > 0.7).float().to(DEV)
+        la, lb = ta(x, y), tb(x, y)
+        assert tb.opt.t == ta.opt.t == it + 1 and int(tb.opt.step_dev) == it + 1
+        tol = dict(rtol=1e-5, atol=1e-6) if act == torch.float32 else dict(rtol=2e-2, atol=2e-3)
+        torch.testing.assert_close(lb.detach().float(), la.detach().float(), **tol)
+        # the atomics of the weight-gradient reductions make two runs differ in the last bits; Adam's first steps turn
+        # that into a few 1e-3 * lr, so compare the updates at that scale
+        torch.testing.assert_close(tb.opt.flat_p, ta.opt.flat_p, rtol=0, atol=(2e-4 if act == torch.float32 else 2e-3))
+    # an eager inference forward after replays sees the updated weights (derived-weight caches were invalidated)
+    with torch.no_grad():
+        oa, ob = ma(x), mb(x)
+    torch.testing.assert_close(ob, oa, rtol=2e-2, atol=2e-2)

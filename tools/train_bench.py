@@ -24,6 +24,8 @@ def main():
     ap.add_argument("--batch", type=int, default=32)
     ap.add_argument("--depth", type=int, default=24)
     ap.add_argument("--dtype", default="bf16")
+    ap.add_argument("--graph", type=int, default=0, help="1: replay a CUDA graph of the whole step")
+    ap.add_argument("--shadow", type=int, default=1, help="0: no 16-bit shadow weights from the Adam kernel")
     args = ap.parse_args()
     rank, local = int(os.environ.get("RANK", 0)), int(os.environ.get("LOCAL_RANK", 0))
     torch.cuda.set_device(local)
@@ -40,11 +42,13 @@ def main():
             blk.mixer.A_log.add_(0.1 * torch.randn(blk.mixer.A_log.shape, generator=g).to(dev))
             blk.mixer.A_b_log.add_(0.1 * torch.randn(blk.mixer.A_b_log.shape, generator=g).to(dev))
     from aum_b200.trainer import TrainStep
-    ts = TrainStep(model, lr=1e-5, n_chunks=3)
+    ts = TrainStep(model, lr=1e-5, n_chunks=3, cuda_graph=bool(args.graph), shadow16=bool(args.shadow))
     red = ts.reducer
     x = (0.5 * torch.randn(args.batch, 1024, 128, generator=g)).to(dev)
     y = (torch.rand(args.batch, 309, generator=g) > 0.97).float().to(dev)
-    ts.timing = ar_ms = []
+    ar_ms = []
+    if not args.graph:
+        ts.timing = ar_ms
 
     def step():
         return ts(x, y)
@@ -64,10 +68,10 @@ def main():
         torch.distributed.barrier()
     torch.cuda.synchronize()
     ms = D.max_over_ranks(t0.elapsed_time(t1) / args.steps, dev)
-    ar = sum(a.elapsed_time(b) for a, b in ar_ms) / len(ar_ms)
+    ar = sum(a.elapsed_time(b) for a, b in ar_ms) / len(ar_ms) if ar_ms else None
     if rank == 0:
         print(json.dumps({"metric": "clips/sec AuM-Base training step (fwd+bwd+allreduce+Adam)", "value": world * args.batch / (ms / 1e3),
-                          "unit": "clips/s", "n_gpus": world, "ms_per_step": ms, "allreduce_ms": ar, "dtype": args.dtype,
+                          "unit": "clips/s", "n_gpus": world, "ms_per_step": ms, "allreduce_ms": ar, "dtype": args.dtype, "graph": args.graph, "shadow": args.shadow,
                           "loss": float(loss), "peak_mem_gb": torch.cuda.max_memory_allocated() / 2**30,
                           "config": {"workload": f"AuM-Base Fo-Bi depth {args.depth}, 309 classes, batch {args.batch}/GPU, 128x1024 mel"}}), flush=True)
     if world > 1:
