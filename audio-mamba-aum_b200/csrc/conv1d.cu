@@ -7,6 +7,8 @@
 // TL+3 input rows of a thread are independent loads issued up front (one DRAM latency per thread), kept PACKED
 // in registers (19 regs) so the kernel runs at full occupancy, and the 3-row halo is served by L1/L2.
 // Algorithmic bytes per (token, channel): read s + write s (s = itemsize).
+#include <stdlib.h>
+
 #include "scan_common.cuh"   // packed fp32x2 helpers
 
 namespace aum {
@@ -413,6 +415,182 @@ conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
   }
 }
 
+
+// ---- streaming form (the production path) --------------------------------------------------------------------
+// The tile kernel above fetches everything a warp's 8-token tile touches up front (14 x rows + 11 rows of each gradient
+// term) and then computes; at AuM-Base size with the three gradient terms of a Fo-Bi block it ran at 26 % of the HBM
+// roofline: 80 registers = 24 warps per SM, each of them alternating between one burst of loads and a long dependent
+// compute phase (long-scoreboard stall 9.1 per issue, profiles/r2_ncu_conv1d_bwd3_summary.txt), with 11/8 of the
+// gradient bytes requested.  Here a thread (one channel pair) WALKS a segment of ~32-64 positions: per position one
+// row of x and of each gradient term is loaded (the loads of the next positions are in flight while this one is
+// computed), the 4-tap windows of x and dc slide through registers, dx[p-3] leaves as soon as dc[p] exists, and the
+// weight / bias gradients accumulate in registers over the whole segment (8 warps = 8 consecutive segments per block,
+// reduced in shared memory, one atomic per value and block).  Packed fp32x2 math on the channel pair.
+// Needs W <= 4, D even and 8-byte-aligned rows (checked by the launcher; anything else takes the tile kernel).
+__device__ __forceinline__ float2 ldg_f2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+
+// UNR / MINB: positions per loop trip / resident blocks per SM the register budget is set for: (2, 4) = 64 registers,
+// 32 warps per SM; (4, 3) = 80 registers, 24 warps with twice the loads in flight per warp (AUM_CONV_BWD_VARIANT=1).
+template <typename T, int NT, int UNR, int MINB>
+__global__ void __launch_bounds__(256, MINB)
+conv1d_bwd_stream_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ bias,
+                         const float* __restrict__ g1, const float* __restrict__ g2, const float* __restrict__ g3, int64_t ldd,
+                         T* __restrict__ dx, int64_t ld_dx, float* __restrict__ dw, float* __restrict__ dbias,
+                         int L, int D, int W, int silu, int reverse, int n_cgrp, int n_tgrp, int seg) {
+  __shared__ float red[8][10][32];
+  const int lane = threadIdx.x & 31, wrp = threadIdx.x >> 5;
+  const int cg = blockIdx.x % n_cgrp;
+  const int tg = (blockIdx.x / n_cgrp) % n_tgrp;
+  const int b = blockIdx.x / (n_cgrp * n_tgrp);
+  const int c0 = (cg * 32 + lane) * 2;
+  const bool ok = c0 < D;
+  const int p0 = (tg * 8 + wrp) * seg;
+  const int p1 = min(p0 + seg, L);
+
+  f32x2 wk[CONV_MAXW];
+  f32x2 bs = pk2(0.f, 0.f);
+  if (ok) {
+#pragma unroll
+    for (int j = 0; j < CONV_MAXW; ++j) {
+      const int k = j - (CONV_MAXW - W);
+      wk[j] = k >= 0 ? pk2(__ldg(w + (int64_t)c0 * W + k), __ldg(w + (int64_t)(c0 + 1) * W + k)) : pk2(0.f, 0.f);
+    }
+    if (bias != nullptr) bs = pk2(__ldg(bias + c0), __ldg(bias + c0 + 1));
+  }
+  f32x2 acc[5];
+#pragma unroll
+  for (int i = 0; i < 5; ++i) acc[i] = pk2(0.f, 0.f);
+
+  if (ok && p0 < L) {
+    // walk position p <-> token (reverse ? L-1-p : p); one step along the walk = sgn rows.  Element offsets are 32-bit
+    // (the launcher checks that every buffer spans < 2^31 elements): half the registers of 64-bit pointers + strides.
+    const int sgn = reverse ? -1 : 1;
+    const int r0 = b * L + (reverse ? (L - 1 - p0) : p0);
+    const T* const xb = x + c0;
+    const float* const q1 = g1 + c0;
+    const float* const q2 = NT >= 2 ? g2 + c0 : nullptr;
+    const float* const q3 = NT >= 3 ? g3 + c0 : nullptr;
+    T* const ob = dx + c0;
+    int ox = r0 * (int)ldx, og = r0 * (int)ldd, oo = r0 * (int)ld_dx;     // rows of x[p], g[p], dx[next row to emit]
+    const int sx = sgn * (int)ldx, sg = sgn * (int)ldd, so = sgn * (int)ld_dx;
+    auto ldx2 = [&](const T* r) { Pair<T> t; t.load(r); const float2 f = t.f(); return pk2(f.x, f.y); };
+    const T* const xp = xb + ox;
+    // x[p0-3 .. p0-1] (zeros before the sequence start)
+    f32x2 xm3 = p0 >= 3 ? ldx2(xp - 3 * sx) : pk2(0.f, 0.f);
+    f32x2 xm2 = p0 >= 2 ? ldx2(xp - 2 * sx) : pk2(0.f, 0.f);
+    f32x2 xm1 = p0 >= 1 ? ldx2(xp - sx) : pk2(0.f, 0.f);
+    f32x2 d1 = pk2(0.f, 0.f), d2 = d1, d3 = d1;    // dc[p-1], dc[p-2], dc[p-3]
+    const f32x2 one = pk2(1.f, 1.f), mone = pk2(-1.f, -1.f);
+
+    // one position with data (p < L).  ACC: p belongs to this segment (its dc feeds dw / dbias); EMIT: dx[p-3] is ours
+    auto step = [&](const bool accum, const bool emit) {
+      const f32x2 xn = ldx2(xb + ox);
+      float2 g = ldg_f2(q1 + og);
+      if (NT >= 2) { const float2 t = ldg_f2(q2 + og); g.x += t.x; g.y += t.y; }
+      if (NT >= 3) { const float2 t = ldg_f2(q3 + og); g.x += t.x; g.y += t.y; }
+      ox += sx; og += sg;
+      f32x2 dcn = pk2(g.x, g.y);
+      if (silu) {
+        const f32x2 c = fma2(wk[3], xn, fma2(wk[2], xm1, fma2(wk[1], xm2, fma2(wk[0], xm3, bs))));
+        float ca, cb;
+        upk2(c, ca, cb);
+        float sa, sb;
+        const float ea = ex2_approx(-1.4426950408889634f * ca), eb = ex2_approx(-1.4426950408889634f * cb);
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sa) : "f"(1.f + ea));
+        asm("rcp.approx.ftz.f32 %0, %1;" : "=f"(sb) : "f"(1.f + eb));
+        const f32x2 sg2 = pk2(sa, sb);
+        // silu'(c) = s (1 + c (1 - s))
+        dcn = mul2(dcn, mul2(sg2, fma2(c, fma2(sg2, mone, one), one)));
+      }
+      if (accum) {
+        acc[0] = fma2(dcn, xm3, acc[0]); acc[1] = fma2(dcn, xm2, acc[1]);
+        acc[2] = fma2(dcn, xm1, acc[2]); acc[3] = fma2(dcn, xn, acc[3]);
+        acc[4] = add2(acc[4], dcn);
+      }
+      if (emit) {                                   // dx[p-3] = w0 dc[p] + w1 dc[p-1] + w2 dc[p-2] + w3 dc[p-3]
+        const f32x2 o = fma2(wk[3], d3, fma2(wk[2], d2, fma2(wk[1], d1, mul2(wk[0], dcn))));
+        float oa, ob_;
+        upk2(o, oa, ob_);
+        Pair<T>::store(ob + oo, oa, ob_);
+        oo += so;
+      }
+      xm3 = xm2; xm2 = xm1; xm1 = xn;
+      d3 = d2; d2 = d1; d1 = dcn;
+    };
+
+    // a position past the sequence end: dc = 0 (no gradient arrives there); EMIT as above
+    auto zstep = [&](const bool emit) {
+      if (emit) {
+        const f32x2 o = fma2(wk[3], d3, fma2(wk[2], d2, mul2(wk[1], d1)));
+        float oa, ob_;
+        upk2(o, oa, ob_);
+        Pair<T>::store(ob + oo, oa, ob_);
+        oo += so;
+      }
+      d3 = d2; d2 = d1; d1 = pk2(0.f, 0.f);
+    };
+    // every segment takes (p1 - p0) + 3 steps: the first three emit nothing (dx[p0] needs dc up to p0 + 3), the last
+    // three are the halo - dc of the NEXT segment's first positions (no dw / dbias from them) or zeros past the end
+    int p = p0;
+#pragma unroll 1
+    for (int i = 0; i < 3; ++i, ++p) {
+      if (p < L) step(p < p1, false); else zstep(false);
+    }
+#pragma unroll UNR
+    for (; p < p1; ++p) step(true, true);
+    const int pend = p1 + 3;
+#pragma unroll 1
+    for (; p < pend; ++p) {
+      if (p < L) step(false, true); else zstep(true);
+    }
+  }
+#pragma unroll
+  for (int i = 0; i < 5; ++i) {
+    float lo, hi;
+    upk2(acc[i], lo, hi);
+    red[wrp][i][lane] = lo; red[wrp][5 + i][lane] = hi;
+  }
+  __syncthreads();
+  if (wrp == 0 && ok) {
+#pragma unroll
+    for (int i = 0; i < 10; ++i) {
+      float sum = 0.f;
+#pragma unroll
+      for (int k = 0; k < 8; ++k) sum += red[k][i][lane];
+      const int v = i / 5, j = i % 5;
+      const int c = c0 + v;
+      if (j < 4) { const int k = j - (CONV_MAXW - W); if (k >= 0) atomicAdd(dw + (int64_t)c * W + k, sum); }
+      else if (dbias != nullptr) atomicAdd(dbias + c, sum);
+    }
+  }
+}
+
+template <typename T, int UNR, int MINB>
+static void launch_conv_bwd_stream_v(const void* x, int64_t ldx, const float* w, const float* bias, const float* g1, const float* g2,
+                                     const float* g3, int64_t ldd, void* dx, int64_t ld_dx, float* dw, float* dbias,
+                                     int batch, int L, int D, int W, int silu, int reverse, cudaStream_t st) {
+  // 8 warps = 8 consecutive segments per block; segments of 32-64 positions (L = 513 -> 2 token groups of 8 x 33)
+  const int n_tgrp = ceil_div(L, 512);
+  const int seg = ceil_div(L, 8 * n_tgrp);
+  const int n_cgrp = ceil_div(D, 64);
+  const unsigned blocks = (unsigned)((int64_t)batch * n_cgrp * n_tgrp);
+  const T* xx = reinterpret_cast<const T*>(x);
+  T* dd = reinterpret_cast<T*>(dx);
+  if (g3 != nullptr)      conv1d_bwd_stream_kernel<T, 3, UNR, MINB><<<blocks, 256, 0, st>>>(xx, ldx, w, bias, g1, g2, g3, ldd, dd, ld_dx, dw, dbias, L, D, W, silu, reverse, n_cgrp, n_tgrp, seg);
+  else if (g2 != nullptr) conv1d_bwd_stream_kernel<T, 2, UNR, MINB><<<blocks, 256, 0, st>>>(xx, ldx, w, bias, g1, g2, g3, ldd, dd, ld_dx, dw, dbias, L, D, W, silu, reverse, n_cgrp, n_tgrp, seg);
+  else                    conv1d_bwd_stream_kernel<T, 1, UNR, MINB><<<blocks, 256, 0, st>>>(xx, ldx, w, bias, g1, g2, g3, ldd, dd, ld_dx, dw, dbias, L, D, W, silu, reverse, n_cgrp, n_tgrp, seg);
+}
+
+template <typename T>
+static void launch_conv_bwd_stream(const void* x, int64_t ldx, const float* w, const float* bias, const float* g1, const float* g2,
+                                   const float* g3, int64_t ldd, void* dx, int64_t ld_dx, float* dw, float* dbias,
+                                   int batch, int L, int D, int W, int silu, int reverse, cudaStream_t st) {
+  static int variant = -1;
+  if (variant < 0) { const char* e = getenv("AUM_CONV_BWD_VARIANT"); variant = (e && atoi(e) == 1) ? 1 : 0; }
+  if (variant == 1) launch_conv_bwd_stream_v<T, 4, 3>(x, ldx, w, bias, g1, g2, g3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st);
+  else              launch_conv_bwd_stream_v<T, 2, 4>(x, ldx, w, bias, g1, g2, g3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st);
+}
+
 }  // namespace aum
 
 extern "C" int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w, const float* bias,
@@ -430,6 +608,27 @@ extern "C" int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w,
   const int64_t blocks = (int64_t)batch * n_cgrp * n_tgrp;
   AUM_REQUIRE(blocks < (1ll << 31), "aum_causal_conv1d_bwd: grid too large");
   cudaStream_t st = (cudaStream_t)stream;
+  {
+    // streaming kernel: channel pairs as 8-byte (fp32) / 4-byte (16-bit) vectors; a second gradient term must come with
+    // the third slot free or filled, never third-only
+    const int esz = dtype_size(dtype);
+    auto al = [](const void* p, int a) { return p == nullptr || (reinterpret_cast<uintptr_t>(p) % a) == 0; };
+    static int force_tile = -1;
+    if (force_tile < 0) force_tile = getenv("AUM_CONV_BWD_TILE") != nullptr ? 1 : 0;
+    const bool stream_ok = !force_tile && D % 2 == 0 && ldx % 2 == 0 && ldd % 2 == 0 && ld_dx % 2 == 0 && al(x, 2 * esz) && al(dx, 2 * esz) &&
+                           al(dout, 8) && al(dout2, 8) && al(dout3, 8) && !(dout2 == nullptr && dout3 != nullptr) &&
+                           (int64_t)batch * ceil_div(D, 64) * ceil_div(L, 512) < (1ll << 31) &&
+                           ((int64_t)batch * L + 4) * (ldx > ldd ? (ldx > ld_dx ? ldx : ld_dx) : (ldd > ld_dx ? ldd : ld_dx)) < (1ll << 31);
+    if (stream_ok) {
+      switch (dtype) {
+        case AUM_F32:  launch_conv_bwd_stream<float>(x, ldx, w, bias, dout, dout2, dout3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st); break;
+        case AUM_F16:  launch_conv_bwd_stream<__half>(x, ldx, w, bias, dout, dout2, dout3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st); break;
+        case AUM_BF16: launch_conv_bwd_stream<__nv_bfloat16>(x, ldx, w, bias, dout, dout2, dout3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st); break;
+        default: set_error("aum_causal_conv1d_bwd: bad dtype %d", dtype); return 1;
+      }
+      return check_launch("aum_causal_conv1d_bwd");
+    }
+  }
   switch (dtype) {
     case AUM_F32:  conv1d_bwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, ldx, w, bias, dout, dout2, dout3, ldd, (float*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
     case AUM_F16:  conv1d_bwd_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, ldx, w, bias, dout, dout2, dout3, ldd, (__half*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;

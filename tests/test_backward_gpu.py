@@ -46,6 +46,64 @@ def test_causal_conv1d_bwd(reverse, B, Lq, D, W):
     _close(db, b.grad, 1e-4, 1e-5, "dbias")
 
 
+@pytest.mark.parametrize("reverse", [False, True])
+@pytest.mark.parametrize("B,Lq,D,W,terms", [(2, 513, 128, 4, 3), (1, 1, 64, 4, 1), (3, 2, 66, 4, 2), (2, 70, 34, 2, 3),
+                                            (1, 1030, 64, 4, 2), (2, 9, 7, 4, 3)])
+@pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16])
+def test_causal_conv1d_bwd_streaming_kernel_multi_term(reverse, B, Lq, D, W, terms, dt):
+    """The production conv backward (segment-walking kernel): x as a strided view of a wider buffer (the x half of xz),
+    1-3 gradient terms summed on the fly (scan du of both directions + the x_proj term), segment boundaries inside the
+    sequence (L = 513 / 1030), sequences shorter than the 3-position halo, an odd channel count (tile-kernel fallback);
+    against autograd through the oracle on the same (rounded) inputs."""
+    from aum_b200 import ops
+    g = gen(3)
+    xw = rnd((B, Lq, 2 * D + 2), g).to(dt)
+    x = xw[..., :D].float().clone().requires_grad_()
+    w = rnd((D, W), g, 0.5).requires_grad_()
+    b = rnd((D,), g, 0.5).requires_grad_()
+    Gs = [rnd((B, Lq, D), g) for _ in range(terms)]
+    xc = x.permute(0, 2, 1)
+    y = O.causal_conv1d_oracle(xc.flip(-1) if reverse else xc, w, b, True)
+    y = (y.flip(-1) if reverse else y).permute(0, 2, 1)
+    (y * sum(Gs)).sum().backward()
+    xd = xw.to(DEV)[..., :D]
+    dx = torch.empty((B, Lq, D), device=DEV, dtype=dt)
+    dw = torch.zeros((D, W), device=DEV)
+    db = torch.zeros((D,), device=DEV)
+    Gd = [G_.to(DEV) for G_ in Gs] + [None, None]
+    ops.causal_conv1d_bwd(xd, w.detach().to(DEV), b.detach().to(DEV), Gd[0], dx, dw, db, silu=True, reverse=reverse,
+                          dout2=Gd[1], dout3=Gd[2])
+    tol = (1e-4, 1e-5) if dt == torch.float32 else (2e-2, 1e-2)
+    _close(dx, x.grad, *tol, "dx")
+    _close(dw, w.grad, 2e-4, 2e-5, "dw")
+    _close(db, b.grad, 2e-4, 2e-5, "dbias")
+
+
+def test_causal_conv1d_bwd_tile_kernel_still_agrees(monkeypatch):
+    """AUM_CONV_BWD_TILE=1 (read once per process) selects the tile kernel: run it in a child process against the
+    streaming kernel's result."""
+    import os, subprocess, sys, textwrap
+    code = textwrap.dedent("""
+        import sys, torch
+        sys.path.insert(0, %r)
+        from aum_b200 import ops
+        g = torch.Generator().manual_seed(4)
+        x = torch.randn(2, 100, 64, generator=g).cuda(); w = torch.randn(64, 4, generator=g).cuda(); b = torch.randn(64, generator=g).cuda()
+        G = torch.randn(2, 100, 64, generator=g).cuda()
+        dx = torch.empty_like(x); dw = torch.zeros(64, 4, device="cuda"); db = torch.zeros(64, device="cuda")
+        ops.causal_conv1d_bwd(x, w, b, G, dx, dw, db, silu=True)
+        torch.save({"dx": dx.cpu(), "dw": dw.cpu(), "db": db.cpu()}, sys.argv[1])
+    """) % os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "audio-mamba-aum_b200")
+    import tempfile
+    outs = []
+    for env_extra in ({}, {"AUM_CONV_BWD_TILE": "1"}):
+        with tempfile.NamedTemporaryFile(suffix=".pt") as f:
+            subprocess.run([sys.executable, "-c", code, f.name], check=True, env=dict(os.environ, **env_extra))
+            outs.append(torch.load(f.name))
+    for k in ("dx", "dw", "db"):
+        torch.testing.assert_close(outs[0][k], outs[1][k], rtol=1e-4, atol=1e-4)
+
+
 @pytest.mark.parametrize("dt", [torch.float32, torch.float16, torch.bfloat16])
 @pytest.mark.parametrize("rows,dim,prenorm,has_res", [(130, 768, True, True), (37, 96, True, False), (20, 384, False, True),
                                                       (9, 100, True, True)])

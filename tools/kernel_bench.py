@@ -152,6 +152,10 @@ def main():
         dw, db_ = torch.zeros((Di, 4), **f32), torch.zeros(Di, **f32)
         report("conv1d_bwd", timeit(lambda: ops.causal_conv1d_bwd(x[..., :Di], w, b_, g32, dx, dw, db_), flush=flush),
                bytes_=M * Di * (2 * s + 4))
+        g2_, g3_ = rn(B, Lq, Di, dtype=torch.float32), rn(B, Lq, Di, dtype=torch.float32)
+        report("conv1d_bwd(3 gradient terms, as a Fo-Bi block calls it)",
+               timeit(lambda: ops.causal_conv1d_bwd(x[..., :Di], w, b_, g32, dx, dw, db_, dout2=g2_, dout3=g3_), flush=flush),
+               bytes_=M * Di * (2 * s + 12))
     if dt != torch.float32 and (not only or "gemm" in only):
         shapes = {"in_proj": (M, 2 * Di, Dm), "out_proj": (M, Dm, Di), "x_proj": (M, R + 2 * N, Di), "dt_proj": (M, Di, R)}
         for name, (m_, n_, k_) in shapes.items():
