@@ -93,7 +93,15 @@ class TrainStep:
             return self._eager(x, labels)
         key = (tuple(x.shape), x.dtype, tuple(labels.shape), labels.dtype, x.device)
         if self._graph is None or self._graph[0] != key:
-            self._capture(x, labels, key)
+            try:
+                self._capture(x, labels, key)
+            except Exception as e:      # e.g. a collective backend that cannot be captured: keep training, eagerly
+                import warnings
+                warnings.warn(f"TrainStep: CUDA-graph capture of the training step failed ({type(e).__name__}: {e}); "
+                              "falling back to eager launches")
+                self.cuda_graph, self._graph = False, None
+                torch.cuda.synchronize(x.device)
+                return self._eager(x, labels)
         _, g, sx, sy, sloss = self._graph
         sx.copy_(x, non_blocking=True)
         sy.copy_(labels, non_blocking=True)

@@ -525,10 +525,13 @@ def main():
     s_act = 2
     # ALGORITHMIC bytes of one fused bidirectional scan launch, SURVEY.md section 8(d):
     #   s*(4*B*D*L + 2*B*N*L) + 4*(2*D*N + 2*D)   (u, delta, z in, out written, B and C rows; A, A_b, D, delta_bias)
-    # with every activation counted at the activation size s = 2.  This build keeps delta and the packed B|C rows in
-    # fp32 in HBM; the bytes it would need with those counted at 4 bytes are reported next to it, not used for `frac`.
+    # with every activation counted at the activation size s = 2.  The inference path stores delta in the activation dtype
+    # (AUM_DELTA_16BIT, default on), so u, delta, z and out move exactly these bytes; the packed B|C rows stay fp32 (2 x the
+    # formula's 2BNL term, 0.5 % of the launch): `bytes_this_build_moves` counts them (and delta, when kept fp32) as stored.
     alg_bytes = s_act * (4 * M * Di + 2 * M * Nst) + 4 * (2 * Di * Nst + 2 * Di)
-    alg_bytes_fp32_delta = M * Di * (3 * s_act + 4) + M * 2 * Nst * 4 + 4 * (2 * Di * Nst + 2 * Di)
+    from aum_b200 import mixer as _mixer
+    delta_sz = s_act if _mixer._DELTA_16BIT else 4
+    build_bytes = M * Di * (3 * s_act + delta_sz) + M * 2 * Nst * 4 + 4 * (2 * Di * Nst + 2 * Di)
     roof = None
     if scan_ms:
         avg = sum(scan_ms) / len(scan_ms)
@@ -539,7 +542,7 @@ def main():
                 "peak": peak, "unit": "GB/s", "frac": ach / peak, "traffic": traffic, "traffic_source": traffic_src,
                 "peak_source": peak_src, "avg_launch_ms": avg, "launches_timed": len(scan_ms),
                 "algorithmic_bytes_per_launch": alg_bytes, "algorithmic_bytes_formula": "SURVEY 8(d): s*(4BDL+2BNL)+4*(2DN+2D), s=2",
-                "achieved_with_fp32_delta_bytes": alg_bytes_fp32_delta / (avg * 1e-3) / 1e9,
+                "bytes_this_build_moves": build_bytes, "delta_dtype": "activation dtype (16-bit)" if delta_sz == 2 else "fp32",
                 "share_of_step": (scan_all_ms / all_ms) if all_ms > 0 else None, "sequences_per_launch": B // mb,
                 # the ceiling that actually binds this kernel: one MUFU.EX2 per (token, channel, state, direction);
                 # peak = 15.8 results/clk/SM measured (profiles/r1_microbench_pipe_rates.txt) x 148 SMs x max SM clock

@@ -10,6 +10,8 @@ g = torch.Generator(device=dev).manual_seed(0)
 rn = lambda *sh, dtype=dt: torch.randn(*sh, device=dev, generator=g).to(dtype)
 u, z = rn(B, Lq, Di), rn(B, Lq, Di)
 delta = torch.nn.functional.softplus(rn(B, Lq, Di, dtype=torch.float32) - 2.0)
+if os.environ.get("DELTA16", "1") == "1":      # as the inference path stores it (mixer._DELTA_16BIT)
+    delta = delta.to(dt)
 bc = rn(B, Lq, 2 * N, dtype=torch.float32)
 A = -torch.exp(torch.log(torch.arange(1, N + 1, device=dev, dtype=torch.float32)).repeat(Di, 1) + 0.1 * rn(Di, N, dtype=torch.float32))
 A_b = -torch.exp(torch.log(torch.arange(1, N + 1, device=dev, dtype=torch.float32)).repeat(Di, 1) + 0.1 * rn(Di, N, dtype=torch.float32))
