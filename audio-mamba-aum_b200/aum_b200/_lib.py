@@ -64,6 +64,7 @@ class ScanBwdDir(C.Structure):
         ("dbc_ws", C.c_void_p),
         ("ckpt", C.c_void_p),
         ("ckpt_valid", C.c_int),
+        ("dgrad_dtype", C.c_int),
     ]
 
 
@@ -93,10 +94,10 @@ SIGNATURES = {
                                          C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64,
                                          C.c_void_p, C.c_int64, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int,
                                          C.c_float, C.c_int, C.c_void_p]),
-    "aum_sum_cast_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
+    "aum_sum_cast_colsum": (C.c_int, [C.c_void_p, C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int, C.c_void_p,
                                       C.c_int, C.c_int, C.c_void_p]),
     "aum_causal_conv1d_bwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64,
-                                        C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
+                                        C.c_int, C.c_void_p, C.c_int64, C.c_void_p, C.c_void_p,
                                         C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p]),
     "aum_add_rmsnorm_fwd": (C.c_int, [C.c_void_p, C.c_int64, C.c_int, C.c_void_p, C.c_int64, C.c_int,
                                       C.c_void_p, C.c_void_p, C.c_void_p, C.c_int64, C.c_int,

@@ -19,6 +19,7 @@ temporary, no cast, no AccumulateGrad pass.
 """
 from __future__ import annotations
 
+import os
 from collections import namedtuple
 
 import torch
@@ -27,6 +28,7 @@ from . import _lib as L
 from . import mixer, ops
 
 F32 = torch.float32
+_GRAD_16BIT = os.environ.get("AUM_GRAD_16BIT", "1") == "1"
 
 
 def _t(w: torch.Tensor, dtype: torch.dtype) -> torch.Tensor:
@@ -214,10 +216,16 @@ class InnerFn(torch.autograd.Function):
         dz = dxz[..., Di:]
         out_z = torch.empty((B, Lq, Di), device=dev, dtype=act)
         A_f = _A(A, cfg)
+        # du / ddelta of the scan (and the x_proj term of d(conv_out)) in the activation dtype when that is 16-bit - what the
+        # reference's kernels hand back under autocast (:541-561, :590); the sums over the terms are still formed in fp32
+        # (conv backward, sum_cast_colsum).  Needs the specialised backward-scan kernel (AUM_GRAD_16BIT=0: fp32 everywhere).
+        g16 = (act != F32 and Di % 128 == 0 and _GRAD_16BIT and "AUM_SCAN_BWD_GENERIC" not in os.environ
+               and "AUM_SCAN_BWD_NOSPEC" not in os.environ)
+        gdt = dict(device=dev, dtype=act if g16 else F32)
         dA = torch.zeros((Di, N), **f32)
         dD_buf, dD_direct = _grad_buffer(D, (1, Di)) if D is not None else (None, False)
-        du = torch.empty((B, Lq, Di), **f32)
-        ddelta = torch.empty((B, Lq, Di), **f32)
+        du = torch.empty((B, Lq, Di), **gdt)
+        ddelta = torch.empty((B, Lq, Di), **gdt)
         dbc = torch.zeros((B, Lq, 2 * N), **f32)
         Dv = mixer._f32(D) if D is not None else None
         d_f = ops.ScanBwdDirection(u, delta, A_f, bc, Dv, du, ddelta, dA, dD_buf.view(Di) if dD_buf is not None else None,
@@ -230,8 +238,8 @@ class InnerFn(torch.autograd.Function):
             # consumed anyway: in the conv backward's input and in the cast + column-sum pass of the dt_proj chain
             A_r = _A(A_b, cfg)
             dA_b = torch.zeros((Di, N), **f32)
-            du_b = torch.empty((B, Lq, Di), **f32)
-            ddelta_b = torch.empty((B, Lq, Di), **f32)
+            du_b = torch.empty((B, Lq, Di), **gdt)
+            ddelta_b = torch.empty((B, Lq, Di), **gdt)
             d_b = ops.ScanBwdDirection(u, delta, A_r, bc, Dv, du_b, ddelta_b, dA_b,
                                        dD_buf.view(Di) if dD_buf is not None else None, dbc, ck_b, ckpt_valid=True)
         elif cfg.mode == "v2":
@@ -239,8 +247,8 @@ class InnerFn(torch.autograd.Function):
             A_r = _A(A_b, cfg)
             dA_b = torch.zeros((Di, N), **f32)
             dDb_buf, dDb_direct = _grad_buffer(D_b, (1, Di)) if D_b is not None else (None, False)
-            du_b = torch.empty((B, Lq, Di), **f32)
-            ddelta_b = torch.empty((B, Lq, Di), **f32)
+            du_b = torch.empty((B, Lq, Di), **gdt)
+            ddelta_b = torch.empty((B, Lq, Di), **gdt)
             dbc_b = torch.zeros((B, Lq, 2 * N), **f32)
             d_b = ops.ScanBwdDirection(ub, deltab, A_r, bc_b, mixer._f32(D_b) if D_b is not None else None, du_b, ddelta_b,
                                        dA_b, dDb_buf.view(Di) if dDb_buf is not None else None, dbc_b, ck_b, ckpt_valid=True)
@@ -288,7 +296,7 @@ class InnerFn(torch.autograd.Function):
             else:
                 wxT = mixer._cache.get(xw_, f"wT_pad:{act}:{wdb}",
                                        lambda p: torch.nn.functional.pad(p.t().to(act), (0, wdb - p.shape[0])).contiguous())
-            du_x = ops.gemm_tn(dxdbl, wxT, out_dtype=F32)                                      # (M, Di) fp32
+            du_x = ops.gemm_tn(dxdbl, wxT, out_dtype=du_.dtype)                                # (M, Di), the scan du's dtype
             Wc = cw_.shape[-1]
             dw_buf, dw_direct = _grad_buffer(cw_, (Di, Wc))
             db_buf, db_direct = _grad_buffer(cb_, (1, Di)) if cb_ is not None else (None, False)

@@ -270,16 +270,16 @@ def causal_conv1d_bwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Ten
                       reverse: bool = False, dout2: Optional[torch.Tensor] = None,
                       dout3: Optional[torch.Tensor] = None) -> None:
     """Backward of causal_conv1d.  x, dx: (B, L, D) token-major (dtype); dout (+ dout2 + dout3, summed on the fly):
-    (B, L, D) fp32; dw (D, W) / dbias (D) fp32 are accumulated into."""
+    (B, L, D), all fp32 or all of x's 16-bit dtype; dw (D, W) / dbias (D) fp32 are accumulated into."""
     L.require_cuda(x, w, dout, dx, dw)
     B, Lq, D = x.shape
-    if dout.dtype != torch.float32 or dw.dtype != torch.float32 or dx.dtype != x.dtype:
-        raise L.AumError("causal_conv1d_bwd: dout/dw must be fp32 and dx must match x")
+    if dout.dtype not in (torch.float32, x.dtype) or dw.dtype != torch.float32 or dx.dtype != x.dtype:
+        raise L.AumError("causal_conv1d_bwd: dout must be fp32 or match x, dw must be fp32 and dx must match x")
     for extra in (dout2, dout3):
-        if extra is not None and (extra.dtype != torch.float32 or _as_rows(extra)[2] != _as_rows(dout)[2]):
-            raise L.AumError("causal_conv1d_bwd: dout2 / dout3 must be fp32 with dout's pitch")
+        if extra is not None and (extra.dtype != dout.dtype or _as_rows(extra)[2] != _as_rows(dout)[2]):
+            raise L.AumError("causal_conv1d_bwd: dout2 / dout3 must have dout's dtype and pitch")
     rc = L.lib().aum_causal_conv1d_bwd(L.ptr(x), _as_rows(x)[2], L.ptr(w), L.ptr(bias), L.ptr(dout), L.ptr(dout2), L.ptr(dout3),
-                                       _as_rows(dout)[2],
+                                       _as_rows(dout)[2], L.dt(dout.dtype),
                                        L.ptr(dx), _as_rows(dx)[2], L.ptr(dw), L.ptr(dbias), B, Lq, D, w.shape[1],
                                        L.dt(x.dtype), int(silu), int(reverse), L.stream())
     L.check(rc, "aum_causal_conv1d_bwd")
@@ -287,25 +287,29 @@ def causal_conv1d_bwd(x: torch.Tensor, w: torch.Tensor, bias: Optional[torch.Ten
 
 def sum_cast_colsum(a: torch.Tensor, b: Optional[torch.Tensor], out_dtype: torch.dtype,
                     colsum: Optional[torch.Tensor] = None) -> torch.Tensor:
-    """out = (a + b).to(out_dtype) and colsum += (a + b).sum(0) in one pass (aum_sum_cast_colsum).  a, b: fp32 (rows, cols)."""
+    """out = (a + b).to(out_dtype) and colsum += (a + b).sum(0) in one pass (aum_sum_cast_colsum).  a, b: (rows, cols) of
+    one dtype (fp32 or 16-bit); the sum is formed in fp32."""
     L.require_cuda(a, b, colsum)
     rows, cols, ld = _as_rows(a)
-    if a.dtype != torch.float32 or (b is not None and (b.dtype != torch.float32 or _as_rows(b) != (rows, cols, ld))):
-        raise L.AumError("sum_cast_colsum: a and b must be fp32 with one shape and pitch")
+    if b is not None and (b.dtype != a.dtype or _as_rows(b) != (rows, cols, ld)):
+        raise L.AumError("sum_cast_colsum: a and b must share dtype, shape and pitch")
     if colsum is not None and (colsum.dtype != torch.float32 or colsum.numel() != cols or not colsum.is_contiguous()):
         raise L.AumError("sum_cast_colsum: colsum must be a contiguous fp32 vector of `cols` elements")
-    if cols % 4 != 0 or ld % 4 != 0 or a.data_ptr() % 16 != 0 or (b is not None and b.data_ptr() % 16 != 0):
+    al = 4 * a.element_size()
+    if cols % 4 != 0 or ld % 4 != 0 or a.data_ptr() % al != 0 or (b is not None and b.data_ptr() % al != 0):
         raise L.AumError("sum_cast_colsum: rows must be addressable as 4-element vectors (cols % 4 == 0, 16-byte aligned)")
     out = torch.empty((rows, cols), device=a.device, dtype=out_dtype)
-    rc = L.lib().aum_sum_cast_colsum(L.ptr(a), L.ptr(b), ld, L.ptr(out), cols, L.dt(out_dtype), L.ptr(colsum), rows, cols, L.stream())
+    rc = L.lib().aum_sum_cast_colsum(L.ptr(a), L.ptr(b), ld, L.dt(a.dtype), L.ptr(out), cols, L.dt(out_dtype), L.ptr(colsum), rows, cols,
+                                     L.stream())
     L.check(rc, "aum_sum_cast_colsum")
     return out
 
 
 class ScanBwdDirection:
     """One time direction of the scan backward (struct aum_scan_bwd_dir).  u: (B,L,D) dtype; delta: (B,L,D) fp32
-    post-softplus; A: (D,16) fp32; bc: (B,L,32) fp32 packed [B|C]; outputs du, ddelta (B,L,D) fp32,
-    dA (D,16), dD (D), dbc (B,L,32) fp32 accumulated into; ckpt: fp32 workspace."""
+    post-softplus; A: (D,16) fp32; bc: (B,L,32) fp32 packed [B|C]; outputs du, ddelta (B,L,D) fp32 - or both of u's
+    16-bit dtype (training configuration only, see aum_b200.h) -, dA (D,16), dD (D), dbc (B,L,32) fp32 accumulated into;
+    ckpt: fp32 workspace."""
 
     def __init__(self, u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt, ckpt_valid=False):
         self.t = (u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt)
@@ -313,9 +317,11 @@ class ScanBwdDirection:
 
     def _struct(self):
         u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt = self.t
-        for t_ in (delta, A, bc, du, ddelta, dA, dbc, ckpt):
+        for t_ in (delta, A, bc, dA, dbc, ckpt):
             if t_.dtype != torch.float32:
-                raise L.AumError("scan bwd: delta/A/bc/du/ddelta/dA/dbc/ckpt must be fp32")
+                raise L.AumError("scan bwd: delta/A/bc/dA/dbc/ckpt must be fp32")
+        if du.dtype != ddelta.dtype or du.dtype not in (torch.float32, u.dtype):
+            raise L.AumError("scan bwd: du and ddelta must share a dtype: fp32 or u's")
         s = L.ScanBwdDir()
         s.u, s.ld_u = u.data_ptr(), _as_rows(u)[2]
         s.delta, s.ld_delta = delta.data_ptr(), _as_rows(delta)[2]
@@ -329,6 +335,7 @@ class ScanBwdDirection:
         s.dBC, s.ld_dbc = dbc.data_ptr(), _as_rows(dbc)[2]
         s.ckpt = ckpt.data_ptr()
         s.ckpt_valid = int(bool(self.ckpt_valid))
+        s.dgrad_dtype = L.dt(du.dtype)
         B, Lq, Dch = u.shape
         n = L.lib().aum_selective_scan_bwd_dbc_ws_floats(B, Lq, Dch)
         self._ws = torch.empty(n, device=u.device, dtype=torch.float32)   # per-warp dB|dC partials (kept alive here)

@@ -8,6 +8,7 @@
 // in registers (19 regs) so the kernel runs at full occupancy, and the 3-row halo is served by L1/L2.
 // Algorithmic bytes per (token, channel): read s + write s (s = itemsize).
 #include <stdlib.h>
+#include <type_traits>
 
 #include "scan_common.cuh"   // packed fp32x2 helpers
 
@@ -427,14 +428,24 @@ conv1d_bwd_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict_
 // weight / bias gradients accumulate in registers over the whole segment (8 warps = 8 consecutive segments per block,
 // reduced in shared memory, one atomic per value and block).  Packed fp32x2 math on the channel pair.
 // Needs W <= 4, D even and 8-byte-aligned rows (checked by the launcher; anything else takes the tile kernel).
-__device__ __forceinline__ float2 ldg_f2(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+// a channel pair of one gradient term as fp32 (TG: float, or the 16-bit activation dtype)
+template <typename TG> __device__ __forceinline__ float2 ldg_pair(const TG* p);
+template <> __device__ __forceinline__ float2 ldg_pair<float>(const float* p) { return __ldg(reinterpret_cast<const float2*>(p)); }
+template <> __device__ __forceinline__ float2 ldg_pair<__half>(const __half* p) {
+  const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+  return __half22float2(*reinterpret_cast<const __half2*>(&v));
+}
+template <> __device__ __forceinline__ float2 ldg_pair<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint32_t v = __ldg(reinterpret_cast<const uint32_t*>(p));
+  return make_float2(__uint_as_float(v << 16), __uint_as_float(v & 0xffff0000u));
+}
 
 // UNR / MINB: positions per loop trip / resident blocks per SM the register budget is set for: (2, 4) = 64 registers,
 // 32 warps per SM; (4, 3) = 80 registers, 24 warps with twice the loads in flight per warp (AUM_CONV_BWD_VARIANT=1).
-template <typename T, int NT, int UNR, int MINB>
+template <typename T, typename TG, int NT, int UNR, int MINB>
 __global__ void __launch_bounds__(256, MINB)
 conv1d_bwd_stream_kernel(const T* __restrict__ x, int64_t ldx, const float* __restrict__ w, const float* __restrict__ bias,
-                         const float* __restrict__ g1, const float* __restrict__ g2, const float* __restrict__ g3, int64_t ldd,
+                         const TG* __restrict__ g1, const TG* __restrict__ g2, const TG* __restrict__ g3, int64_t ldd,
                          T* __restrict__ dx, int64_t ld_dx, float* __restrict__ dw, float* __restrict__ dbias,
                          int L, int D, int W, int silu, int reverse, int n_cgrp, int n_tgrp, int seg) {
   __shared__ float red[8][10][32];
@@ -467,9 +478,9 @@ conv1d_bwd_stream_kernel(const T* __restrict__ x, int64_t ldx, const float* __re
     const int sgn = reverse ? -1 : 1;
     const int r0 = b * L + (reverse ? (L - 1 - p0) : p0);
     const T* const xb = x + c0;
-    const float* const q1 = g1 + c0;
-    const float* const q2 = NT >= 2 ? g2 + c0 : nullptr;
-    const float* const q3 = NT >= 3 ? g3 + c0 : nullptr;
+    const TG* const q1 = g1 + c0;
+    const TG* const q2 = NT >= 2 ? g2 + c0 : nullptr;
+    const TG* const q3 = NT >= 3 ? g3 + c0 : nullptr;
     T* const ob = dx + c0;
     int ox = r0 * (int)ldx, og = r0 * (int)ldd, oo = r0 * (int)ld_dx;     // rows of x[p], g[p], dx[next row to emit]
     const int sx = sgn * (int)ldx, sg = sgn * (int)ldd, so = sgn * (int)ld_dx;
@@ -485,9 +496,9 @@ conv1d_bwd_stream_kernel(const T* __restrict__ x, int64_t ldx, const float* __re
     // one position with data (p < L).  ACC: p belongs to this segment (its dc feeds dw / dbias); EMIT: dx[p-3] is ours
     auto step = [&](const bool accum, const bool emit) {
       const f32x2 xn = ldx2(xb + ox);
-      float2 g = ldg_f2(q1 + og);
-      if (NT >= 2) { const float2 t = ldg_f2(q2 + og); g.x += t.x; g.y += t.y; }
-      if (NT >= 3) { const float2 t = ldg_f2(q3 + og); g.x += t.x; g.y += t.y; }
+      float2 g = ldg_pair<TG>(q1 + og);
+      if (NT >= 2) { const float2 t = ldg_pair<TG>(q2 + og); g.x += t.x; g.y += t.y; }
+      if (NT >= 3) { const float2 t = ldg_pair<TG>(q3 + og); g.x += t.x; g.y += t.y; }
       ox += sx; og += sg;
       f32x2 dcn = pk2(g.x, g.y);
       if (silu) {
@@ -565,9 +576,9 @@ conv1d_bwd_stream_kernel(const T* __restrict__ x, int64_t ldx, const float* __re
   }
 }
 
-template <typename T, int UNR, int MINB>
-static void launch_conv_bwd_stream_v(const void* x, int64_t ldx, const float* w, const float* bias, const float* g1, const float* g2,
-                                     const float* g3, int64_t ldd, void* dx, int64_t ld_dx, float* dw, float* dbias,
+template <typename T, typename TG, int UNR, int MINB>
+static void launch_conv_bwd_stream_v(const void* x, int64_t ldx, const float* w, const float* bias, const void* g1_, const void* g2_,
+                                     const void* g3_, int64_t ldd, void* dx, int64_t ld_dx, float* dw, float* dbias,
                                      int batch, int L, int D, int W, int silu, int reverse, cudaStream_t st) {
   // 8 warps = 8 consecutive segments per block; segments of 32-64 positions (L = 513 -> 2 token groups of 8 x 33)
   const int n_tgrp = ceil_div(L, 512);
@@ -576,30 +587,42 @@ static void launch_conv_bwd_stream_v(const void* x, int64_t ldx, const float* w,
   const unsigned blocks = (unsigned)((int64_t)batch * n_cgrp * n_tgrp);
   const T* xx = reinterpret_cast<const T*>(x);
   T* dd = reinterpret_cast<T*>(dx);
-  if (g3 != nullptr)      conv1d_bwd_stream_kernel<T, 3, UNR, MINB><<<blocks, 256, 0, st>>>(xx, ldx, w, bias, g1, g2, g3, ldd, dd, ld_dx, dw, dbias, L, D, W, silu, reverse, n_cgrp, n_tgrp, seg);
-  else if (g2 != nullptr) conv1d_bwd_stream_kernel<T, 2, UNR, MINB><<<blocks, 256, 0, st>>>(xx, ldx, w, bias, g1, g2, g3, ldd, dd, ld_dx, dw, dbias, L, D, W, silu, reverse, n_cgrp, n_tgrp, seg);
-  else                    conv1d_bwd_stream_kernel<T, 1, UNR, MINB><<<blocks, 256, 0, st>>>(xx, ldx, w, bias, g1, g2, g3, ldd, dd, ld_dx, dw, dbias, L, D, W, silu, reverse, n_cgrp, n_tgrp, seg);
+  const TG *g1 = reinterpret_cast<const TG*>(g1_), *g2 = reinterpret_cast<const TG*>(g2_), *g3 = reinterpret_cast<const TG*>(g3_);
+  if (g3 != nullptr)      conv1d_bwd_stream_kernel<T, TG, 3, UNR, MINB><<<blocks, 256, 0, st>>>(xx, ldx, w, bias, g1, g2, g3, ldd, dd, ld_dx, dw, dbias, L, D, W, silu, reverse, n_cgrp, n_tgrp, seg);
+  else if (g2 != nullptr) conv1d_bwd_stream_kernel<T, TG, 2, UNR, MINB><<<blocks, 256, 0, st>>>(xx, ldx, w, bias, g1, g2, g3, ldd, dd, ld_dx, dw, dbias, L, D, W, silu, reverse, n_cgrp, n_tgrp, seg);
+  else                    conv1d_bwd_stream_kernel<T, TG, 1, UNR, MINB><<<blocks, 256, 0, st>>>(xx, ldx, w, bias, g1, g2, g3, ldd, dd, ld_dx, dw, dbias, L, D, W, silu, reverse, n_cgrp, n_tgrp, seg);
 }
 
+// G16: the gradient terms are of the activation dtype T (else fp32)
 template <typename T>
-static void launch_conv_bwd_stream(const void* x, int64_t ldx, const float* w, const float* bias, const float* g1, const float* g2,
-                                   const float* g3, int64_t ldd, void* dx, int64_t ld_dx, float* dw, float* dbias,
+static void launch_conv_bwd_stream(const void* x, int64_t ldx, const float* w, const float* bias, const void* g1, const void* g2,
+                                   const void* g3, int64_t ldd, bool g16, void* dx, int64_t ld_dx, float* dw, float* dbias,
                                    int batch, int L, int D, int W, int silu, int reverse, cudaStream_t st) {
   static int variant = -1;
   if (variant < 0) { const char* e = getenv("AUM_CONV_BWD_VARIANT"); variant = (e && atoi(e) == 1) ? 1 : 0; }
-  if (variant == 1) launch_conv_bwd_stream_v<T, 4, 3>(x, ldx, w, bias, g1, g2, g3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st);
-  else              launch_conv_bwd_stream_v<T, 2, 4>(x, ldx, w, bias, g1, g2, g3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st);
+  if (g16) {
+    if constexpr (!std::is_same<T, float>::value)
+      launch_conv_bwd_stream_v<T, T, 2, 4>(x, ldx, w, bias, g1, g2, g3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st);
+    return;
+  }
+  if (variant == 1) launch_conv_bwd_stream_v<T, float, 4, 3>(x, ldx, w, bias, g1, g2, g3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st);
+  else              launch_conv_bwd_stream_v<T, float, 2, 4>(x, ldx, w, bias, g1, g2, g3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st);
 }
 
 }  // namespace aum
 
 extern "C" int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w, const float* bias,
-                                     const float* dout, const float* dout2, const float* dout3, int64_t ldd, void* dx, int64_t ld_dx,
+                                     const void* dout_, const void* dout2_, const void* dout3_, int64_t ldd, int dout_dtype,
+                                     void* dx, int64_t ld_dx,
                                      float* dw, float* dbias, int batch, int L, int D, int W,
                                      int dtype, int silu, int reverse, void* stream) {
   using namespace aum;
   DeviceGuard device_guard(dx);
-  AUM_REQUIRE(x && w && dout && dx && dw, "aum_causal_conv1d_bwd: null pointer");
+  AUM_REQUIRE(x && w && dout_ && dx && dw, "aum_causal_conv1d_bwd: null pointer");
+  AUM_REQUIRE(dout_dtype == AUM_F32 || (dout_dtype == dtype && dtype != AUM_F32),
+              "aum_causal_conv1d_bwd: the gradient terms must be fp32 or of the call's 16-bit dtype");
+  const bool g16 = dout_dtype != AUM_F32;
+  const float *dout = (const float*)dout_, *dout2 = (const float*)dout2_, *dout3 = (const float*)dout3_;   // (tile kernel: fp32 only)
   AUM_REQUIRE(W >= 2 && W <= CONV_MAXW, "aum_causal_conv1d_bwd: width %d unsupported (2..4)", W);
   AUM_REQUIRE(batch >= 0 && L >= 0 && D >= 0, "aum_causal_conv1d_bwd: negative size");
   AUM_REQUIRE(ldx >= D && ldd >= D && ld_dx >= D, "aum_causal_conv1d_bwd: leading dimension smaller than D");
@@ -616,19 +639,20 @@ extern "C" int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w,
     static int force_tile = -1;
     if (force_tile < 0) force_tile = getenv("AUM_CONV_BWD_TILE") != nullptr ? 1 : 0;
     const bool stream_ok = !force_tile && D % 2 == 0 && ldx % 2 == 0 && ldd % 2 == 0 && ld_dx % 2 == 0 && al(x, 2 * esz) && al(dx, 2 * esz) &&
-                           al(dout, 8) && al(dout2, 8) && al(dout3, 8) && !(dout2 == nullptr && dout3 != nullptr) &&
+                           al(dout, g16 ? 4 : 8) && al(dout2, g16 ? 4 : 8) && al(dout3, g16 ? 4 : 8) && !(dout2 == nullptr && dout3 != nullptr) &&
                            (int64_t)batch * ceil_div(D, 64) * ceil_div(L, 512) < (1ll << 31) &&
                            ((int64_t)batch * L + 4) * (ldx > ldd ? (ldx > ld_dx ? ldx : ld_dx) : (ldd > ld_dx ? ldd : ld_dx)) < (1ll << 31);
     if (stream_ok) {
       switch (dtype) {
-        case AUM_F32:  launch_conv_bwd_stream<float>(x, ldx, w, bias, dout, dout2, dout3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st); break;
-        case AUM_F16:  launch_conv_bwd_stream<__half>(x, ldx, w, bias, dout, dout2, dout3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st); break;
-        case AUM_BF16: launch_conv_bwd_stream<__nv_bfloat16>(x, ldx, w, bias, dout, dout2, dout3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st); break;
+        case AUM_F32:  launch_conv_bwd_stream<float>(x, ldx, w, bias, dout, dout2, dout3, ldd, g16, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st); break;
+        case AUM_F16:  launch_conv_bwd_stream<__half>(x, ldx, w, bias, dout, dout2, dout3, ldd, g16, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st); break;
+        case AUM_BF16: launch_conv_bwd_stream<__nv_bfloat16>(x, ldx, w, bias, dout, dout2, dout3, ldd, g16, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st); break;
         default: set_error("aum_causal_conv1d_bwd: bad dtype %d", dtype); return 1;
       }
       return check_launch("aum_causal_conv1d_bwd");
     }
   }
+  AUM_REQUIRE(!g16, "aum_causal_conv1d_bwd: 16-bit gradient terms need the streaming kernel (even D and pitches, W <= 4, 4-byte aligned rows)");
   switch (dtype) {
     case AUM_F32:  conv1d_bwd_kernel<float><<<(unsigned)blocks, 256, 0, st>>>((const float*)x, ldx, w, bias, dout, dout2, dout3, ldd, (float*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;
     case AUM_F16:  conv1d_bwd_kernel<__half><<<(unsigned)blocks, 256, 0, st>>>((const __half*)x, ldx, w, bias, dout, dout2, dout3, ldd, (__half*)dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, n_cgrp, n_tgrp); break;

@@ -2,7 +2,8 @@
 // One pass instead of the three torch launches it replaces in BiMambaInnerFn.backward's dt_proj chain
 // (/root/reference/vim-mamba_ssm/mamba_ssm/ops/selective_scan_interface.py:566-586: ddelta of the two directions summed
 // (:556), delta_proj bias gradient = its sum over tokens, and the 16-bit operand of the d(dt_proj.weight) / d(x_dbl)
-// products).  HBM-bound: reads 4 (+4) bytes, writes s bytes per element.
+// products).  HBM-bound: reads 4 (+4) bytes - or 2 (+2) when the backward scan left ddelta in the activation dtype - and
+// writes s bytes per element.
 #include "common.cuh"
 
 namespace aum {
@@ -10,9 +11,22 @@ namespace aum {
 constexpr int RO_ROWS = 64;      // rows per block
 constexpr int RO_THREADS = 256;  // 4 columns per thread -> 1024 columns per block
 
-template <typename T>
+// 4 adjacent elements of a row as fp32
+template <typename TI> __device__ __forceinline__ float4 ld4(const TI* p);
+template <> __device__ __forceinline__ float4 ld4<float>(const float* p) { return __ldg(reinterpret_cast<const float4*>(p)); }
+template <> __device__ __forceinline__ float4 ld4<__half>(const __half* p) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  const float2 lo = __half22float2(*reinterpret_cast<const __half2*>(&v.x)), hi = __half22float2(*reinterpret_cast<const __half2*>(&v.y));
+  return make_float4(lo.x, lo.y, hi.x, hi.y);
+}
+template <> __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bfloat16* p) {
+  const uint2 v = __ldg(reinterpret_cast<const uint2*>(p));
+  return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
+}
+
+template <typename T, typename TI>
 __global__ void __launch_bounds__(RO_THREADS)
-sum_cast_colsum_kernel(const float* __restrict__ a, const float* __restrict__ b, int64_t ld, T* __restrict__ out, int64_t ldo,
+sum_cast_colsum_kernel(const TI* __restrict__ a, const TI* __restrict__ b, int64_t ld, T* __restrict__ out, int64_t ldo,
                        float* __restrict__ colsum, int rows, int cols) {
   const int c0 = (blockIdx.x * RO_THREADS + threadIdx.x) * 4;
   if (c0 >= cols) return;
@@ -20,9 +34,9 @@ sum_cast_colsum_kernel(const float* __restrict__ a, const float* __restrict__ b,
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
 #pragma unroll 4
   for (int r = r0; r < r1; ++r) {
-    float4 v = __ldg(reinterpret_cast<const float4*>(a + (int64_t)r * ld + c0));
+    float4 v = ld4<TI>(a + (int64_t)r * ld + c0);
     if (b != nullptr) {
-      const float4 w = __ldg(reinterpret_cast<const float4*>(b + (int64_t)r * ld + c0));
+      const float4 w = ld4<TI>(b + (int64_t)r * ld + c0);
       v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
     }
     s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
@@ -44,7 +58,21 @@ sum_cast_colsum_kernel(const float* __restrict__ a, const float* __restrict__ b,
 
 }  // namespace aum
 
-extern "C" int aum_sum_cast_colsum(const float* a, const float* b, int64_t ld, void* out, int64_t ld_out, int out_dtype,
+namespace aum {
+template <typename TI>
+static void launch_sum_cast(const void* a, const void* b, int64_t ld, void* out, int64_t ld_out, int out_dtype, float* colsum,
+                            int rows, int cols, cudaStream_t st) {
+  dim3 grid(ceil_div(cols, RO_THREADS * 4), ceil_div(rows, RO_ROWS));
+  const TI *aa = reinterpret_cast<const TI*>(a), *bb = reinterpret_cast<const TI*>(b);
+  switch (out_dtype) {
+    case AUM_F32:  sum_cast_colsum_kernel<float, TI><<<grid, RO_THREADS, 0, st>>>(aa, bb, ld, (float*)out, ld_out, colsum, rows, cols); break;
+    case AUM_F16:  sum_cast_colsum_kernel<__half, TI><<<grid, RO_THREADS, 0, st>>>(aa, bb, ld, (__half*)out, ld_out, colsum, rows, cols); break;
+    default:       sum_cast_colsum_kernel<__nv_bfloat16, TI><<<grid, RO_THREADS, 0, st>>>(aa, bb, ld, (__nv_bfloat16*)out, ld_out, colsum, rows, cols); break;
+  }
+}
+}  // namespace aum
+
+extern "C" int aum_sum_cast_colsum(const void* a, const void* b, int64_t ld, int in_dtype, void* out, int64_t ld_out, int out_dtype,
                                    float* colsum, int rows, int cols, void* stream) {
   using namespace aum;
   DeviceGuard device_guard(out);
@@ -52,17 +80,17 @@ extern "C" int aum_sum_cast_colsum(const float* a, const float* b, int64_t ld, v
   AUM_REQUIRE(a && out, "aum_sum_cast_colsum: null pointer");
   AUM_REQUIRE(rows > 0 && cols > 0 && cols % 4 == 0, "aum_sum_cast_colsum: cols must be a positive multiple of 4");
   AUM_REQUIRE(out_dtype >= AUM_F32 && out_dtype <= AUM_BF16, "aum_sum_cast_colsum: bad dtype %d", out_dtype);
+  AUM_REQUIRE(in_dtype >= AUM_F32 && in_dtype <= AUM_BF16, "aum_sum_cast_colsum: bad input dtype %d", in_dtype);
   AUM_REQUIRE(ld >= cols && ld_out >= cols, "aum_sum_cast_colsum: leading dimension smaller than the row length");
-  const int osz = dtype_size(out_dtype);
-  AUM_REQUIRE(aligned16(a) && (b == nullptr || aligned16(b)) && (ld * 4) % 16 == 0 &&
-              (reinterpret_cast<uintptr_t>(out) % (4 * osz) == 0) && (ld_out * osz) % (4 * osz) == 0,
+  const int osz = dtype_size(out_dtype), isz = dtype_size(in_dtype);
+  auto al = [](const void* p, int n) { return p == nullptr || reinterpret_cast<uintptr_t>(p) % n == 0; };
+  AUM_REQUIRE(al(a, 4 * isz) && al(b, 4 * isz) && ld % 4 == 0 && al(out, 4 * osz) && ld_out % 4 == 0,
               "aum_sum_cast_colsum: rows must be addressable in 4-element vectors");
-  dim3 grid(ceil_div(cols, RO_THREADS * 4), ceil_div(rows, RO_ROWS));
   cudaStream_t st = (cudaStream_t)stream;
-  switch (out_dtype) {
-    case AUM_F32:  sum_cast_colsum_kernel<float><<<grid, RO_THREADS, 0, st>>>(a, b, ld, (float*)out, ld_out, colsum, rows, cols); break;
-    case AUM_F16:  sum_cast_colsum_kernel<__half><<<grid, RO_THREADS, 0, st>>>(a, b, ld, (__half*)out, ld_out, colsum, rows, cols); break;
-    default:       sum_cast_colsum_kernel<__nv_bfloat16><<<grid, RO_THREADS, 0, st>>>(a, b, ld, (__nv_bfloat16*)out, ld_out, colsum, rows, cols); break;
+  switch (in_dtype) {
+    case AUM_F32:  launch_sum_cast<float>(a, b, ld, out, ld_out, out_dtype, colsum, rows, cols, st); break;
+    case AUM_F16:  launch_sum_cast<__half>(a, b, ld, out, ld_out, out_dtype, colsum, rows, cols, st); break;
+    default:       launch_sum_cast<__nv_bfloat16>(a, b, ld, out, ld_out, out_dtype, colsum, rows, cols, st); break;
   }
   return check_launch("aum_sum_cast_colsum");
 }

@@ -130,7 +130,7 @@ scan_bwd_kernel(const ScanBwdParams p) {
   const T* gb = reinterpret_cast<const T*>(p.dout) + ch;
   T* dzb = p.dz ? reinterpret_cast<T*>(p.dz) + ch : nullptr;
   T* ozb = p.outz ? reinterpret_cast<T*>(p.outz) + ch : nullptr;
-  float* dub = d.du + ch;
+  float* dub = d.du + ch;           // (fp32 only in this kernel: the entry point refuses 16-bit du / ddelta here)
   float* ddb = d.ddelta + ch;
 
   // visiting order q = 0..L-1 of sweep 2 is s = L-1-q.  With shared du/ddelta the first Q1 visits park partials.
@@ -332,9 +332,13 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
     AUM_REQUIRE(aligned16(s->A) && aligned16(s->BC) && (s->ld_bc % 4) == 0, "aum_selective_scan_bwd: A / BC must be 16-byte aligned");
     ScanBwdDirDev& d = p.dir[p.ndirs++];
     d.u = s->u; d.ld_u = s->ld_u; d.delta = s->delta; d.ld_delta = s->ld_delta; d.A = s->A;
-    d.BC = s->BC; d.ld_bc = s->ld_bc; d.D = s->D; d.du = s->du; d.ld_du = s->ld_du;
-    d.ddelta = s->ddelta; d.ld_dd = s->ld_dd; d.dA = s->dA; d.dD = s->dD; d.dBC = s->dBC; d.ld_dbc = s->ld_dbc;
+    d.BC = s->BC; d.ld_bc = s->ld_bc; d.D = s->D; d.du = (float*)s->du; d.ld_du = s->ld_du;
+    d.ddelta = (float*)s->ddelta; d.ld_dd = s->ld_dd; d.dA = s->dA; d.dD = s->dD; d.dBC = s->dBC; d.ld_dbc = s->ld_dbc;
     d.ckpt = s->ckpt; d.ckpt_valid = s->ckpt_valid; d.reverse = i; d.dbc_ws = s->dbc_ws;
+    AUM_REQUIRE(s->dgrad_dtype == AUM_F32 || (s->dgrad_dtype == dtype && dtype != AUM_F32),
+                "aum_selective_scan_bwd: du / ddelta must be fp32 or of the call's 16-bit dtype");
+    AUM_REQUIRE(p.ndirs == 1 || (s->dgrad_dtype != AUM_F32) == (p.g16 != 0), "aum_selective_scan_bwd: both directions must share dgrad_dtype");
+    p.g16 = s->dgrad_dtype != AUM_F32 ? 1 : 0;
   }
   if (p.ndirs == 2) {
     const bool same_du = p.dir[0].du == p.dir[1].du, same_dd = p.dir[0].ddelta == p.dir[1].ddelta;
@@ -361,6 +365,8 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
   }
   const int fast = launch_scan_bwd_tma(p, dtype, st);     // TMA-streamed kernel when eligible
   if (fast > 0) return fast;
+  AUM_REQUIRE(fast == 0 || !p.g16, "aum_selective_scan_bwd: 16-bit du / ddelta need the specialised TMA-streamed kernel "
+                                   "(forward checkpoints, z + y_pre + dz + out_z, softplus_grad, separate du / ddelta per direction, D %% 128 == 0)");
   if (fast < 0) {
     switch (dtype) {
       case AUM_F32:  scan_bwd_kernel<float><<<grid, SB_CH * p.ndirs, smem, st>>>(p); break;

@@ -27,6 +27,7 @@ struct ScanBwdDirDev {
 struct ScanBwdParams {
   ScanBwdDirDev dir[2];
   int ndirs, shared_du;
+  int g16;            // du / ddelta are of the activation dtype (specialised TMA kernel only), else fp32
   const void* z; int64_t ld_z;
   const void* ypre; int64_t ld_y;
   const void* dout; int64_t ld_dout;

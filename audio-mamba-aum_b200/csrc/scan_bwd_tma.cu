@@ -19,6 +19,7 @@
 // 16-byte aligned bases and row pitches.  Anything else runs scan_bwd.cu.
 #include <cuda.h>
 #include <stdlib.h>
+#include <type_traits>
 
 #include "scan_bwd_common.cuh"
 #include "tma.cuh"
@@ -150,7 +151,8 @@ __device__ __forceinline__ float sigmoid_ftz(float x) {
 // the parameter block at run time; in the 2-step unrolled reverse-time loop that is ~90 of ~340 instructions per step
 // (uniform branches, predicate set-up, 64-bit pointer selects) and, worse for a latency-bound kernel, it cuts the step
 // into basic blocks the scheduler cannot interleave across.
-template <typename T, bool SPEC, bool REV_, bool GATE_>
+// TG: element type of du / ddelta (float, or T in the specialised instantiation when the caller asked for 16-bit gradients)
+template <typename T, bool SPEC, bool REV_, bool GATE_, typename TG>
 __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const ScanBwdParams& p, uint8_t* smem_raw) {
   using BL = BwdLayout<T>;
   const uint32_t smem0 = (s_u32(smem_raw) + 127u) & ~127u;
@@ -315,8 +317,8 @@ __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const Scan
       uint32_t a_y = st + BL::OFF_Y + e16 + (uint32_t)(jl * s16);
       uint32_t slot = hcol + (uint32_t)jl * SCAN_NS;
       const int64_t r_last = (int64_t)row0 + (rev ? (L - 1 - (s0 + jl)) : (s0 + jl));      // global row of step s0+jl
-      float* dup = d.du + r_last * d.ld_du + ch;
-      float* ddp = d.ddelta + r_last * d.ld_dd + ch;
+      TG* dup = reinterpret_cast<TG*>(d.du) + r_last * d.ld_du + ch;
+      TG* ddp = reinterpret_cast<TG*>(d.ddelta) + r_last * d.ld_dd + ch;
       float* wsp = d.dbc_ws + ((int64_t)part * rows_total + r_last) * 32 + 2 * (lane & 15);   // lanes 0-15 store float2
       T* dzp = (SPEC ? GATE_ : (p.dz != nullptr)) ? reinterpret_cast<T*>(p.dz) + r_last * p.ld_dz + ch : nullptr;
       T* ozp = (SPEC ? GATE_ : (p.outz != nullptr)) ? reinterpret_cast<T*>(p.outz) + r_last * p.ld_oz + ch : nullptr;
@@ -372,8 +374,12 @@ __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const Scan
         }
         if (spg_on) dd *= 1.f - ex2_approx(-1.4426950408889634f * dl);   // softplus'(pre) = 1 - exp(-delta), delta >= 0
         if (active) {
-          if (accumulate) { red_add_f32(dup, duv); red_add_f32(ddp, dd); }
-          else { *dup = duv; *ddp = dd; }
+          if constexpr (std::is_same<TG, float>::value) {
+            if (accumulate) { red_add_f32(dup, duv); red_add_f32(ddp, dd); }
+            else { *dup = duv; *ddp = dd; }
+          } else {
+            *dup = from_f<TG>(duv); *ddp = from_f<TG>(dd);
+          }
           if (gate) {
             const float yp = want_y ? ldst<T>(a_y + o16) : 0.f;
             if (dzp) *dzp = from_f<T>(go * yp * (sg * (1.f + zv * (1.f - sg))));
@@ -424,15 +430,16 @@ __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const Scan
   if (tig < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BT_TMEM_COLS) : "memory");
 }
 
-template <typename T, bool SPEC>
+template <typename T, bool SPEC, bool G16>
 __global__ void __launch_bounds__(BT_CH, 3)
 scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
+  using TG = typename std::conditional<G16, T, float>::type;
   if (SPEC) {
-    if (blockIdx.z == 0) scan_bwd_cta<T, true, false, true>(maps, p, smem_raw);
-    else                 scan_bwd_cta<T, true, true, false>(maps, p, smem_raw);
+    if (blockIdx.z == 0) scan_bwd_cta<T, true, false, true, TG>(maps, p, smem_raw);
+    else                 scan_bwd_cta<T, true, true, false, TG>(maps, p, smem_raw);
   } else {
-    scan_bwd_cta<T, false, false, false>(maps, p, smem_raw);
+    scan_bwd_cta<T, false, false, false, float>(maps, p, smem_raw);
   }
 }
 
@@ -449,17 +456,23 @@ static bool bwd_spec_ok(const ScanBwdParams& p) {
 template <typename T>
 static int launch_bt(const ScanBwdMaps& maps, const ScanBwdParams& p, cudaStream_t st) {
   using BL = BwdLayout<T>;
+  constexpr bool T16 = !std::is_same<T, float>::value;
   static PerDevice<bool> attr_set_dev;
   bool& attr_set = attr_set_dev.cur();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T, true>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
+    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
+    if (e == cudaSuccess && T16) e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T, true, T16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("aum_selective_scan_bwd: cudaFuncSetAttribute(smem=%d): %s", BL::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
     attr_set = true;
   }
   dim3 grid(ceil_div(p.Dch, BT_CH), p.batch, p.ndirs);
-  if (bwd_spec_ok(p)) scan_bwd_tma_kernel<T, true><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
-  else                scan_bwd_tma_kernel<T, false><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
+  const bool spec = bwd_spec_ok(p);
+  if (p.g16) {
+    if (!spec || !T16) return -1;                         // (the entry point turns this into an error)
+    scan_bwd_tma_kernel<T, true, T16><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
+  } else if (spec) scan_bwd_tma_kernel<T, true, false><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
+  else             scan_bwd_tma_kernel<T, false, false><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
   return check_launch("aum_selective_scan_bwd(tma)");
 }
 

@@ -118,18 +118,22 @@ AUM_API int aum_conv_xproj_fwd(const void* x, int64_t ldx, const float* conv_w, 
 
 /* Backward of the above.  replaces causal_conv1d_cuda.causal_conv1d_bwd(x, w, bias, dout, None, dx, silu)
  *   (selective_scan_interface.py:281-283, 425-427, 594-596).  dout (+ optional dout2, dout3, same pitch; summed on the
- *   fly — the scan's du of either direction (:556) and the x_proj term of :590): fp32 gradient w.r.t. the conv output
- *   (after the activation); dx: written (dtype); dw (D, W) and dbias (D) are ACCUMULATED (+=): zero them first. */
+ *   fly — the scan's du of either direction (:556) and the x_proj term of :590): gradient w.r.t. the conv output
+ *   (after the activation), all terms of ONE element type dout_dtype: AUM_F32, or the call's 16-bit `dtype` (what the
+ *   reference accumulates dconv1d_out in under autocast; the sum is formed in fp32 here); dx: written (dtype); dw (D, W)
+ *   and dbias (D) are ACCUMULATED (+=): zero them first. */
 AUM_API int aum_causal_conv1d_bwd(const void* x, int64_t ldx, const float* w, const float* bias,
-                          const float* dout, const float* dout2, const float* dout3, int64_t ldd, void* dx, int64_t ld_dx,
+                          const void* dout, const void* dout2, const void* dout3, int64_t ldd, int dout_dtype,
+                          void* dx, int64_t ld_dx,
                           float* dw, float* dbias, int batch, int L, int D, int W,
                           int dtype, int silu, int reverse, void* stream);
 
 /* out[r, c] = (out_dtype)(a[r, c] + b[r, c]),  colsum[c] += sum_r (a + b)[r, c]   (b and colsum optional).
  *   One pass for the dt_proj chain of the three backward functions (selective_scan_interface.py:556 ddelta of the two
  *   directions summed, :583-586 delta_proj bias gradient = sum over tokens, and the 16-bit operand of the
- *   d(dt_proj.weight) / d(x_dbl) products).  a, b: fp32 (rows, cols) with pitch ld; cols % 4 == 0. */
-AUM_API int aum_sum_cast_colsum(const float* a, const float* b, int64_t ld, void* out, int64_t ld_out, int out_dtype,
+ *   d(dt_proj.weight) / d(x_dbl) products).  a, b: (rows, cols) of in_dtype (fp32, or 16-bit as the backward scan leaves
+ *   ddelta with dgrad_dtype) with pitch ld; the sum is formed in fp32; cols % 4 == 0. */
+AUM_API int aum_sum_cast_colsum(const void* a, const void* b, int64_t ld, int in_dtype, void* out, int64_t ld_out, int out_dtype,
                         float* colsum, int rows, int cols, void* stream);
 
 /* ---------------------------------------------------------------------------------------------
@@ -186,8 +190,8 @@ typedef struct aum_scan_bwd_dir {
   const float* A;                        /* (D, N) */
   const float* BC;    int64_t ld_bc;     /* (batch*L, 2N) fp32 [B|C] */
   const float* D;                        /* (D) or NULL */
-  float* du;     int64_t ld_du;          /* out (batch*L, D) fp32 */
-  float* ddelta; int64_t ld_dd;          /* out (batch*L, D) fp32 */
+  void* du;      int64_t ld_du;          /* out (batch*L, D) fp32, or dtype when dgrad_dtype says so */
+  void* ddelta;  int64_t ld_dd;          /* out (batch*L, D) same dtype as du */
   float* dA;                             /* += (D, N) */
   float* dD;                             /* += (D) or NULL */
   float* dBC;    int64_t ld_dbc;         /* += (batch*L, 2N) */
@@ -195,6 +199,12 @@ typedef struct aum_scan_bwd_dir {
   float* ckpt;                           /* workspace (same size as the forward's ckpt) */
   int ckpt_valid;                        /* 1: ckpt was filled by aum_selective_scan_fwd for the SAME direction slot and
                                             directionality (uni/bi) — the backward then skips its own forward sweep */
+  int dgrad_dtype;                       /* dtype of du and ddelta: AUM_F32 (= 0, the default of a zeroed struct) or the
+                                            call's 16-bit `dtype` - what the reference's kernels return under autocast
+                                            (selective_scan_interface.py:541-561: du, ddelta in the input dtypes).  The
+                                            16-bit form needs the training configuration the TMA-streamed kernel is
+                                            specialised for (checkpoints, z, y_pre, dz, out_z, softplus_grad, one du /
+                                            ddelta pair per direction, D % 128 == 0); anything else is refused. */
 } aum_scan_bwd_dir_t;
 
 AUM_API int64_t aum_selective_scan_bwd_workspace_floats(int batch, int L, int D);

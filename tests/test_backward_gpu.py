@@ -486,3 +486,63 @@ def test_sum_cast_colsum(dt):
         res.append((dx.cpu(), dw.cpu(), db.cpu()))
     for p_, q_ in zip(res[0], res[1]):
         torch.testing.assert_close(p_, q_, rtol=1e-5, atol=1e-5)
+
+
+@pytest.mark.parametrize("dt", [torch.bfloat16, torch.float16])
+def test_16bit_gradient_terms_equal_the_rounded_fp32_ones(dt):
+    """The training step keeps du / ddelta of the backward scan and the gradient terms of the conv backward in the
+    activation dtype (aum_scan_bwd_dir.dgrad_dtype, aum_causal_conv1d_bwd(dout_dtype), aum_sum_cast_colsum(in_dtype)):
+    the 16-bit outputs are the fp32 ones rounded once, and consumers fed the rounded terms agree with fp32 arithmetic on
+    those same rounded values."""
+    from aum_b200 import ops
+    g = gen(41)
+    B, Lq, D, N = 2, 70, 256, 16
+    u, z, G = (rnd((B, Lq, D), g).to(DEV).to(dt) for _ in range(3))
+    delta = torch.nn.functional.softplus(rnd((B, Lq, D), g) - 2.0).to(DEV)
+    bc = rnd((B, Lq, 2 * N), g).to(DEV)
+    A = -torch.exp(rnd((D, N), g, 0.3)).to(DEV); A_b = -torch.exp(rnd((D, N), g, 0.3)).to(DEV)
+    Dv = torch.ones(D, device=DEV)
+    ck = {k: ops.scan_bwd_workspace(B, Lq, D, DEV) for k in "fb"}
+    y_pre = torch.empty((B, Lq, D), device=DEV, dtype=dt)
+    mkf = lambda Ax, k: ops.ScanDirection(u, delta, Ax, bc[..., :N], bc[..., N:], Dv, ckpt=ck[k])
+    ops.selective_scan(mkf(A, "f"), mkf(A_b, "b"), z, y_pre=y_pre)
+    res = {}
+    for gdt in (torch.float32, dt):
+        du = [torch.full((B, Lq, D), float("nan"), device=DEV, dtype=gdt) for _ in range(2)]
+        dd = [torch.full((B, Lq, D), float("nan"), device=DEV, dtype=gdt) for _ in range(2)]
+        dbc = torch.zeros((B, Lq, 2 * N), device=DEV)
+        dA = [torch.zeros((D, N), device=DEV) for _ in range(2)]
+        dD = torch.zeros((D,), device=DEV)
+        dz = torch.empty((B, Lq, D), device=DEV, dtype=dt); oz = torch.empty_like(dz)
+        mk = lambda Ax, i, k: ops.ScanBwdDirection(u, delta, Ax, bc, Dv, du[i], dd[i], dA[i], dD, dbc, ck[k], ckpt_valid=True)
+        ops.selective_scan_bwd(mk(A, 0, "f"), mk(A_b, 1, "b"), z, y_pre, G, dz, oz, softplus_grad=True)
+        res[gdt] = (du, dd, dbc, dA, dz)
+    f32r, lo = res[torch.float32], res[dt]
+    for i in range(2):
+        assert torch.equal(lo[0][i], f32r[0][i].to(dt)) and torch.equal(lo[1][i], f32r[1][i].to(dt))
+    torch.testing.assert_close(lo[2], f32r[2], rtol=1e-5, atol=1e-5)          # dB|dC, dA, dz do not depend on the store dtype
+    torch.testing.assert_close(lo[3][0], f32r[3][0], rtol=1e-5, atol=1e-5)
+    assert torch.equal(lo[4], f32r[4])
+    # consumers: the 16-bit terms summed in fp32
+    du_f, du_b = lo[0]
+    g2 = rnd((B, Lq, D), g).to(DEV).to(dt)
+    x = rnd((B, Lq, D), g).to(DEV).to(dt); w = rnd((D, 4), g, 0.5).to(DEV); bias = rnd((D,), g, 0.5).to(DEV)
+    out = []
+    for terms in ((du_f, g2, du_b), (du_f.float(), g2.float(), du_b.float())):
+        dx = torch.empty((B, Lq, D), device=DEV, dtype=dt); dw = torch.zeros((D, 4), device=DEV); db = torch.zeros((D,), device=DEV)
+        ops.causal_conv1d_bwd(x, w, bias, terms[0], dx, dw, db, dout2=terms[1], dout3=terms[2])
+        out.append((dx, dw, db))
+    assert torch.equal(out[0][0], out[1][0])
+    torch.testing.assert_close(out[0][1], out[1][1], rtol=1e-5, atol=1e-4)
+    torch.testing.assert_close(out[0][2], out[1][2], rtol=1e-5, atol=1e-4)
+    dd_f, dd_b = lo[1]
+    cs0, cs1 = torch.zeros(D, device=DEV), torch.zeros(D, device=DEV)
+    s0 = ops.sum_cast_colsum(dd_f.view(-1, D), dd_b.view(-1, D), dt, cs0)
+    s1 = ops.sum_cast_colsum(dd_f.float().view(-1, D), dd_b.float().view(-1, D), dt, cs1)
+    assert torch.equal(s0, s1)
+    torch.testing.assert_close(cs0, cs1, rtol=1e-5, atol=1e-4)
+    # outside the specialised configuration the 16-bit form is refused, loudly
+    du16 = torch.empty((B, Lq, D), device=DEV, dtype=dt)
+    with pytest.raises(Exception):
+        ops.selective_scan_bwd(ops.ScanBwdDirection(u, delta, A, bc, Dv, du16, du16.clone(), dA[0], dD, dbc, ck["f"], ckpt_valid=True),
+                               None, None, None, G, None, None)

@@ -145,6 +145,19 @@ def main():
             ops.ScanBwdDirection(u, delta, A_b, bc, Dv, du2, dd2, dAb, dD, dbc, ckb, ckpt_valid=True),
             z, ypre, dout, dz, oz, softplus_grad=True)
         report("biscan_bwd(training call: per-direction du/ddelta, softplus')", timeit(bw, iters=5, flush=flush))
+        if dt != torch.float32:
+            h = dict(device=dev, dtype=dt)
+            duh, ddh, du2h, dd2h = (torch.empty((B, Lq, Di), **h) for _ in range(4))
+            bwh = lambda: ops.selective_scan_bwd(
+                ops.ScanBwdDirection(u, delta, A, bc, Dv, duh, ddh, dA, dD, dbc, ckf, ckpt_valid=True),
+                ops.ScanBwdDirection(u, delta, A_b, bc, Dv, du2h, dd2h, dAb, dD, dbc, ckb, ckpt_valid=True),
+                z, ypre, dout, dz, oz, softplus_grad=True)
+            report("biscan_bwd(training call, 16-bit du/ddelta)", timeit(bwh, iters=5, flush=flush))
+            csum = torch.zeros(Di, **f32)
+            report("sum_cast_colsum(fp32 in)", timeit(lambda: ops.sum_cast_colsum(dd.view(M, Di), dd2.view(M, Di), dt, csum), flush=flush),
+                   bytes_=M * Di * (8 + s))
+            report("sum_cast_colsum(16-bit in)", timeit(lambda: ops.sum_cast_colsum(ddh.view(M, Di), dd2h.view(M, Di), dt, csum), flush=flush),
+                   bytes_=M * Di * (4 + s))
         x = rn(B, Lq, 2 * Di)
         w, b_ = rn(Di, 4, dtype=torch.float32), rn(Di, dtype=torch.float32)
         g32 = rn(B, Lq, Di, dtype=torch.float32)
@@ -156,6 +169,11 @@ def main():
         report("conv1d_bwd(3 gradient terms, as a Fo-Bi block calls it)",
                timeit(lambda: ops.causal_conv1d_bwd(x[..., :Di], w, b_, g32, dx, dw, db_, dout2=g2_, dout3=g3_), flush=flush),
                bytes_=M * Di * (2 * s + 12))
+        if dt != torch.float32:
+            h1, h2, h3 = g32.to(dt), g2_.to(dt), g3_.to(dt)
+            report("conv1d_bwd(3 gradient terms, 16-bit)",
+                   timeit(lambda: ops.causal_conv1d_bwd(x[..., :Di], w, b_, h1, dx, dw, db_, dout2=h2, dout3=h3), flush=flush),
+                   bytes_=M * Di * (2 * s + 6))
     if dt != torch.float32 and (not only or "gemm" in only):
         shapes = {"in_proj": (M, 2 * Di, Dm), "out_proj": (M, Dm, Di), "x_proj": (M, R + 2 * N, Di), "dt_proj": (M, Di, R)}
         for name, (m_, n_, k_) in shapes.items():
