@@ -65,6 +65,7 @@ class ScanBwdDir(C.Structure):
         ("ckpt", C.c_void_p),
         ("ckpt_valid", C.c_int),
         ("dgrad_dtype", C.c_int),
+        ("delta_dtype", C.c_int),
     ]
 
 

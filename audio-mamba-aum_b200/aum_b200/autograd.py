@@ -114,6 +114,15 @@ def _A(a, cfg):
     return mixer._neg_exp(a) if cfg.a_is_log else mixer._f32(a)
 
 
+def _train16(act, Di) -> bool:
+    """Training keeps delta (forward and recomputed), du / ddelta of the backward scan and the x_proj term of d(conv_out) in
+    the activation dtype when that is 16-bit - the rounding points of the reference's kernels under autocast
+    (selective_scan_interface.py:468, :541-561, :590); every sum over those terms is still formed in fp32.  Needs the
+    specialised backward-scan kernel (128-channel CTAs); AUM_GRAD_16BIT=0 keeps fp32 everywhere."""
+    return (act != F32 and Di % 128 == 0 and _GRAD_16BIT and "AUM_SCAN_BWD_GENERIC" not in os.environ
+            and "AUM_SCAN_BWD_NOSPEC" not in os.environ)
+
+
 def _branch_fwd(xz, Di, N, cw, cb, xw, dtw, dtb, reverse, act):
     """conv -> x_proj -> dt_proj of one parameter set (selective_scan_interface.py:461-496); returns (u, delta, dt, bc)."""
     B, Lq, _ = xz.shape
@@ -129,7 +138,8 @@ def _branch_fwd(xz, Di, N, cw, cb, xw, dtw, dtb, reverse, act):
         u = ops.causal_conv1d(xz[..., :Di], cw_, cb_, silu=True, reverse=reverse)
         ops.gemm_tn(u.view(M, Di), wx, out=dt, out2=bc, split=R)
     delta = ops.gemm_tn(dt, mixer._w(dtw, act, pad_cols=Rpad), k=R,
-                        bias=mixer._f32(dtb) if dtb is not None else None, act=L.ACT_SOFTPLUS, out_dtype=F32)
+                        bias=mixer._f32(dtb) if dtb is not None else None, act=L.ACT_SOFTPLUS,
+                        out_dtype=act if _train16(act, Di) else F32)
     return u, delta.view(B, Lq, Di), dt, bc.view(B, Lq, 2 * N)
 
 
@@ -195,7 +205,8 @@ class InnerFn(torch.autograd.Function):
             u_ = ops.causal_conv1d(xz[..., :Di], mixer._conv_w(cw_), mixer._f32(cb_) if cb_ is not None else None,
                                    silu=True, reverse=reverse)
             delta_ = ops.gemm_tn(dt_, mixer._w(dtw_, act, pad_cols=dt_.shape[1]), k=R,
-                                 bias=mixer._f32(dtb_) if dtb_ is not None else None, act=L.ACT_SOFTPLUS, out_dtype=F32)
+                                 bias=mixer._f32(dtb_) if dtb_ is not None else None, act=L.ACT_SOFTPLUS,
+                                 out_dtype=act if _train16(act, Di) else F32)
             return u_, delta_.view(B, Lq, Di)
 
         u, delta = recompute(cw, cb, dtw, dtb, dt, False)
@@ -219,8 +230,7 @@ class InnerFn(torch.autograd.Function):
         # du / ddelta of the scan (and the x_proj term of d(conv_out)) in the activation dtype when that is 16-bit - what the
         # reference's kernels hand back under autocast (:541-561, :590); the sums over the terms are still formed in fp32
         # (conv backward, sum_cast_colsum).  Needs the specialised backward-scan kernel (AUM_GRAD_16BIT=0: fp32 everywhere).
-        g16 = (act != F32 and Di % 128 == 0 and _GRAD_16BIT and "AUM_SCAN_BWD_GENERIC" not in os.environ
-               and "AUM_SCAN_BWD_NOSPEC" not in os.environ)
+        g16 = _train16(act, Di)
         gdt = dict(device=dev, dtype=act if g16 else F32)
         dA = torch.zeros((Di, N), **f32)
         dD_buf, dD_direct = _grad_buffer(D, (1, Di)) if D is not None else (None, False)

@@ -317,9 +317,11 @@ class ScanBwdDirection:
 
     def _struct(self):
         u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt = self.t
-        for t_ in (delta, A, bc, dA, dbc, ckpt):
+        for t_ in (A, bc, dA, dbc, ckpt):
             if t_.dtype != torch.float32:
-                raise L.AumError("scan bwd: delta/A/bc/dA/dbc/ckpt must be fp32")
+                raise L.AumError("scan bwd: A/bc/dA/dbc/ckpt must be fp32")
+        if delta.dtype not in (torch.float32, u.dtype):
+            raise L.AumError("scan bwd: delta must be fp32 or of u's dtype")
         if du.dtype != ddelta.dtype or du.dtype not in (torch.float32, u.dtype):
             raise L.AumError("scan bwd: du and ddelta must share a dtype: fp32 or u's")
         s = L.ScanBwdDir()
@@ -336,6 +338,7 @@ class ScanBwdDirection:
         s.ckpt = ckpt.data_ptr()
         s.ckpt_valid = int(bool(self.ckpt_valid))
         s.dgrad_dtype = L.dt(du.dtype)
+        s.delta_dtype = L.dt(delta.dtype)
         B, Lq, Dch = u.shape
         n = L.lib().aum_selective_scan_bwd_dbc_ws_floats(B, Lq, Dch)
         self._ws = torch.empty(n, device=u.device, dtype=torch.float32)   # per-warp dB|dC partials (kept alive here)

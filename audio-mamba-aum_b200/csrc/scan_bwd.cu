@@ -87,7 +87,7 @@ scan_bwd_kernel(const ScanBwdParams p) {
   }
   const float Dv = d.D ? __ldg(d.D + ch) : 0.f;
   const T* ub = reinterpret_cast<const T*>(d.u) + ch;
-  const float* db = d.delta + ch;
+  const float* db = reinterpret_cast<const float*>(d.delta) + ch;      // (fp32 only here: the entry point refuses a 16-bit delta)
   float* ck = d.ckpt + ((int64_t)b * scan_ck_count_max(L)) * SCAN_NS * p.Dch + ch;    // [b][chunk][n][D]
   auto token = [&](int s) { return rev ? (L - 1 - s) : s; };
 
@@ -339,6 +339,10 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
                 "aum_selective_scan_bwd: du / ddelta must be fp32 or of the call's 16-bit dtype");
     AUM_REQUIRE(p.ndirs == 1 || (s->dgrad_dtype != AUM_F32) == (p.g16 != 0), "aum_selective_scan_bwd: both directions must share dgrad_dtype");
     p.g16 = s->dgrad_dtype != AUM_F32 ? 1 : 0;
+    AUM_REQUIRE(s->delta_dtype == AUM_F32 || (s->delta_dtype == dtype && dtype != AUM_F32),
+                "aum_selective_scan_bwd: delta must be fp32 or of the call's 16-bit dtype");
+    AUM_REQUIRE(p.ndirs == 1 || (s->delta_dtype != AUM_F32) == (p.d16 != 0), "aum_selective_scan_bwd: both directions must share delta_dtype");
+    p.d16 = s->delta_dtype != AUM_F32 ? 1 : 0;
   }
   if (p.ndirs == 2) {
     const bool same_du = p.dir[0].du == p.dir[1].du, same_dd = p.dir[0].ddelta == p.dir[1].ddelta;
@@ -365,6 +369,7 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
   }
   const int fast = launch_scan_bwd_tma(p, dtype, st);     // TMA-streamed kernel when eligible
   if (fast > 0) return fast;
+  AUM_REQUIRE(fast == 0 || !p.d16, "aum_selective_scan_bwd: a 16-bit delta needs the TMA-streamed kernel (forward checkpoints, aligned rows)");
   AUM_REQUIRE(fast == 0 || !p.g16, "aum_selective_scan_bwd: 16-bit du / ddelta need the specialised TMA-streamed kernel "
                                    "(forward checkpoints, z + y_pre + dz + out_z, softplus_grad, separate du / ddelta per direction, D %% 128 == 0)");
   if (fast < 0) {

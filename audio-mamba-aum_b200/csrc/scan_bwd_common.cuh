@@ -10,7 +10,7 @@ constexpr int SB_WARPS = SB_CH / 32;   // warps per direction group
 
 struct ScanBwdDirDev {
   const void* u; int64_t ld_u;
-  const float* delta; int64_t ld_delta;
+  const void* delta; int64_t ld_delta;
   const float* A;
   const float* BC; int64_t ld_bc;
   const float* D;
@@ -28,6 +28,7 @@ struct ScanBwdParams {
   ScanBwdDirDev dir[2];
   int ndirs, shared_du;
   int g16;            // du / ddelta are of the activation dtype (specialised TMA kernel only), else fp32
+  int d16;            // delta is of the activation dtype (TMA kernels only), else fp32
   const void* z; int64_t ld_z;
   const void* ypre; int64_t ld_y;
   const void* dout; int64_t ld_dout;

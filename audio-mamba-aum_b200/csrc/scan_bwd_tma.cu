@@ -32,9 +32,10 @@ constexpr int BT_TT = 8;      // steps per checkpoint chunk (== SCAN_CK)
 static_assert(BT_TT == SCAN_CK, "chunk length must match the forward kernels' checkpoint interval");
 constexpr int BT_TMEM_COLS = BT_TT * SCAN_NS;   // 128 columns: 8 history slots x 16 states (power of two >= 32)
 
-template <typename T> struct BwdLayout {
+// TD: element type of delta (float or T)
+template <typename T, typename TD = float> struct BwdLayout {
   static constexpr int CK_BYTES = SCAN_NS * BT_CH * 4;             // checkpoint tile [n][ch]
-  static constexpr int D_BYTES = BT_TT * BT_CH * 4;                // delta tile
+  static constexpr int D_BYTES = BT_TT * BT_CH * (int)sizeof(TD);  // delta tile
   static constexpr int BC_BYTES = BT_TT * SCAN_ROW * 4;            // [B|C] rows
   static constexpr int A_BYTES = BT_TT * BT_CH * (int)sizeof(T);   // u, dout, z, y_pre tiles
   static constexpr int OFF_CK = 0, OFF_D = OFF_CK + CK_BYTES, OFF_BC = OFF_D + D_BYTES, OFF_U = OFF_BC + BC_BYTES;
@@ -152,9 +153,9 @@ __device__ __forceinline__ float sigmoid_ftz(float x) {
 // (uniform branches, predicate set-up, 64-bit pointer selects) and, worse for a latency-bound kernel, it cuts the step
 // into basic blocks the scheduler cannot interleave across.
 // TG: element type of du / ddelta (float, or T in the specialised instantiation when the caller asked for 16-bit gradients)
-template <typename T, bool SPEC, bool REV_, bool GATE_, typename TG>
+template <typename T, bool SPEC, bool REV_, bool GATE_, typename TG, typename TD>
 __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const ScanBwdParams& p, uint8_t* smem_raw) {
-  using BL = BwdLayout<T>;
+  using BL = BwdLayout<T, TD>;
   const uint32_t smem0 = (s_u32(smem_raw) + 127u) & ~127u;
   const uint32_t stages = smem0;
   const uint32_t redt = stages + 2 * BL::STAGE_BYTES;
@@ -251,7 +252,7 @@ __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const Scan
 
   // signed strides of one step forwards in time (tile rows / global rows run backwards for the reverse direction)
   const int s16 = rev ? -(BT_CH * (int)sizeof(T)) : (BT_CH * (int)sizeof(T));
-  const int s32 = rev ? -(BT_CH * 4) : (BT_CH * 4);
+  const int s32 = rev ? -(BT_CH * (int)sizeof(TD)) : (BT_CH * (int)sizeof(TD));     // delta rows
   const int sbc = rev ? -(SCAN_ROW * 4) : (SCAN_ROW * 4);
   const int rstep = rev ? -1 : 1;
   const int part = blockIdx.x * (BT_CH / 32) + (tig >> 5);     // this warp's slice of the dB|dC partial workspace
@@ -273,7 +274,7 @@ __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const Scan
 
     const int row_first = rev ? (BT_TT - 1) : 0;                 // tile row of step 0 of the chunk
     const uint32_t e16 = (uint32_t)(row_first * BT_CH + tig) * (uint32_t)sizeof(T);
-    const uint32_t e32 = (uint32_t)(row_first * BT_CH + tig) * 4u;
+    const uint32_t e32 = (uint32_t)(row_first * BT_CH + tig) * (uint32_t)sizeof(TD);
     const uint32_t t_u = st + BL::OFF_U + e16, t_d = st + BL::OFF_D + e32;
     const uint32_t t_bc = st + BL::OFF_BC + (uint32_t)row_first * SCAN_ROW * 4u;
 
@@ -288,20 +289,20 @@ __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const Scan
       if (SPEC && ns == BT_TT) {       // full chunk: every shared-memory / tensor-memory address is base + immediate
 #pragma unroll
         for (int j = 0; j < BT_TT - 1; ++j)
-          replay_step<true>(ldst<T>(t_u + (uint32_t)(j * s16)), ldsf(t_d + (uint32_t)(j * s32)), t_bc + (uint32_t)(j * sbc),
+          replay_step<true>(ldst<T>(t_u + (uint32_t)(j * s16)), ldst<TD>(t_d + (uint32_t)(j * s32)), t_bc + (uint32_t)(j * sbc),
                             hcol + (uint32_t)(j + 1) * SCAN_NS, h, a2);
-        replay_step<false>(ldst<T>(t_u + (uint32_t)((BT_TT - 1) * s16)), ldsf(t_d + (uint32_t)((BT_TT - 1) * s32)),
+        replay_step<false>(ldst<T>(t_u + (uint32_t)((BT_TT - 1) * s16)), ldst<TD>(t_d + (uint32_t)((BT_TT - 1) * s32)),
                            t_bc + (uint32_t)((BT_TT - 1) * sbc), 0u, h, a2);
       } else {
         uint32_t a_u = t_u, a_d = t_d, a_bc = t_bc, slot = hcol + SCAN_NS;
 #pragma unroll 1
         for (int j = 0; j < ns - 1; ++j) {
-          replay_step<true>(ldst<T>(a_u), ldsf(a_d), a_bc, slot, h, a2);
+          replay_step<true>(ldst<T>(a_u), ldst<TD>(a_d), a_bc, slot, h, a2);
           a_u += s16; a_d += s32; a_bc += sbc; slot += SCAN_NS;
         }
         // the chunk's last step: its result h_{ns-1} is not history (it is the next chunk's checkpoint) but the
         // reverse-time loop below starts with it, and from there on carries h_s over from the h_{s-1} it loads
-        replay_step<false>(ldst<T>(a_u), ldsf(a_d), a_bc, slot, h, a2);
+        replay_step<false>(ldst<T>(a_u), ldst<TD>(a_d), a_bc, slot, h, a2);
       }
 #pragma unroll
       for (int k = 0; k < SCAN_NS / 2; ++k) hcur[k] = h[k];
@@ -325,7 +326,7 @@ __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const Scan
 
       // one reverse-time step; every o* is the (compile-time, when unrolled) offset of the step from the a_* bases
       auto rstep_fn = [&](const uint32_t o16, const uint32_t o32, const uint32_t obc, const uint32_t oslot) {
-        const float u = ldst<T>(a_u + o16), dl = ldsf(a_d + o32), go = ldst<T>(a_g + o16) * scale;
+        const float u = ldst<T>(a_u + o16), dl = ldst<TD>(a_d + o32), go = ldst<T>(a_g + o16) * scale;
         const float zv = has_z ? ldst<T>(a_z + o16) : 0.f;
         const float sg = has_z ? sigmoid_ftz(zv) : 1.f;          // sigmoid(z); silu(z) = z sg
         const float sz = has_z ? zv * sg : 1.f;
@@ -394,7 +395,7 @@ __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const Scan
       if (SPEC && ns == BT_TT) {
         // full chunk: two steps per trip, the second at compile-time offsets from the same bases
         constexpr int S16 = REV_ ? -(BT_CH * (int)sizeof(T)) : (BT_CH * (int)sizeof(T));
-        constexpr int S32 = REV_ ? -(BT_CH * 4) : (BT_CH * 4);
+        constexpr int S32 = REV_ ? -(BT_CH * (int)sizeof(TD)) : (BT_CH * (int)sizeof(TD));
         constexpr int SBC = REV_ ? -(SCAN_ROW * 4) : (SCAN_ROW * 4);
 #pragma unroll 1
         for (int j = 0; j < BT_TT / 2; ++j) {
@@ -430,16 +431,21 @@ __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const Scan
   if (tig < 32) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "n"(BT_TMEM_COLS) : "memory");
 }
 
-template <typename T, bool SPEC, bool G16>
-__global__ void __launch_bounds__(BT_CH, 3)
+// G16: du / ddelta of the activation dtype; D16: delta of the activation dtype.  MINB: resident CTAs per SM the register
+// budget is set for: 3 (168 registers) in general; 4 (128 registers, 16 warps per SM, all 512 TMEM columns) where the stages
+// are small enough for four CTAs to fit in shared memory, i.e. with a 16-bit delta (56.5 KB per CTA) - the kernel is
+// latency-bound (issue slots 45 % used at 12 warps).  Measured: no gain (see launch_bt), so 3 is what ships.
+template <typename T, bool SPEC, bool G16, bool D16, int MINB>
+__global__ void __launch_bounds__(BT_CH, MINB)
 scan_bwd_tma_kernel(const __grid_constant__ ScanBwdMaps maps, const ScanBwdParams p) {
   extern __shared__ uint8_t smem_raw[];
   using TG = typename std::conditional<G16, T, float>::type;
+  using TD = typename std::conditional<D16, T, float>::type;
   if (SPEC) {
-    if (blockIdx.z == 0) scan_bwd_cta<T, true, false, true, TG>(maps, p, smem_raw);
-    else                 scan_bwd_cta<T, true, true, false, TG>(maps, p, smem_raw);
+    if (blockIdx.z == 0) scan_bwd_cta<T, true, false, true, TG, TD>(maps, p, smem_raw);
+    else                 scan_bwd_cta<T, true, true, false, TG, TD>(maps, p, smem_raw);
   } else {
-    scan_bwd_cta<T, false, false, false, float>(maps, p, smem_raw);
+    scan_bwd_cta<T, false, false, false, float, TD>(maps, p, smem_raw);
   }
 }
 
@@ -453,27 +459,40 @@ static bool bwd_spec_ok(const ScanBwdParams& p) {
   return off == 0;
 }
 
-template <typename T>
-static int launch_bt(const ScanBwdMaps& maps, const ScanBwdParams& p, cudaStream_t st) {
-  using BL = BwdLayout<T>;
-  constexpr bool T16 = !std::is_same<T, float>::value;
+template <typename T, bool SPEC, bool G16, bool D16, int MINB>
+static int launch_bt_v(const ScanBwdMaps& maps, const ScanBwdParams& p, cudaStream_t st) {
+  using BL = BwdLayout<T, typename std::conditional<D16, T, float>::type>;
   static PerDevice<bool> attr_set_dev;
   bool& attr_set = attr_set_dev.cur();
   if (!attr_set) {
-    cudaError_t e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T, false, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
-    if (e == cudaSuccess) e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T, true, false>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
-    if (e == cudaSuccess && T16) e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T, true, T16>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
+    cudaError_t e = cudaFuncSetAttribute(scan_bwd_tma_kernel<T, SPEC, G16, D16, MINB>, cudaFuncAttributeMaxDynamicSharedMemorySize, BL::SMEM_BYTES);
     if (e != cudaSuccess) { set_error("aum_selective_scan_bwd: cudaFuncSetAttribute(smem=%d): %s", BL::SMEM_BYTES, cudaGetErrorString(e)); return 2; }
     attr_set = true;
   }
   dim3 grid(ceil_div(p.Dch, BT_CH), p.batch, p.ndirs);
-  const bool spec = bwd_spec_ok(p);
-  if (p.g16) {
-    if (!spec || !T16) return -1;                         // (the entry point turns this into an error)
-    scan_bwd_tma_kernel<T, true, T16><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
-  } else if (spec) scan_bwd_tma_kernel<T, true, false><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
-  else             scan_bwd_tma_kernel<T, false, false><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
+  scan_bwd_tma_kernel<T, SPEC, G16, D16, MINB><<<grid, BT_CH, BL::SMEM_BYTES, st>>>(maps, p);
   return check_launch("aum_selective_scan_bwd(tma)");
+}
+
+template <typename T>
+static int launch_bt(const ScanBwdMaps& maps, const ScanBwdParams& p, cudaStream_t st) {
+  constexpr bool T16 = !std::is_same<T, float>::value;
+  const bool spec = bwd_spec_ok(p);
+  if ((p.g16 && !spec) || ((p.g16 || p.d16) && !T16)) return -1;       // (the entry point turns this into an error)
+  // 4 CTAs per SM (AUM_SCAN_BWD_4CTA=1) measured no faster than 3: 0.9575 vs 0.9544 ms per config-3 launch, 47.5 vs 47.7 ms
+  // per training step (noise) - the 56 bytes the 128-register cap spills cost what the fourth CTA's latency hiding returns
+  static int minb3 = -1;
+  if (minb3 < 0) minb3 = getenv("AUM_SCAN_BWD_4CTA") != nullptr ? 0 : 1;
+  if constexpr (T16) {
+    if (p.d16) {
+      if (spec && p.g16) return minb3 ? launch_bt_v<T, true, true, true, 3>(maps, p, st) : launch_bt_v<T, true, true, true, 4>(maps, p, st);
+      if (spec) return launch_bt_v<T, true, false, true, 3>(maps, p, st);
+      return launch_bt_v<T, false, false, true, 3>(maps, p, st);
+    }
+    if (spec && p.g16) return launch_bt_v<T, true, true, false, 3>(maps, p, st);
+  }
+  if (spec) return launch_bt_v<T, true, false, false, 3>(maps, p, st);
+  return launch_bt_v<T, false, false, false, 3>(maps, p, st);
 }
 
 int launch_scan_bwd_tma(const ScanBwdParams& p, int dtype, cudaStream_t st) {
@@ -487,7 +506,7 @@ int launch_scan_bwd_tma(const ScanBwdParams& p, int dtype, cudaStream_t st) {
   for (int g = 0; g < p.ndirs; ++g) {
     const ScanBwdDirDev& d = p.dir[g];
     if (!d.ckpt_valid || d.ld_bc != SCAN_ROW || !aligned16(d.BC) || !aligned16(d.ckpt)) return -1;
-    if (!ok_mat(d.u, d.ld_u, esz) || !ok_mat(d.delta, d.ld_delta, 4)) return -1;
+    if (!ok_mat(d.u, d.ld_u, esz) || !ok_mat(d.delta, d.ld_delta, p.d16 ? esz : 4)) return -1;
   }
   ScanBwdMaps maps;
   const int64_t rows = (int64_t)p.batch * p.L;
@@ -495,7 +514,7 @@ int launch_scan_bwd_tma(const ScanBwdParams& p, int dtype, cudaStream_t st) {
   for (int g = 0; g < 2; ++g) {
     const ScanBwdDirDev& d = p.dir[g < p.ndirs ? g : 0];
     if (int rc = tma_encode_2d(&maps.u[g], d.u, dtype, rows, p.Dch, d.ld_u, BT_TT, BT_CH, false, "aum_selective_scan_bwd(u)")) return rc;
-    if (int rc = tma_encode_2d(&maps.d[g], d.delta, AUM_F32, rows, p.Dch, d.ld_delta, BT_TT, BT_CH, false, "aum_selective_scan_bwd(delta)")) return rc;
+    if (int rc = tma_encode_2d(&maps.d[g], d.delta, p.d16 ? dtype : AUM_F32, rows, p.Dch, d.ld_delta, BT_TT, BT_CH, false, "aum_selective_scan_bwd(delta)")) return rc;
     if (int rc = tma_encode_2d(&maps.ck[g], d.ckpt, AUM_F32, ck_rows, p.Dch, p.Dch, SCAN_NS, BT_CH, false, "aum_selective_scan_bwd(ckpt)")) return rc;
   }
   if (int rc = tma_encode_2d(&maps.g, p.dout, dtype, rows, p.Dch, p.ld_dout, BT_TT, BT_CH, false, "aum_selective_scan_bwd(dout)")) return rc;

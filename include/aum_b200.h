@@ -186,7 +186,7 @@ AUM_API int aum_selective_scan_fwd(const aum_scan_dir_t* fwd, const aum_scan_dir
  * ------------------------------------------------------------------------------------------- */
 typedef struct aum_scan_bwd_dir {
   const void* u;      int64_t ld_u;      /* (batch*L, D) dtype */
-  const float* delta; int64_t ld_delta;  /* (batch*L, D) fp32, post-softplus */
+  const void* delta;  int64_t ld_delta;  /* (batch*L, D) post-softplus; fp32, or dtype when delta_dtype says so */
   const float* A;                        /* (D, N) */
   const float* BC;    int64_t ld_bc;     /* (batch*L, 2N) fp32 [B|C] */
   const float* D;                        /* (D) or NULL */
@@ -205,6 +205,8 @@ typedef struct aum_scan_bwd_dir {
                                             16-bit form needs the training configuration the TMA-streamed kernel is
                                             specialised for (checkpoints, z, y_pre, dz, out_z, softplus_grad, one du /
                                             ddelta pair per direction, D % 128 == 0); anything else is refused. */
+  int delta_dtype;                       /* dtype of delta: AUM_F32 (= 0) or the call's 16-bit `dtype` (delta as the forward
+                                            call read it, see aum_scan_dir_t.delta_dtype); TMA-streamed kernel only. */
 } aum_scan_bwd_dir_t;
 
 AUM_API int64_t aum_selective_scan_bwd_workspace_floats(int batch, int L, int D);

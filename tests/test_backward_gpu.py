@@ -541,6 +541,29 @@ def test_16bit_gradient_terms_equal_the_rounded_fp32_ones(dt):
     s1 = ops.sum_cast_colsum(dd_f.float().view(-1, D), dd_b.float().view(-1, D), dt, cs1)
     assert torch.equal(s0, s1)
     torch.testing.assert_close(cs0, cs1, rtol=1e-5, atol=1e-4)
+    # delta in the activation dtype as well (the training default): same results as fp32 arithmetic on the rounded delta
+    d16 = delta.to(dt)
+    outs = []
+    for dl_ in (d16, d16.float()):
+        ckd = {k: ops.scan_bwd_workspace(B, Lq, D, DEV) for k in "fb"}
+        yp = torch.empty((B, Lq, D), device=DEV, dtype=dt)
+        mkf2 = lambda Ax, k: ops.ScanDirection(u, dl_, Ax, bc[..., :N], bc[..., N:], Dv, ckpt=ckd[k])
+        o = ops.selective_scan(mkf2(A, "f"), mkf2(A_b, "b"), z, y_pre=yp)
+        gd = dt if dl_.dtype == dt else torch.float32
+        du = [torch.empty((B, Lq, D), device=DEV, dtype=gd) for _ in range(2)]
+        dd = [torch.empty((B, Lq, D), device=DEV, dtype=gd) for _ in range(2)]
+        dbc = torch.zeros((B, Lq, 2 * N), device=DEV)
+        dA = [torch.zeros((D, N), device=DEV) for _ in range(2)]
+        dD = torch.zeros((D,), device=DEV)
+        dz = torch.empty((B, Lq, D), device=DEV, dtype=dt); oz = torch.empty_like(dz)
+        mk = lambda Ax, i, k: ops.ScanBwdDirection(u, dl_, Ax, bc, Dv, du[i], dd[i], dA[i], dD, dbc, ckd[k], ckpt_valid=True)
+        ops.selective_scan_bwd(mk(A, 0, "f"), mk(A_b, 1, "b"), z, yp, G, dz, oz, softplus_grad=True)
+        outs.append((o, [t.to(dt) for t in du], [t.to(dt) for t in dd], dbc, dA[0], dz))
+    assert torch.equal(outs[0][0], outs[1][0]) and torch.equal(outs[0][5], outs[1][5])
+    for i in range(2):
+        assert torch.equal(outs[0][1][i], outs[1][1][i]) and torch.equal(outs[0][2][i], outs[1][2][i])
+    torch.testing.assert_close(outs[0][3], outs[1][3], rtol=1e-5, atol=1e-5)
+    torch.testing.assert_close(outs[0][4], outs[1][4], rtol=1e-5, atol=1e-5)
     # outside the specialised configuration the 16-bit form is refused, loudly
     du16 = torch.empty((B, Lq, D), device=DEV, dtype=dt)
     with pytest.raises(Exception):

@@ -153,6 +153,16 @@ def main():
                 ops.ScanBwdDirection(u, delta, A_b, bc, Dv, du2h, dd2h, dAb, dD, dbc, ckb, ckpt_valid=True),
                 z, ypre, dout, dz, oz, softplus_grad=True)
             report("biscan_bwd(training call, 16-bit du/ddelta)", timeit(bwh, iters=5, flush=flush))
+            d16 = delta.to(dt)
+            fw16 = lambda: ops.selective_scan(ops.ScanDirection(u, d16, A, bc[..., :N], bc[..., N:], Dv, ckpt=ckf),
+                                              ops.ScanDirection(u, d16, A_b, bc[..., :N], bc[..., N:], Dv, ckpt=ckb), z, out=out, y_pre=ypre)
+            report("biscan_fwd_train(ckpt+ypre, 16-bit delta)", timeit(fw16, flush=flush))
+            bwh16 = lambda: ops.selective_scan_bwd(
+                ops.ScanBwdDirection(u, d16, A, bc, Dv, duh, ddh, dA, dD, dbc, ckf, ckpt_valid=True),
+                ops.ScanBwdDirection(u, d16, A_b, bc, Dv, du2h, dd2h, dAb, dD, dbc, ckb, ckpt_valid=True),
+                z, ypre, dout, dz, oz, softplus_grad=True)
+            report("biscan_bwd(training call, 16-bit du/ddelta/delta: %s CTAs per SM)" % ("3" if not os.environ.get("AUM_SCAN_BWD_4CTA") else "4"),
+                   timeit(bwh16, iters=5, flush=flush))
             csum = torch.zeros(Di, **f32)
             report("sum_cast_colsum(fp32 in)", timeit(lambda: ops.sum_cast_colsum(dd.view(M, Di), dd2.view(M, Di), dt, csum), flush=flush),
                    bytes_=M * Di * (8 + s))

@@ -28,6 +28,25 @@ elif which == "conv_xproj":
     wx = rn(R + 2 * N, Di, sc=Di ** -0.5)
     dtb, bc = torch.empty(M, 48, device=dev, dtype=dt), torch.empty(M, 2 * N, **f32)
     fn = lambda: ops.conv_xproj(x[..., :Di], cw, cb, wx, R, dtb, bc)
+elif which == "scan_bwd":       # as the training step calls it: 16-bit delta / du / ddelta, per-direction outputs, softplus'
+    u, z, ypre, dout = (rn(B, Lq, Di) for _ in range(4))
+    delta = torch.nn.functional.softplus(rn(B, Lq, Di, dtype=torch.float32) - 2.0).to(dt)
+    bc = rn(B, Lq, 2 * N, dtype=torch.float32)
+    mkA = lambda: -torch.exp(torch.log(torch.arange(1, N + 1, device=dev, dtype=torch.float32)).repeat(Di, 1) + 0.1 * rn(Di, N, dtype=torch.float32))
+    A, A_b = mkA(), mkA()
+    Dv = torch.ones(Di, device=dev)
+    h = dict(device=dev, dtype=dt)
+    du, dd, du2, dd2 = (torch.empty((B, Lq, Di), **h) for _ in range(4))
+    dbc = torch.zeros((B, Lq, 2 * N), **f32)
+    dA, dAb, dD = torch.zeros((Di, N), **f32), torch.zeros((Di, N), **f32), torch.zeros(Di, **f32)
+    dz, oz, out = torch.empty_like(u), torch.empty_like(u), torch.empty_like(u)
+    ckf, ckb = ops.scan_bwd_workspace(B, Lq, Di, dev), ops.scan_bwd_workspace(B, Lq, Di, dev)
+    ops.selective_scan(ops.ScanDirection(u, delta, A, bc[..., :N], bc[..., N:], Dv, ckpt=ckf),
+                       ops.ScanDirection(u, delta, A_b, bc[..., :N], bc[..., N:], Dv, ckpt=ckb), z, out=out, y_pre=ypre)
+    fn = lambda: ops.selective_scan_bwd(
+        ops.ScanBwdDirection(u, delta, A, bc, Dv, du, dd, dA, dD, dbc, ckf, ckpt_valid=True),
+        ops.ScanBwdDirection(u, delta, A_b, bc, Dv, du2, dd2, dAb, dD, dbc, ckb, ckpt_valid=True),
+        z, ypre, dout, dz, oz, softplus_grad=True)
 else:
     raise SystemExit("unknown kernel " + which)
 for _ in range(4):
