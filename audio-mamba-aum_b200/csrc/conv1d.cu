@@ -598,11 +598,18 @@ template <typename T>
 static void launch_conv_bwd_stream(const void* x, int64_t ldx, const float* w, const float* bias, const void* g1, const void* g2,
                                    const void* g3, int64_t ldd, bool g16, void* dx, int64_t ld_dx, float* dw, float* dbias,
                                    int batch, int L, int D, int W, int silu, int reverse, cudaStream_t st) {
-  static int variant = -1;
-  if (variant < 0) { const char* e = getenv("AUM_CONV_BWD_VARIANT"); variant = (e && atoi(e) == 1) ? 1 : 0; }
-  if (g16) {
-    if constexpr (!std::is_same<T, float>::value)
-      launch_conv_bwd_stream_v<T, T, 2, 4>(x, ldx, w, bias, g1, g2, g3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st);
+  static int variant = -1, variant16 = -1;
+  if (variant < 0) {
+    const char* e = getenv("AUM_CONV_BWD_VARIANT"); variant = (e && atoi(e) == 1) ? 1 : 0;
+    const char* f = getenv("AUM_CONV_BWD_VARIANT16"); variant16 = f ? atoi(f) : 0;
+  }
+  if (g16) {      // 16-bit terms.  Deeper unrolling measured SLOWER at AuM-Base size: 0.086 ms (2 positions per trip, 32 warps per
+                  // SM) vs 0.104 (4 per trip) vs 0.123 (8 per trip, 24 warps) - AUM_CONV_BWD_VARIANT16=1 / 2 select those
+    if constexpr (!std::is_same<T, float>::value) {
+      if (variant16 == 0)      launch_conv_bwd_stream_v<T, T, 2, 4>(x, ldx, w, bias, g1, g2, g3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st);
+      else if (variant16 == 2) launch_conv_bwd_stream_v<T, T, 8, 3>(x, ldx, w, bias, g1, g2, g3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st);
+      else                     launch_conv_bwd_stream_v<T, T, 4, 4>(x, ldx, w, bias, g1, g2, g3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st);
+    }
     return;
   }
   if (variant == 1) launch_conv_bwd_stream_v<T, float, 4, 3>(x, ldx, w, bias, g1, g2, g3, ldd, dx, ld_dx, dw, dbias, batch, L, D, W, silu, reverse, st);

@@ -9,7 +9,7 @@
 namespace aum {
 
 constexpr int RO_ROWS = 64;      // rows per block
-constexpr int RO_THREADS = 256;  // 4 columns per thread -> 1024 columns per block
+constexpr int RO_THREADS = 256;  // 64 column quads x 4 row lanes -> 256 columns per block
 
 // 4 adjacent elements of a row as fp32
 template <typename TI> __device__ __forceinline__ float4 ld4(const TI* p);
@@ -24,35 +24,50 @@ template <> __device__ __forceinline__ float4 ld4<__nv_bfloat16>(const __nv_bflo
   return make_float4(__uint_as_float(v.x << 16), __uint_as_float(v.x & 0xffff0000u), __uint_as_float(v.y << 16), __uint_as_float(v.y & 0xffff0000u));
 }
 
+// Block = 64 column quads (256 columns) x 4 row lanes over RO_ROWS rows: a thread walks every fourth row of the block's row
+// range with all its loads of one trip in flight (8 rows x 1-2 inputs), the four row lanes' column sums meet in shared
+// memory, one atomic per column and block.  (The first version gave every thread 64 consecutive rows: 514 blocks = 28 warps
+// per SM, 43 % of HBM on 16-bit inputs.)
+constexpr int RO_LANES = 4;
 template <typename T, typename TI>
 __global__ void __launch_bounds__(RO_THREADS)
 sum_cast_colsum_kernel(const TI* __restrict__ a, const TI* __restrict__ b, int64_t ld, T* __restrict__ out, int64_t ldo,
                        float* __restrict__ colsum, int rows, int cols) {
-  const int c0 = (blockIdx.x * RO_THREADS + threadIdx.x) * 4;
-  if (c0 >= cols) return;
+  __shared__ float4 red[RO_LANES][RO_THREADS / RO_LANES];
+  const int cq = threadIdx.x % (RO_THREADS / RO_LANES), rl = threadIdx.x / (RO_THREADS / RO_LANES);
+  const int c0 = (blockIdx.x * (RO_THREADS / RO_LANES) + cq) * 4;
+  const bool ok = c0 < cols;
   const int r0 = blockIdx.y * RO_ROWS, r1 = min(rows, r0 + RO_ROWS);
   float4 s = make_float4(0.f, 0.f, 0.f, 0.f);
-#pragma unroll 4
-  for (int r = r0; r < r1; ++r) {
-    float4 v = ld4<TI>(a + (int64_t)r * ld + c0);
-    if (b != nullptr) {
-      const float4 w = ld4<TI>(b + (int64_t)r * ld + c0);
-      v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
-    }
-    s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
-    T* o = out + (int64_t)r * ldo + c0;
-    if constexpr (sizeof(T) == 4) {
-      *reinterpret_cast<float4*>(o) = v;
-    } else {
-      const T t0 = from_f<T>(v.x), t1 = from_f<T>(v.y), t2 = from_f<T>(v.z), t3 = from_f<T>(v.w);
-      uint2 pk;
-      pk.x = (uint32_t)(*reinterpret_cast<const unsigned short*>(&t0)) | ((uint32_t)(*reinterpret_cast<const unsigned short*>(&t1)) << 16);
-      pk.y = (uint32_t)(*reinterpret_cast<const unsigned short*>(&t2)) | ((uint32_t)(*reinterpret_cast<const unsigned short*>(&t3)) << 16);
-      *reinterpret_cast<uint2*>(o) = pk;
+  if (ok) {
+#pragma unroll 8
+    for (int r = r0 + rl; r < r1; r += RO_LANES) {
+      float4 v = ld4<TI>(a + (int64_t)r * ld + c0);
+      if (b != nullptr) {
+        const float4 w = ld4<TI>(b + (int64_t)r * ld + c0);
+        v.x += w.x; v.y += w.y; v.z += w.z; v.w += w.w;
+      }
+      s.x += v.x; s.y += v.y; s.z += v.z; s.w += v.w;
+      T* o = out + (int64_t)r * ldo + c0;
+      if constexpr (sizeof(T) == 4) {
+        *reinterpret_cast<float4*>(o) = v;
+      } else {
+        const T t0 = from_f<T>(v.x), t1 = from_f<T>(v.y), t2 = from_f<T>(v.z), t3 = from_f<T>(v.w);
+        uint2 pk;
+        pk.x = (uint32_t)(*reinterpret_cast<const unsigned short*>(&t0)) | ((uint32_t)(*reinterpret_cast<const unsigned short*>(&t1)) << 16);
+        pk.y = (uint32_t)(*reinterpret_cast<const unsigned short*>(&t2)) | ((uint32_t)(*reinterpret_cast<const unsigned short*>(&t3)) << 16);
+        *reinterpret_cast<uint2*>(o) = pk;
+      }
     }
   }
-  if (colsum != nullptr) {
-    atomicAdd(colsum + c0, s.x); atomicAdd(colsum + c0 + 1, s.y); atomicAdd(colsum + c0 + 2, s.z); atomicAdd(colsum + c0 + 3, s.w);
+  if (colsum != nullptr) {            // (uniform across the block)
+    red[rl][cq] = s;
+    __syncthreads();
+    if (rl == 0 && ok) {
+#pragma unroll
+      for (int k = 1; k < RO_LANES; ++k) { const float4 t = red[k][cq]; s.x += t.x; s.y += t.y; s.z += t.z; s.w += t.w; }
+      atomicAdd(colsum + c0, s.x); atomicAdd(colsum + c0 + 1, s.y); atomicAdd(colsum + c0 + 2, s.z); atomicAdd(colsum + c0 + 3, s.w);
+    }
   }
 }
 
@@ -62,7 +77,7 @@ namespace aum {
 template <typename TI>
 static void launch_sum_cast(const void* a, const void* b, int64_t ld, void* out, int64_t ld_out, int out_dtype, float* colsum,
                             int rows, int cols, cudaStream_t st) {
-  dim3 grid(ceil_div(cols, RO_THREADS * 4), ceil_div(rows, RO_ROWS));
+  dim3 grid(ceil_div(cols, (RO_THREADS / RO_LANES) * 4), ceil_div(rows, RO_ROWS));
   const TI *aa = reinterpret_cast<const TI*>(a), *bb = reinterpret_cast<const TI*>(b);
   switch (out_dtype) {
     case AUM_F32:  sum_cast_colsum_kernel<float, TI><<<grid, RO_THREADS, 0, st>>>(aa, bb, ld, (float*)out, ld_out, colsum, rows, cols); break;
