@@ -167,7 +167,13 @@ extern "C" int aum_add_rmsnorm_fwd(const void* x, int64_t ldx, int x_dtype,
 // ======================================================================================================
 namespace aum {
 
-constexpr int RNB_ROWS = 16;   // rows per warp
+// rows per warp.  16 at first: 129 blocks of 8 warps for the 16 416 rows of a config-3 launch - fewer blocks than SMs, ~7 warps
+// per SM, each walking its rows one after the other: latency-bound at 54 % of HBM.  4 rows per warp = 513 blocks; the
+// shared-memory reduction + 768 atomics per block stay small against 32 rows of traffic.  (AUM_RNB_ROWS at build time.)
+#ifndef AUM_RNB_ROWS
+#define AUM_RNB_ROWS 4
+#endif
+constexpr int RNB_ROWS = AUM_RNB_ROWS;
 
 template <typename TD, int NC>
 __global__ void __launch_bounds__(256)

@@ -146,7 +146,11 @@ def test_hot_kernels_do_not_spill():
     fwd = [e for e in entries("scan_fwd_tma.ptxas.log") if "scan_fwd_tma_kernel" in e[0]]
     assert fwd and all(st == 0 and ss == 0 and sl == 0 and regs <= 128 for _, st, ss, sl, regs in fwd), fwd
     bwd = [e for e in entries("scan_bwd_tma.ptxas.log") if "scan_bwd_tma_kernel" in e[0]]
-    assert bwd and all(st == 0 and ss == 0 and regs <= 168 for _, st, ss, sl, regs in bwd), bwd
+    # (the opt-in 4-CTAs-per-SM instantiation - last template argument 4, AUM_SCAN_BWD_4CTA - is capped at 128 registers and
+    # spills 56 bytes: measured no faster, not the shipped path)
+    shipped = [e for e in bwd if "Li4EEEv" not in e[0]]
+    assert shipped and len(shipped) < len(bwd), bwd
+    assert all(st == 0 and ss == 0 and regs <= 168 for _, st, ss, sl, regs in shipped), shipped
     gemm = [e for e in entries("gemm_tcgen05.ptxas.log") if "gemm_tcgen05" in e[0]]
     assert gemm and all(ss == 0 and sl == 0 for _, st, ss, sl, regs in gemm), gemm
 

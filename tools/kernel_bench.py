@@ -168,6 +168,10 @@ def main():
                    bytes_=M * Di * (8 + s))
             report("sum_cast_colsum(16-bit in)", timeit(lambda: ops.sum_cast_colsum(ddh.view(M, Di), dd2h.view(M, Di), dt, csum), flush=flush),
                    bytes_=M * Di * (4 + s))
+        dy_n, dro_n, r_n = rn(M, Dm), rn(M, Dm, dtype=torch.float32), rn(M, Dm, dtype=torch.float32)
+        rstd_n, w_n, dwt_n = torch.rand(M, device=dev) + 0.5, torch.ones(Dm, device=dev), torch.zeros(Dm, device=dev)
+        report("add_rmsnorm_bwd", timeit(lambda: ops.add_rmsnorm_bwd(dy_n, dro_n, r_n, rstd_n, w_n, dwt_n, want_dres_in=True), flush=flush),
+               bytes_=M * Dm * (2 * s + 12))
         x = rn(B, Lq, 2 * Di)
         w, b_ = rn(Di, 4, dtype=torch.float32), rn(Di, dtype=torch.float32)
         g32 = rn(B, Lq, Di, dtype=torch.float32)
