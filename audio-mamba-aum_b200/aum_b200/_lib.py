@@ -66,6 +66,7 @@ class ScanBwdDir(C.Structure):
         ("ckpt_valid", C.c_int),
         ("dgrad_dtype", C.c_int),
         ("delta_dtype", C.c_int),
+        ("dA_is_dAlog", C.c_int),
     ]
 
 

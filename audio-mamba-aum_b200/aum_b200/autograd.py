@@ -232,36 +232,45 @@ class InnerFn(torch.autograd.Function):
         # (conv backward, sum_cast_colsum).  Needs the specialised backward-scan kernel (AUM_GRAD_16BIT=0: fp32 everywhere).
         g16 = _train16(act, Di)
         gdt = dict(device=dev, dtype=act if g16 else F32)
-        dA = torch.zeros((Di, N), **f32)
+        # A = -exp(A_log) (module path): the kernel accumulates dA * A = dA_log straight into the A_log gradient when that is a
+        # view of the trainer's flat buffer - no zero fill, product and add per direction
+        def dA_target(a_param):
+            if cfg.a_is_log and _direct(a_param):
+                return a_param.grad.view(Di, N), True
+            return torch.zeros((Di, N), **f32), False
+        dA, dA_direct = dA_target(A)
         dD_buf, dD_direct = _grad_buffer(D, (1, Di)) if D is not None else (None, False)
         du = torch.empty((B, Lq, Di), **gdt)
         ddelta = torch.empty((B, Lq, Di), **gdt)
         dbc = torch.zeros((B, Lq, 2 * N), **f32)
         Dv = mixer._f32(D) if D is not None else None
         d_f = ops.ScanBwdDirection(u, delta, A_f, bc, Dv, du, ddelta, dA, dD_buf.view(Di) if dD_buf is not None else None,
-                                   dbc, ck_f, ckpt_valid=True)
+                                   dbc, ck_f, ckpt_valid=True, dA_is_dAlog=dA_direct)
         d_b = None
+        dAb_direct = False
         du_b = ddelta_b = None
         if cfg.mode == "v1":
             # each direction writes its own du / ddelta with plain stores (sharing one pair costs a 2 x 100 MB zero fill
             # plus atomic read-modify-writes from both directions at AuM-Base size); their sum is formed where they are
             # consumed anyway: in the conv backward's input and in the cast + column-sum pass of the dt_proj chain
             A_r = _A(A_b, cfg)
-            dA_b = torch.zeros((Di, N), **f32)
+            dA_b, dAb_direct = dA_target(A_b)
             du_b = torch.empty((B, Lq, Di), **gdt)
             ddelta_b = torch.empty((B, Lq, Di), **gdt)
             d_b = ops.ScanBwdDirection(u, delta, A_r, bc, Dv, du_b, ddelta_b, dA_b,
-                                       dD_buf.view(Di) if dD_buf is not None else None, dbc, ck_b, ckpt_valid=True)
+                                       dD_buf.view(Di) if dD_buf is not None else None, dbc, ck_b, ckpt_valid=True,
+                                       dA_is_dAlog=dAb_direct)
         elif cfg.mode == "v2":
             ub, deltab = recompute(cw_b, cb_b, dtw_b, dtb_b, dt_b, True)
             A_r = _A(A_b, cfg)
-            dA_b = torch.zeros((Di, N), **f32)
+            dA_b, dAb_direct = dA_target(A_b)
             dDb_buf, dDb_direct = _grad_buffer(D_b, (1, Di)) if D_b is not None else (None, False)
             du_b = torch.empty((B, Lq, Di), **gdt)
             ddelta_b = torch.empty((B, Lq, Di), **gdt)
             dbc_b = torch.zeros((B, Lq, 2 * N), **f32)
             d_b = ops.ScanBwdDirection(ub, deltab, A_r, bc_b, mixer._f32(D_b) if D_b is not None else None, du_b, ddelta_b,
-                                       dA_b, dDb_buf.view(Di) if dDb_buf is not None else None, dbc_b, ck_b, ckpt_valid=True)
+                                       dA_b, dDb_buf.view(Di) if dDb_buf is not None else None, dbc_b, ck_b, ckpt_valid=True,
+                                       dA_is_dAlog=dAb_direct)
         # ddelta comes back already multiplied by softplus'(pre) = 1 - exp(-delta): it IS d(pre-activation)
         ops.selective_scan_bwd(d_f, d_b, z, y_pre, dout_z, dz, out_z, out_scale=cfg.scale, softplus_grad=True)
 
@@ -320,13 +329,13 @@ class InnerFn(torch.autograd.Function):
         branch_bwd("", cw, cb, xw, dtw, dtb, u, dt, du, ddelta, dbc, False, dxz[..., :Di] if cfg.mode != "v2" else dxc,
                    du2_=du_b if cfg.mode == "v1" else None, ddelta2_=ddelta_b if cfg.mode == "v1" else None)
         # A = -exp(A_log)  =>  dA_log = dA * A
-        g["A"] = _deliver_value(A, dA * A_f if cfg.a_is_log else dA)
+        g["A"] = None if dA_direct else _deliver_value(A, dA * A_f if cfg.a_is_log else dA)
         g["D"] = _deliver(D, dD_buf, dD_direct) if D is not None else None
         if cfg.mode == "v1":
-            g["A_b"] = _deliver_value(A_b, dA_b * A_r if cfg.a_is_log else dA_b)
+            g["A_b"] = None if dAb_direct else _deliver_value(A_b, dA_b * A_r if cfg.a_is_log else dA_b)
         elif cfg.mode == "v2":
             branch_bwd("_b", cw_b, cb_b, xw_b, dtw_b, dtb_b, ub, dt_b, du_b, ddelta_b, dbc_b, True, dxc_b)
-            g["A_b"] = _deliver_value(A_b, dA_b * A_r if cfg.a_is_log else dA_b)
+            g["A_b"] = None if dAb_direct else _deliver_value(A_b, dA_b * A_r if cfg.a_is_log else dA_b)
             g["D_b"] = _deliver(D_b, dDb_buf, dDb_direct) if D_b is not None else None
             torch.add(dxc, dxc_b, out=dxz[..., :Di])
 

@@ -311,9 +311,10 @@ class ScanBwdDirection:
     16-bit dtype (training configuration only, see aum_b200.h) -, dA (D,16), dD (D), dbc (B,L,32) fp32 accumulated into;
     ckpt: fp32 workspace."""
 
-    def __init__(self, u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt, ckpt_valid=False):
+    def __init__(self, u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt, ckpt_valid=False, dA_is_dAlog=False):
         self.t = (u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt)
         self.ckpt_valid = ckpt_valid   # ckpt was filled by selective_scan(... ScanDirection(ckpt=...)) of the same call shape
+        self.dA_is_dAlog = dA_is_dAlog   # dA receives dA * A: the gradient w.r.t. A_log of A = -exp(A_log)
 
     def _struct(self):
         u, delta, A, bc, D, du, ddelta, dA, dD, dbc, ckpt = self.t
@@ -339,6 +340,7 @@ class ScanBwdDirection:
         s.ckpt_valid = int(bool(self.ckpt_valid))
         s.dgrad_dtype = L.dt(du.dtype)
         s.delta_dtype = L.dt(delta.dtype)
+        s.dA_is_dAlog = int(bool(self.dA_is_dAlog))
         B, Lq, Dch = u.shape
         n = L.lib().aum_selective_scan_bwd_dbc_ws_floats(B, Lq, Dch)
         self._ws = torch.empty(n, device=u.device, dtype=torch.float32)   # per-warp dB|dC partials (kept alive here)

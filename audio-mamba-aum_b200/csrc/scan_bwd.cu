@@ -274,7 +274,7 @@ scan_bwd_kernel(const ScanBwdParams p) {
   if (active) {
 #pragma unroll
     for (int k = 0; k < SCAN_NS / 2; ++k) {
-      float lo, hi; upk2(dA_acc[k], lo, hi);
+      float lo, hi; upk2(d.dA_log ? mul2(dA_acc[k], Av2[k]) : dA_acc[k], lo, hi);
       atomicAdd(d.dA + (int64_t)ch * SCAN_NS + 2 * k, lo);
       atomicAdd(d.dA + (int64_t)ch * SCAN_NS + 2 * k + 1, hi);
     }
@@ -334,7 +334,7 @@ extern "C" int aum_selective_scan_bwd(const aum_scan_bwd_dir_t* fwd, const aum_s
     d.u = s->u; d.ld_u = s->ld_u; d.delta = s->delta; d.ld_delta = s->ld_delta; d.A = s->A;
     d.BC = s->BC; d.ld_bc = s->ld_bc; d.D = s->D; d.du = (float*)s->du; d.ld_du = s->ld_du;
     d.ddelta = (float*)s->ddelta; d.ld_dd = s->ld_dd; d.dA = s->dA; d.dD = s->dD; d.dBC = s->dBC; d.ld_dbc = s->ld_dbc;
-    d.ckpt = s->ckpt; d.ckpt_valid = s->ckpt_valid; d.reverse = i; d.dbc_ws = s->dbc_ws;
+    d.ckpt = s->ckpt; d.ckpt_valid = s->ckpt_valid; d.reverse = i; d.dbc_ws = s->dbc_ws; d.dA_log = s->dA_is_dAlog ? 1 : 0;
     AUM_REQUIRE(s->dgrad_dtype == AUM_F32 || (s->dgrad_dtype == dtype && dtype != AUM_F32),
                 "aum_selective_scan_bwd: du / ddelta must be fp32 or of the call's 16-bit dtype");
     AUM_REQUIRE(p.ndirs == 1 || (s->dgrad_dtype != AUM_F32) == (p.g16 != 0), "aum_selective_scan_bwd: both directions must share dgrad_dtype");

@@ -22,6 +22,7 @@ struct ScanBwdDirDev {
   float* ckpt;
   int ckpt_valid;
   int reverse;
+  int dA_log;         // accumulate dA * A (the gradient w.r.t. A_log) instead of dA
 };
 
 struct ScanBwdParams {

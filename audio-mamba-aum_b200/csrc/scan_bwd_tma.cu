@@ -420,7 +420,9 @@ __device__ __forceinline__ void scan_bwd_cta(const ScanBwdMaps& maps, const Scan
   if (active) {
 #pragma unroll
     for (int k = 0; k < SCAN_NS / 2; ++k) {
-      float lo, hi; upk2(dA_acc[k], lo, hi);
+      // (a2 = A log2(e): dA * A = dA * a2 * ln 2)
+      const f32x2 ln2 = pk2(0.6931471805599453f, 0.6931471805599453f);
+      float lo, hi; upk2(d.dA_log ? mul2(mul2(dA_acc[k], a2[k]), ln2) : dA_acc[k], lo, hi);
       atomicAdd(d.dA + (int64_t)ch * SCAN_NS + 2 * k, lo);
       atomicAdd(d.dA + (int64_t)ch * SCAN_NS + 2 * k + 1, hi);
     }

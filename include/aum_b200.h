@@ -207,6 +207,8 @@ typedef struct aum_scan_bwd_dir {
                                             ddelta pair per direction, D % 128 == 0); anything else is refused. */
   int delta_dtype;                       /* dtype of delta: AUM_F32 (= 0) or the call's 16-bit `dtype` (delta as the forward
                                             call read it, see aum_scan_dir_t.delta_dtype); TMA-streamed kernel only. */
+  int dA_is_dAlog;                       /* 1: dA += dA * A, the gradient w.r.t. A_log of A = -exp(A_log)
+                                            (mamba_simple.py:193,197): lets the caller point dA at the A_log gradient itself */
 } aum_scan_bwd_dir_t;
 
 AUM_API int64_t aum_selective_scan_bwd_workspace_floats(int batch, int L, int D);

@@ -437,13 +437,18 @@ def test_functional_selective_scan_fn_and_conv_backward_vs_oracle_autograd():
     _close(bd.grad, br.grad, 1e-4, 1e-5, "conv db")
 
 
-def test_direct_gradient_accumulation_into_a_flat_buffer():
+@pytest.mark.parametrize("embed,act,bt,generic", [(192, torch.bfloat16, "v1", False), (96, torch.float32, "v2", False),
+                                                  (64, torch.float32, "v1", True)])
+def test_direct_gradient_accumulation_into_a_flat_buffer(embed, act, bt, generic, monkeypatch):
     """FlatGradReducer marks parameters for in-place gradient accumulation: the kernels write straight into the flat
-    buffer (no temporaries, no AccumulateGrad) and the result equals the autograd-delivered gradients."""
+    buffer (no temporaries, no AccumulateGrad; dA * A lands in the A_log gradient from inside the backward scan -
+    specialised, general and generic kernel) and the result equals the autograd-delivered gradients."""
     from aum_b200.audio_mamba import AudioMamba
     from aum_b200.dist import FlatGradReducer
+    if generic:
+        monkeypatch.setenv("AUM_SCAN_BWD_GENERIC", "1")
     torch.manual_seed(11)
-    kw = dict(embed_dim=192, depth=2, num_classes=35, spectrogram_size=(128, 128), bimamba_type="v1", act_dtype=torch.bfloat16)
+    kw = dict(embed_dim=embed, depth=2, num_classes=35, spectrogram_size=(128, 128), bimamba_type=bt, act_dtype=act)
     a = AudioMamba(**kw).to(DEV)
     b = AudioMamba(**kw).to(DEV)
     b.load_state_dict(a.state_dict())
@@ -456,7 +461,7 @@ def test_direct_gradient_accumulation_into_a_flat_buffer():
     for (n, pa), (_, pb) in zip(a.named_parameters(), b.named_parameters()):
         assert pb.grad.data_ptr() >= red.flat.data_ptr() and pb.grad.data_ptr() < red.flat.data_ptr() + red.flat.numel() * 4, n
         scale = max(pa.grad.abs().max().item(), 1e-9)
-        assert (pa.grad - pb.grad).abs().max().item() <= 2e-2 * scale, (n, scale)
+        assert (pa.grad - pb.grad).abs().max().item() <= (2e-2 if act != torch.float32 else 1e-4) * scale, (n, scale)
 
 
 @pytest.mark.parametrize("dt", [torch.float32, torch.bfloat16, torch.float16])
