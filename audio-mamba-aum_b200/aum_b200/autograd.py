@@ -71,6 +71,10 @@ def _wgrad(dy2d, x2d, p):
     if p is None or not p.requires_grad:
         return None
     buf, direct = _grad_buffer(p, (dy2d.shape[1], x2d.shape[1]))
+    if direct and mixer._WGRAD_SIDE:
+        # accumulates into the trainer's flat buffer, which nothing reads before FlatGradReducer joins: second stream
+        mixer.side_work.launch(lambda: ops.gemm_wgrad(dy2d, x2d, buf), dy2d, x2d, buf)
+        return None
     ops.gemm_wgrad(dy2d, x2d, buf)
     return _deliver(p, buf, direct)
 

@@ -100,6 +100,8 @@ class FlatGradReducer:
         kernels already enqueued on the current stream)."""
         if k_end <= self._launched:
             return
+        from . import mixer
+        mixer.side_work.join()          # weight-gradient GEMMs launched on the side stream accumulate into this buffer
         lo, hi = self.bounds[self._launched], self.bounds[k_end]
         self._launched = k_end
         if not self._active() or hi <= lo:
@@ -123,6 +125,8 @@ class FlatGradReducer:
         """Launch what has not been launched yet, wait for every piece (the current stream waits; the host does not
         block on NCCL), and return the averaged flat gradient."""
         self._launch_upto(self.n_chunks)
+        from . import mixer
+        mixer.side_work.join()
         world = dist.get_world_size() if self._active() else 1
         for w, sl in self._works:
             w.wait()

@@ -59,6 +59,51 @@ def generation() -> int:
     return _GENERATION
 
 
+# Weight-gradient GEMMs on a side stream (training with a flat gradient buffer, aum_b200.dist.FlatGradReducer): dW = dY^T X
+# is off the critical path of backward - nothing reads it before the all-reduce / optimiser - so it is launched on a second
+# stream, ordered after the kernels that produce its operands, and fills SMs the main stream's kernels leave idle (the
+# backward scan's 1.73-wave tail, the small kernels of the dt_proj chain).  The operands are kept alive until the join;
+# FlatGradReducer joins before it launches an all-reduce piece and before the optimiser step.  AUM_WGRAD_SIDE=0 turns it off.
+_WGRAD_SIDE = os.environ.get("AUM_WGRAD_SIDE", "1") == "1"
+
+
+class _SideWork:
+    def __init__(self):
+        self.streams = {}
+        self.pending = []
+        self.dirty = set()
+        self.cb_queued = False
+
+    def launch(self, fn, *keep):
+        dev = keep[0].device
+        cur = torch.cuda.current_stream(dev)
+        side = self.streams.get(dev)
+        if side is None:
+            side = self.streams[dev] = torch.cuda.Stream(device=dev)
+        side.wait_stream(cur)                  # the operands are final
+        with torch.cuda.stream(side):
+            fn()
+        self.pending.extend(keep)              # (their memory must not be handed out again before the join)
+        self.dirty.add(dev)
+        if not self.cb_queued:                 # whoever reads .grad after loss.backward() returns sees finished gradients
+            from torch.autograd import Variable
+            Variable._execution_engine.queue_callback(self._backward_done)
+            self.cb_queued = True
+
+    def _backward_done(self):
+        self.cb_queued = False
+        self.join()
+
+    def join(self):
+        for dev in self.dirty:
+            torch.cuda.current_stream(dev).wait_stream(self.streams[dev])
+        self.dirty.clear()
+        self.pending.clear()
+
+
+side_work = _SideWork()
+
+
 class _DerivedCache:
     """Derived, read-only views of parameters (16-bit copies, zero-padded copies, A = -exp(A_log)).
     Entries are revalidated against the parameter's version counter and storage pointer, so in-place
