@@ -300,18 +300,21 @@ def test_mamba_module_backward_with_generic_scan_kernel(monkeypatch):
     test_mamba_module_backward_vs_oracle_autograd("v2", {"if_devide_out": True})
 
 
+@pytest.mark.parametrize("bt", ["v1", "v2", "none"])
 @pytest.mark.parametrize("dt,budget", [(torch.float16, 2e-2), (torch.bfloat16, 8e-2)])
-def test_mamba_module_backward_16bit_budget(dt, budget):
+def test_mamba_module_backward_16bit_budget(dt, budget, bt):
+    """16-bit training tiers (d_inner = 256: the specialised backward scan with 16-bit delta / du / ddelta, the 16-bit
+    gradient terms of the conv backward - three for Fo-Bi, two for Bi-Bi and Fo-Fo) against fp32 autograd through the oracle."""
     from mamba_ssm.modules.mamba_simple import Mamba
     Dm, Lq, B = 128, 65, 2
-    p = O.make_mamba_params(Dm, bimamba_type="v1", seed=31, perturb_A=0.1)
+    p = O.make_mamba_params(Dm, bimamba_type=bt, seed=31, perturb_A=0.1)
     g = gen(7)
     hidden = rnd((B, Lq, Dm), g)
     G = rnd((B, Lq, Dm), g)
     ref_p = {k: v.clone().requires_grad_() for k, v in p.items()}
     h_ref = hidden.clone().requires_grad_()
-    (O.mamba_forward_oracle(ref_p, h_ref, "v1") * G).sum().backward()
-    m = Mamba(Dm, bimamba_type="v1").to(DEV)
+    (O.mamba_forward_oracle(ref_p, h_ref, bt) * G).sum().backward()
+    m = Mamba(Dm, bimamba_type=bt).to(DEV)
     m.load_state_dict(p)
     h = hidden.to(DEV).to(dt).requires_grad_()
     (m(h).float() * G.to(DEV)).sum().backward()
