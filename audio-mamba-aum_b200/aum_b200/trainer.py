@@ -25,7 +25,8 @@ class TrainStep:
     into the captured buffers, the returned loss is the captured tensor (overwritten by the next call)."""
 
     def __init__(self, model, lr: float = 1e-5, betas=(0.95, 0.999), eps: float = 1e-8, weight_decay: float = 5e-7,
-                 n_chunks: int = 3, loss: str = "bce", shadow16: bool = True, cuda_graph: bool = False):
+                 n_chunks: int = 3, loss: str = "bce", shadow16: bool = True, cuda_graph: bool = False,
+                 loss_scale: float = 1.0):
         self.model = model
         params, chunk_after, self.hook_layers = model.grad_ready_order(n_chunks)
         self.reducer = FlatGradReducer(params, chunk_after=chunk_after)
@@ -37,6 +38,12 @@ class TrainStep:
         self.timing: Optional[List] = None     # when a list: (start, end) CUDA events around the exposed part of the all-reduce
         self.cuda_graph = cuda_graph
         self._graph = None                     # (key, CUDAGraph, static x, static labels, static loss)
+        # fp16 activations: the reference's recipe relies on accelerate's GradScaler (--mixed_precision=fp16); here a static
+        # scale - the loss is multiplied by it before backward (so the 16-bit gradient terms stay in fp16's range), the
+        # fused Adam divides it out again, and an eagerly launched step whose gradients overflowed is skipped (p, m, v and
+        # the step count untouched; `last_step_applied` tells the caller to lower the scale).  bf16 / fp32: leave it at 1.
+        self.loss_scale = float(loss_scale)
+        self.last_step_applied = True
 
     def loss_fn(self, logits, labels):
         if self.loss_name == "bce":
@@ -46,7 +53,8 @@ class TrainStep:
     def _eager(self, x: torch.Tensor, labels: torch.Tensor) -> torch.Tensor:
         self.reducer.zero()                                   # optimizer.zero_grad()   (traintest.py:167)
         loss = self.loss_fn(self.model(x), labels)            # (:144-152)
-        loss.backward()                                       # accelerator.backward: chunks launch from hooks (:168)
+        scaled = self.loss_scale != 1.0
+        (loss * self.loss_scale if scaled else loss).backward()   # accelerator.backward: chunks launch from hooks (:168)
         if self.timing is not None:
             e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
             e0.record()
@@ -54,7 +62,9 @@ class TrainStep:
         if self.timing is not None:
             e1.record()
             self.timing.append((e0, e1))
-        self.opt.step()                                       # (:169)
+        # (the non-finite check is a host read: not inside a captured graph)
+        check = scaled and not torch.cuda.is_current_stream_capturing()
+        self.last_step_applied = self.opt.step(grad_scale=1.0 / self.loss_scale, skip_nonfinite=check)      # (:169)
         return loss
 
     def _capture(self, x: torch.Tensor, labels: torch.Tensor, key):

@@ -135,3 +135,28 @@ def test_graphed_training_step_equals_the_eager_one(act):
     with torch.no_grad():
         oa, ob = ma(x), mb(x)
     torch.testing.assert_close(ob, oa, rtol=2e-2, atol=2e-2)
+
+
+def test_train_step_static_loss_scale_is_divided_out_and_overflow_skips_the_step():
+    """fp16 recipe (the reference trains with --mixed_precision=fp16 and accelerate's GradScaler): TrainStep(loss_scale=s)
+    scales the loss before backward and the fused Adam divides it out - same update as the unscaled step where nothing
+    over- or underflows (fp32 activations here, so the comparison is exact up to rounding) - and an overflowing scale
+    leaves parameters, moments and the step count untouched."""
+    from aum_b200.audio_mamba import AudioMamba
+    from aum_b200.trainer import TrainStep
+    kw = dict(embed_dim=64, depth=2, num_classes=11, bimamba_type="v1", spectrogram_size=(32, 64), act_dtype=torch.float32)
+    torch.manual_seed(31)
+    ma, mb, mc = (AudioMamba(**kw).to(DEV) for _ in range(3))
+    mb.load_state_dict(ma.state_dict()); mc.load_state_dict(ma.state_dict())
+    ta, tb, tc = TrainStep(ma, lr=1e-3), TrainStep(mb, lr=1e-3, loss_scale=1024.0), TrainStep(mc, lr=1e-3, loss_scale=float("inf"))
+    g = torch.Generator().manual_seed(32)
+    x = torch.randn(3, 64, 32, generator=g).to(DEV)
+    y = (torch.rand(3, 11, generator=g) > 0.7).float().to(DEV)
+    la, lb = ta(x, y), tb(x, y)
+    torch.testing.assert_close(lb.detach(), la.detach(), rtol=1e-6, atol=1e-7)          # the returned loss is the unscaled one
+    torch.testing.assert_close(tb.opt.flat_p, ta.opt.flat_p, rtol=0, atol=2e-4)
+    assert tb.last_step_applied and tb.opt.t == 1
+    before = tc.opt.flat_p.clone()
+    tc(x, y)
+    assert tc.last_step_applied is False and tc.opt.t == 0 and int(tc.opt.step_dev) == 0
+    assert torch.equal(tc.opt.flat_p, before) and float(tc.opt.m.abs().sum()) == 0.0
