@@ -112,7 +112,11 @@ __device__ __forceinline__ void tc_epilogue_tile(const EpiParams& ep, const CUte
             if (colb >= ep.act_col0) {              // whole chunk inside the activated column range
               if (act == AUM_ACT_SILU) {
 #pragma unroll
-                for (int i = 0; i < 32; ++i) r[i] = __float_as_uint(silu_ftz(__uint_as_float(r[i])));
+                for (int i = 0; i < 32; i += 2) {
+                  float v0, v1;
+                  upk2(silu_ftz2(pk2(__uint_as_float(r[i]), __uint_as_float(r[i + 1]))), v0, v1);
+                  r[i] = __float_as_uint(v0); r[i + 1] = __float_as_uint(v1);
+                }
               } else {
 #pragma unroll
                 for (int i = 0; i < 32; i += 2) {
