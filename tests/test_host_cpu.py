@@ -35,6 +35,32 @@ def test_derived_weight_cache_follows_parameter_versions():
     assert torch.equal(neg, -torch.ones(4, 16))
 
 
+def test_shadow_weight_policy_and_16bit_training_switch():
+    """Host logic of two round-2 additions: (1) mixer._w / _w2d hand out the optimiser-maintained 16-bit shadow of a parameter
+    only while its version counter has not moved since the shadow was written and the dtype matches; (2) the 16-bit
+    delta / gradient-term policy of the training path needs 16-bit activations, 128-channel CTAs and no generic-kernel
+    override."""
+    from aum_b200 import autograd as AG, mixer
+    w = torch.nn.Parameter(torch.randn(8, 16))
+    assert mixer.shadow16(w, torch.bfloat16) is None
+    sh = w.detach().to(torch.bfloat16)
+    w._aum_w16, w._aum_w16_ver = sh, w._version
+    assert mixer._w(w, torch.bfloat16) is sh and mixer.shadow16(w, torch.float16) is None
+    assert mixer._w2d(w, torch.bfloat16).data_ptr() == sh.data_ptr()
+    assert mixer._w(w, torch.bfloat16, pad_cols=24).shape == (8, 24)          # padded copies never come from the shadow
+    with torch.no_grad():
+        w.mul_(2.0)                                                           # somebody edits the parameter in place
+    fresh = mixer._w(w, torch.bfloat16)
+    assert fresh is not sh and torch.equal(fresh, w.detach().to(torch.bfloat16))
+    assert AG._train16(torch.bfloat16, 1536) and AG._train16(torch.float16, 768)
+    assert not AG._train16(torch.float32, 1536) and not AG._train16(torch.bfloat16, 192)
+    os.environ["AUM_SCAN_BWD_GENERIC"] = "1"
+    try:
+        assert not AG._train16(torch.bfloat16, 1536)
+    finally:
+        del os.environ["AUM_SCAN_BWD_GENERIC"]
+
+
 def test_flat_gradient_buffer_layout():
     """Every tensor of the flat gradient buffer starts on a 32-byte boundary, gradients alias it, zero() clears it."""
     from aum_b200 import dist as D
